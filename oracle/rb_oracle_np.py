@@ -1,0 +1,257 @@
+"""Second, independent CPU restatement (numpy, matrix form, vectorised over the batch).
+
+ORACLE = test infrastructure, NOT product code.  PARITY UNPINNED (see oracle/rb_oracle.h).
+
+Where oracle/rb_oracle.c follows the reference's *shape* (quaternion isometries, (m, c, I_c)
+inertias, one state at a time), this file restates the same algorithm in the generalised form
+SURVEY.md section 7 step 1 asks for: 3x3 rotation matrices, 10-parameter spatial inertias
+(m, h = m c, I_o), any serial chain length.  tests/test_oracle.py proves the two equal to <= 1e-12,
+which is evidence (1) of SURVEY.md section 8c.  An mpmath evaluation of the same formulas
+(`rnea_mp`) bounds the absolute rounding error of both.
+
+Conventions (all citations relative to the reference checkout):
+  X_i(q) = parent_i o Rot(z, q_i) is the pose of frame i in frame i-1 (joint.rs:36-38), R_i = R_p Rz(q).
+  motion  parent->child: rot' = R^T rot, lin' = R^T (lin - t x rot)          (spatial.rs:110-116)
+  force   child->parent: lin' = R lin,  rot' = R rot + t x (R lin)           (spatial.rs:242-248 on X^-1)
+  I a: lin = m a.lin - h x a.rot ; rot = I_o a.rot + h x a.lin               (inertia.rs:107-117)
+  v x* f: lin = w x f.lin ; rot = w x f.rot + v.lin x f.lin                  (spatial.rs:129-134)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GRAVITY = 9.81          # multibody.rs:118, base acceleration +z
+
+
+def _rx(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+
+
+def _ry(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def _rz(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+
+
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+
+class ChainNP:
+    """Flattened serial chain: R_p [n,3,3], t_p [n,3], m [n], h [n,3], I_o [n,3,3]."""
+
+    def __init__(self, model):
+        n = model.n
+        self.n = n
+        self.Rp = np.stack([_rz(y) @ _ry(p) @ _rx(r) for r, p, y in model.rpy])   # joint.rs:59-63
+        self.tp = np.array(model.xyz, dtype=np.float64)
+        self.m = np.array(model.mass, dtype=np.float64)
+        c = np.array(model.com, dtype=np.float64)
+        self.h = self.m[:, None] * c
+        Io = []
+        for i in range(n):
+            s = model.inertia6[i]
+            Ic = np.array([[s[0], s[1], s[2]], [s[1], s[3], s[4]], [s[2], s[4], s[5]]])
+            C = _skew(c[i])
+            Io.append(Ic + self.m[i] * C @ C.T)                                   # inertia.rs:31-32
+        self.Io = np.stack(Io)
+
+    # -- helpers, all batched over leading axis B
+    def _R(self, i, q):
+        """R_i(q) = R_p Rz(q): [B,3,3]"""
+        c, s = np.cos(q), np.sin(q)
+        Rz = np.zeros(q.shape + (3, 3))
+        Rz[..., 0, 0] = c; Rz[..., 0, 1] = -s; Rz[..., 1, 0] = s; Rz[..., 1, 1] = c; Rz[..., 2, 2] = 1.0
+        return self.Rp[i] @ Rz
+
+    def _Imul(self, i, lin, rot):
+        f_lin = self.m[i] * lin - np.cross(self.h[i], rot)
+        f_rot = rot @ self.Io[i].T + np.cross(self.h[i], lin)
+        return f_lin, f_rot
+
+    def rnea(self, q, dq, ddq):
+        """q, dq, ddq: [B, n] -> tau [B, n]  (multibody.rs:111-153)"""
+        q, dq, ddq = (np.atleast_2d(np.asarray(x, dtype=np.float64)) for x in (q, dq, ddq))
+        B, n = q.shape
+        R = [self._R(i, q[:, i]) for i in range(n)]
+        v_lin = np.zeros((B, 3)); v_rot = np.zeros((B, 3))
+        a_lin = np.zeros((B, 3)); a_lin[:, 2] = GRAVITY
+        a_rot = np.zeros((B, 3))
+        f_lin, f_rot = [], []
+        for i in range(n):
+            Rt = np.swapaxes(R[i], 1, 2)
+            t = self.tp[i]
+            v_lin = np.einsum("bij,bj->bi", Rt, v_lin - np.cross(t, v_rot))
+            v_rot = np.einsum("bij,bj->bi", Rt, v_rot)
+            v_rot[:, 2] += dq[:, i]
+            a_lin = np.einsum("bij,bj->bi", Rt, a_lin - np.cross(t, a_rot))
+            a_rot = np.einsum("bij,bj->bi", Rt, a_rot)
+            a_rot[:, 2] += ddq[:, i]
+            a_lin[:, 0] += v_lin[:, 1] * dq[:, i]
+            a_lin[:, 1] += -v_lin[:, 0] * dq[:, i]
+            a_rot[:, 0] += v_rot[:, 1] * dq[:, i]
+            a_rot[:, 1] += -v_rot[:, 0] * dq[:, i]
+            Ia_l, Ia_r = self._Imul(i, a_lin, a_rot)
+            Iv_l, Iv_r = self._Imul(i, v_lin, v_rot)
+            f_lin.append(Ia_l + np.cross(v_rot, Iv_l))
+            f_rot.append(Ia_r + np.cross(v_rot, Iv_r) + np.cross(v_lin, Iv_l))
+        tau = np.zeros((B, n))
+        for i in range(n - 1, -1, -1):
+            tau[:, i] = f_rot[i][:, 2]
+            if i > 0:
+                Rl = np.einsum("bij,bj->bi", R[i], f_lin[i])
+                f_lin[i - 1] = f_lin[i - 1] + Rl
+                f_rot[i - 1] = f_rot[i - 1] + np.einsum("bij,bj->bi", R[i], f_rot[i]) + np.cross(self.tp[i], Rl)
+        return tau
+
+    def crba(self, q, symmetric=False):
+        """q [B,n] -> H [B,n,n]; reference convention: diagonal + strict upper, lower = 0 (multibody.rs:155-174)."""
+        q = np.atleast_2d(np.asarray(q, dtype=np.float64))
+        B, n = q.shape
+        R = [self._R(i, q[:, i]) for i in range(n)]
+        H = np.zeros((B, n, n))
+        m = np.full(B, self.m[n - 1]); h = np.tile(self.h[n - 1], (B, 1)); Io = np.tile(self.Io[n - 1], (B, 1, 1))
+        for i in range(n - 1, -1, -1):
+            H[:, i, i] = Io[:, 2, 2]
+            F_lin = -np.cross(h, np.array([0.0, 0.0, 1.0]))     # I * S_z
+            F_rot = Io[:, :, 2].copy()
+            for j in range(i - 1, -1, -1):
+                Rl = np.einsum("bij,bj->bi", R[j + 1], F_lin)
+                F_rot = np.einsum("bij,bj->bi", R[j + 1], F_rot) + np.cross(self.tp[j + 1], Rl)
+                F_lin = Rl
+                H[:, j, i] = F_rot[:, 2]
+            if i > 0:
+                # composite inertia into the parent frame, 10-parameter form:
+                # h' = R h + m t ;  I_o' = R I_o R^T - [t]x[Rh]x - [Rh]x[t]x - m [t]x[t]x
+                t = self.tp[i]
+                Rh = np.einsum("bij,bj->bi", R[i], h)
+                RIR = R[i] @ Io @ np.swapaxes(R[i], 1, 2)
+                T = _skew(t)
+                S = np.zeros((B, 3, 3))
+                S[:, 0, 1] = -Rh[:, 2]; S[:, 0, 2] = Rh[:, 1]; S[:, 1, 0] = Rh[:, 2]
+                S[:, 1, 2] = -Rh[:, 0]; S[:, 2, 0] = -Rh[:, 1]; S[:, 2, 1] = Rh[:, 0]
+                Io = RIR - T @ S - S @ T - m[:, None, None] * (T @ T) + self.Io[i - 1]
+                h = Rh + m[:, None] * t + self.h[i - 1]
+                m = m + self.m[i - 1]
+        if symmetric:
+            iu = np.triu_indices(n, 1)
+            H[:, iu[1], iu[0]] = H[:, iu[0], iu[1]]
+        else:
+            il = np.tril_indices(n, -1)
+            H[:, il[0], il[1]] = 0.0
+        return H
+
+    def forward_dynamics(self, q, dq, tau):
+        """qdd = chol_solve(sym(crba(q)), tau - rnea(q,dq,0))."""
+        q, dq, tau = (np.atleast_2d(np.asarray(x, dtype=np.float64)) for x in (q, dq, tau))
+        c = self.rnea(q, dq, np.zeros_like(q))
+        H = self.crba(q, symmetric=True)
+        L = np.linalg.cholesky(H)
+        y = np.linalg.solve(L, (tau - c)[..., None])
+        return np.linalg.solve(np.swapaxes(L, 1, 2), y)[..., 0]
+
+    def fwd_kin(self, q):
+        """q [B,n] -> (R [B,3,3], p [B,3]) of the tip in the base frame (multibody.rs:87-93)."""
+        q = np.atleast_2d(np.asarray(q, dtype=np.float64))
+        B, n = q.shape
+        Racc = np.tile(np.eye(3), (B, 1, 1)); p = np.zeros((B, 3))
+        for i in range(n - 1, -1, -1):
+            Ri = self._R(i, q[:, i])
+            p = np.einsum("bij,bj->bi", Ri, p) + self.tp[i]
+            Racc = Ri @ Racc
+        return Racc, p
+
+    def jac(self, q):
+        """q [B,n] -> J [B,6,n], rows lin then rot, expressed in the tip frame (multibody.rs:95-108)."""
+        q = np.atleast_2d(np.asarray(q, dtype=np.float64))
+        B, n = q.shape
+        J = np.zeros((B, 6, n))
+        Racc = np.tile(np.eye(3), (B, 1, 1)); p = np.zeros((B, 3))   # pose of tip in frame i
+        z = np.array([0.0, 0.0, 1.0])
+        for i in range(n - 1, -1, -1):
+            Rt = np.swapaxes(Racc, 1, 2)
+            J[:, 0:3, i] = np.einsum("bij,bj->bi", Rt, -np.cross(p, z))
+            J[:, 3:6, i] = Rt[:, :, 2]
+            Ri = self._R(i, q[:, i])
+            p = np.einsum("bij,bj->bi", Ri, p) + self.tp[i]
+            Racc = Ri @ Racc
+        return J
+
+    def potential_energy(self, q):
+        """U(q) = sum_i m_i g z_i(com) with the base accelerating +z (gravity points -z)."""
+        q = np.atleast_2d(np.asarray(q, dtype=np.float64))
+        B, n = q.shape
+        U = np.zeros(B)
+        Racc = np.tile(np.eye(3), (B, 1, 1)); p = np.zeros((B, 3))
+        for i in range(n):
+            Ri = self._R(i, q[:, i])
+            p = p + np.einsum("bij,j->bi", Racc, self.tp[i])
+            Racc = Racc @ Ri
+            com_w = p + np.einsum("bij,j->bi", Racc, self.h[i] / self.m[i])
+            U += self.m[i] * GRAVITY * com_w[:, 2]
+        return U
+
+
+def rnea_mp(model, q, dq, ddq, dps=40):
+    """mpmath evaluation of the matrix-form RNEA for ONE state at `dps` digits (error bound for the fp64 paths).
+    URDF decimal strings are taken at their fp64 values, as the reference does."""
+    import mpmath as mp
+    mp.mp.dps = dps
+    n = model.n
+    M = mp.matrix
+
+    def rot(axis, a):
+        c, s = mp.cos(a), mp.sin(a)
+        if axis == "x":
+            return M([[1, 0, 0], [0, c, -s], [0, s, c]])
+        if axis == "y":
+            return M([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+        return M([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+
+    def cross(a, b):
+        return M([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+    def skew(v):
+        return M([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+    R, t, m, h, Io = [], [], [], [], []
+    for i in range(n):
+        r, p, y = (mp.mpf(float(x)) for x in model.rpy[i])
+        R.append(rot("z", y) * rot("y", p) * rot("x", r) * rot("z", mp.mpf(float(q[i]))))
+        t.append(M([mp.mpf(float(x)) for x in model.xyz[i]]))
+        mi = mp.mpf(float(model.mass[i])); m.append(mi)
+        c = M([mp.mpf(float(x)) for x in model.com[i]])
+        h.append(mi * c)
+        s = [mp.mpf(float(x)) for x in model.inertia6[i]]
+        Ic = M([[s[0], s[1], s[2]], [s[1], s[3], s[4]], [s[2], s[4], s[5]]])
+        Cx = skew(c)
+        Io.append(Ic + mi * Cx * Cx.T)
+    zero = M([0, 0, 0])
+    vl, vr, al, ar = zero.copy(), zero.copy(), M([0, 0, mp.mpf(GRAVITY)]), zero.copy()
+    fl, fr = [], []
+    for i in range(n):
+        Rt = R[i].T
+        dqi, ddqi = mp.mpf(float(dq[i])), mp.mpf(float(ddq[i]))
+        vl, vr = Rt * (vl - cross(t[i], vr)), Rt * vr
+        vr[2] += dqi
+        al, ar = Rt * (al - cross(t[i], ar)), Rt * ar
+        ar[2] += ddqi
+        al[0] += vl[1] * dqi; al[1] += -vl[0] * dqi
+        ar[0] += vr[1] * dqi; ar[1] += -vr[0] * dqi
+        Ial = m[i] * al - cross(h[i], ar); Iar = Io[i] * ar + cross(h[i], al)
+        Ivl = m[i] * vl - cross(h[i], vr); Ivr = Io[i] * vr + cross(h[i], vl)
+        fl.append(Ial + cross(vr, Ivl))
+        fr.append(Iar + cross(vr, Ivr) + cross(vl, Ivl))
+    tau = [None] * n
+    for i in range(n - 1, -1, -1):
+        tau[i] = fr[i][2]
+        if i > 0:
+            Rl = R[i] * fl[i]
+            fl[i - 1] = fl[i - 1] + Rl
+            fr[i - 1] = fr[i - 1] + R[i] * fr[i] + cross(t[i], Rl)
+    return np.array([float(x) for x in tau])
