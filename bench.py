@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: FR3 RNEA+FD evals/sec (fp64) on N B200s, with roofline fractions.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference arm: the CPU oracle on all host threads
+
+One step = one batched RNEA pass (BASELINE.json configs[1]) + one batched forward-dynamics pass (configs[2]) over
+2^24 synthetic FR3 states per GPU, device-resident SoA, sampled on the device by the counter-based generator of
+SURVEY.md 8d.  Each GPU owns its own 2^24 states (weak scaling, no data-path collective).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "FR3 RNEA+FD evals/sec (fp64)"
+UNIT = "evals/s"
+STATES_PER_GPU = 1 << 24
+# algorithmic work per evaluation (SURVEY.md 8d / BASELINE.md section 2), N = 7
+RNEA_FLOPS, FD_FLOPS, BYTES_PER_EVAL = 2026.0, 4180.0, 224.0
+SEED_RNEA, SEED_FD = 0x5EED0001, 0x5EED0002
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) == 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle; test infrastructure)
+def cpu_arm(sample_states, steps, warmup):
+    """Times oracle/rb_oracle.c (reference-shaped C restatement; the Rust crate cannot be built in this image),
+    OpenMP static chunks over all host threads: RNEA + FD over `sample_states` states per step."""
+    from oracle.rb_oracle import Oracle
+    orc = Oracle.from_urdf(os.path.join(ROOT, "assets", "fr3.urdf"), fast=True)   # rebuilt -march=native on this host
+    m = orc.model
+    threads = orc.max_threads()
+    if sample_states is None:       # calibrate to ~4 s of wall time per step
+        S0 = 1 << 14
+        q = orc.fill(SEED_RNEA, 0, m.lower, m.upper, 0, S0); dq = orc.fill(SEED_RNEA, 1, -m.velocity, m.velocity, 0, S0)
+        t0 = time.perf_counter()
+        orc.rnea_batch(q, dq, q); orc.forward_dynamics_batch(q, dq, q)
+        per = (time.perf_counter() - t0) / S0
+        sample_states = int(min(1 << 22, max(1 << 14, 4.0 / per)))
+    S = sample_states
+    q = orc.fill(SEED_RNEA, 0, m.lower, m.upper, 0, S)
+    dq = orc.fill(SEED_RNEA, 1, -m.velocity, m.velocity, 0, S)
+    ddq = orc.fill(SEED_RNEA, 2, -10.0, 10.0, 0, S)
+    tau = orc.fill(SEED_FD, 3, -m.effort, m.effort, 0, S)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.rnea_batch(q, dq, ddq)
+        orc.forward_dynamics_batch(q, dq, tau)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": 2.0 * S / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{S} FR3 states per step (RNEA + FD each), {steps} timed steps, OpenMP static over {threads} threads, "
+                      f"oracle/rb_oracle.c -O3 -march=native"}, sec, S
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cb, sec, S = cpu_arm(None, max(1, args.steps), max(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "fr3_rnea+fd", "states_per_step": S, "layout": "soa",
+                       "note": "CPU port of the reference path (oracle/); the Rust crate cannot be built here"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import rigidbody_rs_b200 as rb
+    from rigidbody_rs_b200.shard import max_over_ranks, sum_over_ranks
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    mb = rb.Multibody.from_urdf(os.path.join(ROOT, "assets", "fr3.urdf"), device=local_rank)
+    n, B = mb.n, args.states
+    lim = mb.limits()
+    first = rank * B                                   # each rank samples its own slice of the global index space
+    q = torch.empty((n, B), dtype=torch.float64, device=dev)
+    dq, ddq, tau_in = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    tau, qdd = torch.empty_like(q), torch.empty_like(q)
+    mb.fill(q, SEED_RNEA, 0, lim["lower"], lim["upper"], first)
+    mb.fill(dq, SEED_RNEA, 1, -lim["velocity"], lim["velocity"], first)
+    mb.fill(ddq, SEED_RNEA, 2, -10.0, 10.0, first)
+    mb.fill(tau_in, SEED_FD, 3, -lim["effort"], lim["effort"], first)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        mb.rnea(q, dq, ddq, out=tau)
+        mb.forward_dynamics(q, dq, tau_in, out=qdd)
+
+    for _ in range(args.warmup):
+        step()
+    fp64_peak = mb.fp64_peak_tflops(100)               # DFMA probe, same GPU, same run (untimed)
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    launches0 = mb.launch_count
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(K):
+        ev[k][0].record()
+        mb.rnea(q, dq, ddq, out=tau)
+        ev[k][1].record()
+        mb.forward_dynamics(q, dq, tau_in, out=qdd)
+        ev[k][2].record()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = mb.launch_count - launches0
+    mb.sync()
+    total_ms = t_start.elapsed_time(t_end)
+    ms_step = max_over_ranks(total_ms / K, dev)
+    ms_rnea = max_over_ranks(sum(e[0].elapsed_time(e[1]) for e in ev) / K, dev)
+    ms_fd = max_over_ranks(sum(e[1].elapsed_time(e[2]) for e in ev) / K, dev)
+    units = sum_over_ranks(2.0 * B, dev)               # evaluations all ranks processed per step
+    value = units / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    Be = args.e2e_states
+    hq, hdq, hddq, htau_in = (rb.host_empty((n, Be)) for _ in range(4))
+    htau, hqdd = rb.host_empty((n, Be)), rb.host_empty((n, Be))
+    for h, d in ((hq, q), (hdq, dq), (hddq, ddq), (htau_in, tau_in)):
+        h[...] = d[:, :Be].cpu().numpy()
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    mb.rnea(hq, hdq, hddq, out=htau); mb.forward_dynamics(hq, hdq, htau_in, out=hqdd)      # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        mb.rnea(hq, hdq, hddq, out=htau)
+        mb.forward_dynamics(hq, hdq, htau_in, out=hqdd)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, dev)
+    e2e_units = sum_over_ranks(2.0 * Be, dev)
+    # the host results equal the device-resident ones bit for bit (same kernels, same inputs)
+    same = bool(np.array_equal(htau[:, :4096], tau[:, :4096].cpu().numpy()))
+
+    hbm_peak, hbm_src = measured_peaks()
+    rnea_s, fd_s = ms_rnea * 1e-3, ms_fd * 1e-3
+
+    def roof(kernel, flops, sec):
+        tf = flops * B / sec / 1e12
+        gbs = BYTES_PER_EVAL * B / sec / 1e9
+        return {"kernel": kernel, "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": tf / fp64_peak, "traffic": None, "evals_per_s": B / sec, "ms": sec * 1e3,
+                "peak_source": "DFMA probe (multibody_gpu_measure_fp64_peak) on this GPU in this run; nominal 37.2",
+                "flops_per_eval": flops, "bytes_per_eval": BYTES_PER_EVAL,
+                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "fr3_rnea+fd_16M", "states_per_gpu": B, "n_joints": n, "layout": "soa",
+                   "kernel_variant": mb.kernel_variant, "cache": "inputs larger than L2 (2.8 GB read per kernel)",
+                   "step": "1 RNEA launch + 1 forward-dynamics launch over all states", "parallelism": f"dp{world}"},
+        "roofline": roof("rb_fd_kernel", FD_FLOPS, fd_s),
+        "roofline_rnea": roof("rb_rnea_kernel", RNEA_FLOPS, rnea_s),
+        "e2e": {"value": e2e_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 6 * n * Be * 8,
+                "d2h_bytes_per_step": 2 * n * Be * 8, "states_per_gpu": Be, "steps": e2e_steps, "ms_per_step": e2e_ms,
+                "api": "Multibody.rnea/forward_dynamics on pinned numpy arrays -> multibody_*_batch(RB_MEM_HOST)",
+                "matches_device_path": same},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb, _, _ = cpu_arm(None, 2, 1)
+        line["cpu_baseline"] = cb
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--states", type=int, default=STATES_PER_GPU, help="states per GPU per step")
+    ap.add_argument("--e2e-states", type=int, default=STATES_PER_GPU, help="states per GPU per end-to-end step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/*
+ * rigidbody.h -- C ABI of the B200 batched rigid-body dynamics engine.
+ *
+ * A superset of the reference's rigidbody_bindings/rigidbody.h:11-16.  Part 1 keeps the six
+ * single-state symbols with the reference's signatures (so rigidbody_bindings/main.cpp:66-98 links
+ * unchanged).  Part 2 adds the batched, caller-allocated, status-returning entry points that the
+ * reference's FFI crate (rigidbody_bindings/src/lib.rs) would bind for the batched hot path.
+ *
+ * Valid as C and as C++ (the reference header is only valid C++: bare `Multibody*` after
+ * `struct Multibody;`, rigidbody.h:8,11).  Nothing here mentions torch, CUDA types or C++ types:
+ * plain pointers, sizes and enums only.  No call throws or aborts across the boundary; every
+ * fallible call returns an RbStatus and records a message readable with multibody_last_error().
+ * There is no CPU fallback: without a usable sm_100 device the constructors fail with RB_ERR_CUDA.
+ */
+#ifndef MULTIBODY_INTERFACE_H
+#define MULTIBODY_INTERFACE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================== Part 1: reference symbols */
+/* Opaque single-model handle; replaces the Rust `Multibody` (rigidbody/src/multibody.rs:32). */
+typedef struct Multibody Multibody;
+
+/* rigidbody_bindings/src/lib.rs:8-12.  The reference hard-codes an absolute URDF path (:10); here the
+ * path comes from $RIGIDBODY_URDF, else "assets/fr3.urdf" relative to the working directory.
+ * Returns NULL on failure (the reference panics). */
+Multibody* multibody_new(void);
+/* Explicit-path variant of the above (new). */
+Multibody* multibody_new_from_urdf(const char* urdf_path);
+/* lib.rs:46-57 -> 3 doubles (tip translation).  Result is malloc'ed; release with multibody_free_result
+ * (the reference leaks it, lib.rs:55). */
+double* multibody_fwd_kin(const Multibody* mb, const double q[7]);
+/* lib.rs:60-70 -> 6 x n doubles column-major, rows lin(0-2) then rot(3-5), tip frame. */
+double* multibody_jac(const Multibody* mb, const double q[7]);
+/* lib.rs:15-30 -> n doubles. */
+double* multibody_rnea(const Multibody* mb, const double q[7], const double dq[7], const double ddq[7]);
+/* lib.rs:32-43 -> n x n doubles column-major; diagonal + strict upper triangle, lower = 0, as
+ * multibody.rs:155-174 leaves it. */
+double* multibody_crba(const Multibody* mb, const double q[7]);
+/* lib.rs:73-78, null-safe. */
+void multibody_free(Multibody* mb);
+/* New: frees an array returned by the four calls above (null-safe). */
+void multibody_free_result(double* p);
+/* New: number of movable joints kept by from_urdf (7 for the FR3; the reference panics otherwise, multibody.rs:76). */
+int multibody_n_joints(const Multibody* mb);
+/* New: the flattened model as loaded on the host (no GPU needed): parent_rot [9n], parent_trans [3n], mass [n],
+ * h = m*com [3n], inertia_origin [6n] (xx xy xz yy yz zz).  Any output may be NULL. */
+int multibody_get_model(const Multibody* mb, double* parent_rot, double* parent_trans, double* mass,
+                        double* h, double* inertia_origin);
+
+/* ===================================================================== Part 2: batched engine */
+typedef enum RbStatus {
+    RB_OK = 0,
+    RB_ERR_NULL = -1,          /* a required pointer was NULL */
+    RB_ERR_ARG = -2,           /* bad size / layout / enum / chain */
+    RB_ERR_URDF = -3,          /* URDF could not be read or holds no movable joint */
+    RB_ERR_CUDA = -4,          /* CUDA runtime error or no usable device (no CPU fallback exists) */
+    RB_ERR_NOT_SPD = -5,       /* forward dynamics met a mass matrix that is not positive definite */
+    RB_ERR_UNSUPPORTED = -6    /* valid request this build cannot serve (e.g. n_joints > RB_MAX_JOINTS) */
+} RbStatus;
+
+/* Batch layout of every state array. */
+typedef enum RbLayout {
+    RB_LAYOUT_SOA = 0,   /* joint-major [n_joints][ld]: element (joint i, state s) at i*ld + s.  Native, coalesced. */
+    RB_LAYOUT_AOS = 1    /* state-major [n_states][n_joints]: the reference's per-state double[7], repeated. */
+} RbLayout;
+
+/* Where the pointers passed to a batched call live. */
+typedef enum RbMem {
+    RB_MEM_HOST = 0,     /* host memory (pinned or pageable); the call copies in, computes, copies out */
+    RB_MEM_DEVICE = 1    /* device memory on the engine's GPU; nothing is copied */
+} RbMem;
+
+#define RB_MAX_JOINTS 64
+
+/*
+ * Flattened, topologically ordered chain descriptor: what the Rust side extracts from
+ * `Multibody::iter()` (multibody.rs:79-81) and the pub fields of RevoluteJoint / Inertia
+ * (joint.rs:26-31, inertia.rs:12-17).  All arrays are borrowed for the duration of the call.
+ */
+typedef struct RbChainDesc {
+    int32_t n_joints;             /* 1..RB_MAX_JOINTS */
+    const int32_t* parent;        /* [n] parent link index, -1 = base.  NULL = serial chain (i-1).  Only serial
+                                     chains are accepted: the reference is serial-only (multibody.rs:148,165). */
+    const double* axis;           /* [3n] unit joint axes (joint.rs:27).  Must be (0,0,1): rnea/crba hard-code z
+                                     (multibody.rs:29,130).  NULL = all z. */
+    const double* parent_rot;     /* [9n] row-major rotation of joint frame i in link i-1 (joint.rs:29 .rotation) */
+    const double* parent_trans;   /* [3n] translation of joint frame i in link i-1 (joint.rs:29 .translation) */
+    const double* mass;           /* [n]  inertia.rs:13 */
+    const double* com;            /* [3n] inertia.rs:14, in link coordinates */
+    const double* inertia_com;    /* [9n] row-major, about the COM (inertia.rs:15) */
+    double gravity[3];            /* base linear acceleration; the reference uses (0,0,+9.81) (multibody.rs:118) */
+} RbChainDesc;
+
+/* Per-joint limits read from the URDF (sampling synthetic states; not used by the dynamics). */
+typedef struct RbJointLimits {
+    double lower[RB_MAX_JOINTS], upper[RB_MAX_JOINTS], velocity[RB_MAX_JOINTS], effort[RB_MAX_JOINTS];
+} RbJointLimits;
+
+/* Opaque engine: one chain descriptor resident on one GPU, plus its streams and staging buffers. */
+typedef struct RbGpu RbGpu;
+
+/* ---- construction -------------------------------------------------------------------------- */
+/* Upload a descriptor to CUDA device `device` (ordinal).  Replaces nothing in the reference: it is the
+ * one-time "flatten + upload" step the north star adds next to multibody_new. */
+int multibody_gpu_new(const RbChainDesc* desc, int device, RbGpu** out);
+/* Load a URDF exactly as Multibody::from_urdf does (multibody.rs:65-77: k-th joint zipped with k-th link in
+ * document order, joints whose type contains "fixed" dropped; joint.rs:53-68), then upload. */
+int multibody_gpu_new_from_urdf(const char* urdf_path, int device, RbGpu** out);
+/* Engine for an existing reference-style handle. */
+int multibody_gpu_from_multibody(const Multibody* mb, int device, RbGpu** out);
+void multibody_gpu_free(RbGpu* g);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int multibody_gpu_n_joints(const RbGpu* g);
+int multibody_gpu_device(const RbGpu* g);
+/* Which kernel family serves this chain: "fr3-specialised", "generic-7", "generic-n", ... */
+const char* multibody_gpu_kernel_variant(const RbGpu* g);
+/* Copies the flattened descriptor the engine uploaded (tests compare it with the oracle's model):
+ * parent_rot [9n], parent_trans [3n], mass [n], h = m*com [3n], inertia_origin [6n] (xx xy xz yy yz zz). */
+int multibody_gpu_get_model(const RbGpu* g, double* parent_rot, double* parent_trans, double* mass,
+                            double* h, double* inertia_origin);
+int multibody_gpu_get_limits(const RbGpu* g, RbJointLimits* out);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* multibody_last_error(void);
+
+/* ---- the batched hot path ------------------------------------------------------------------ */
+/*
+ * Common arguments:  n_states states; `ld` = leading dimension in elements for RB_LAYOUT_SOA (>= n_states;
+ * 0 means n_states), ignored for AOS; `mem` says where ALL pointers of the call live.
+ * RB_MEM_DEVICE calls are asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the engine's own
+ * stream) and return after the launch; call multibody_gpu_sync (or sync the stream yourself) before reading.
+ * RB_MEM_HOST calls are synchronous: they stage through the engine's pinned buffers in chunks, overlapping
+ * H2D, compute and D2H, and return when `out` is complete.
+ * With n_states = 1, AOS, HOST these are the reference's single-state calls minus the leak.
+ */
+
+/* tau = ID(q, dq, ddq): multibody_rnea (lib.rs:15-30) = get_transforms (multibody.rs:83-85) + rnea (:111-153). */
+int multibody_rnea_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, double* tau,
+                         size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
+/* qdd = FD(q, dq, tau) = chol_solve(sym(crba(q)), tau - rnea(q, dq, 0)) -- composed from multibody.rs:111-153
+ * (ddq = 0) and :155-174; the solve is new.  For RB_MEM_HOST calls a non-SPD mass matrix
+ * yields RB_ERR_NOT_SPD (qdd of that state is NaN); for device calls query multibody_gpu_status. */
+int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const double* dq, const double* tau, double* qdd,
+                                     size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
+/* H = crba(q): multibody_crba (lib.rs:32-43).  Output convention of the reference: n*n entries per state,
+ * entry k = r + n*c (column-major), diagonal + strict upper triangle filled, strict lower = 0.
+ * SOA: H[k*ld + s];  AOS: H[s*n*n + k]. */
+int multibody_crba_batch(RbGpu* g, const double* q, double* H,
+                         size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
+/* Tip translation: multibody_fwd_kin (lib.rs:46-57).  3 entries per state (SOA: xyz[k*ld + s]; AOS: xyz[3s + k]). */
+int multibody_fwd_kin_batch(RbGpu* g, const double* q, double* xyz,
+                            size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
+/* Tip-frame Jacobian: multibody_jac (lib.rs:60-70).  6n entries per state, entry k = r + 6*c. */
+int multibody_jac_batch(RbGpu* g, const double* q, double* J,
+                        size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
+/* MPC rollout: for t in 0..horizon: qdd = FD(q, dq, tau[t]); dq += dt*qdd; q += dt*dq.
+ * q0, dq0: one state array each (layout/ld as above).  tau: `horizon` consecutive state arrays
+ * (SOA: [horizon][n][ld]; AOS: [horizon][n_traj][n]).  q_traj/dq_traj: same shape as tau, the state AFTER
+ * each step; either may be NULL.  q_final/dq_final (one state array each) may be NULL. */
+int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
+                      double* q_traj, double* dq_traj, double* q_final, double* dq_final,
+                      size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
+/* ---- device-side helpers (bench / tests) --------------------------------------------------- */
+/* Fill a device SOA array [n][ld] with the counter-based sampler of SURVEY.md 8d:
+ * value(joint i, state s) = fma(hi[i]-lo[i], u, lo[i]),  u = top 53 bits of
+ * splitmix64(seed + GOLDEN*(1 + (field<<58 | i<<50 | first_index+s))).  lo/hi are host arrays [n]. */
+int multibody_gpu_fill(RbGpu* g, double* dev_out, uint64_t seed, uint32_t field, const double* lo, const double* hi,
+                       size_t first_index, size_t count, size_t ld, void* stream);
+/* Wait for the engine's stream and report a sticky device-side status (RB_ERR_NOT_SPD, RB_ERR_CUDA) once. */
+int multibody_gpu_sync(RbGpu* g);
+int multibody_gpu_status(RbGpu* g);
+/* Kernel launches issued by this engine since creation (bench.py's `gpu_launches`). */
+uint64_t multibody_gpu_launch_count(const RbGpu* g);
+/* Pinned host allocations, so RB_MEM_HOST calls copy at full PCIe rate without a staging hop. */
+int multibody_host_alloc(void** out, size_t bytes);
+void multibody_host_free(void* p);
+/* Sustained FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), measured with a register-only
+ * dependent-chain kernel for `millis` ms: the FP64 roofline denominator bench.py reports against. */
+int multibody_gpu_measure_fp64_peak(RbGpu* g, int millis, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTIBODY_INTERFACE_H */

@@ -1,0 +1,700 @@
+// rb_api.cu -- the C ABI declared in include/rigidbody.h.
+//
+// Host side of the engine: owns the flattened model, picks a kernel family, validates arguments, moves host
+// batches through pinned/pipelined copies, and never lets an exception or a CUDA error escape as anything
+// but an RbStatus + message.  There is no CPU implementation behind any entry point.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rigidbody.h"
+#include "rb_host_model.h"
+#include "rb_kernels.cuh"
+#include "rb_util.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return RB_ERR_CUDA;
+}
+#define RB_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call);      \
+    } while (0)
+
+struct RbNParamHost {           // must match RbNParam in rb_kernels_n.cu
+    const double* model; int n; double* scratch; size_t threads; size_t slots;
+};
+
+constexpr int kSlots = 3;       // depth of the host-batch pipeline
+
+struct DevBuf {
+    double* p = nullptr; size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return RB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc((void**)&p, need);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(staging)");
+        bytes = need;
+        return RB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct RbGpu {
+    int device = 0;
+    int sm_count = 0;
+    RbHostModel model;
+    const RbOps* ops = nullptr;
+    std::vector<unsigned char> param;     // host image of the kernel-parameter block `ops` expects
+    double* d_model = nullptr;            // generic-n: model rows on the device
+    DevBuf scratch;                       // generic-n: per-thread strided scratch
+    size_t scratch_threads = 0;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
+    DevBuf in[kSlots], out[kSlots], tmp[kSlots];
+    int* d_status = nullptr;
+    int* h_status = nullptr;              // pinned
+    int sticky = RB_OK;
+    uint64_t launches = 0;
+    std::mutex mu;                        // serialises host-batch calls that share the staging buffers
+};
+
+struct Multibody {
+    RbHostModel model;
+    RbGpu* gpu = nullptr;                 // created on first use
+    std::mutex mu;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int pick_ops(RbGpu* g) {
+    const char* force = getenv("RIGIDBODY_B200_VARIANT");
+    const std::string want = force ? force : "auto";
+    const int n = g->model.n;
+    std::vector<double> flat = rb_model_flat(g->model);
+    const bool is_fr3 = n == 7 && memcmp(flat.data(), rb_fr3_table(), sizeof(double) * (7 * 24 + 3)) == 0;
+    if ((want == "auto" || want == "fr3-specialised") && is_fr3) {
+        g->ops = rb_ops_fr3();
+        g->param.assign(g->ops->param_bytes, 0);
+        return RB_OK;
+    }
+    if (want == "fr3-specialised") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=fr3-specialised but the chain is not the compiled-in FR3 model");
+    if ((want == "auto" || want == "generic-7") && n == 7) {
+        g->ops = rb_ops_rt7();
+        g->param.assign(g->ops->param_bytes, 0);
+        if (g->ops->param_bytes != flat.size() * sizeof(double)) return fail(RB_ERR_ARG, "internal: RbModelK<7> size mismatch");
+        memcpy(g->param.data(), flat.data(), g->ops->param_bytes);
+        return RB_OK;
+    }
+    if (want == "generic-7") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=generic-7 needs a 7-joint chain");
+    if (want != "auto" && want != "generic-n") return fail(RB_ERR_ARG, "unknown RIGIDBODY_B200_VARIANT '" + want + "'");
+    g->ops = rb_ops_generic_n();
+    RB_CUDA(cudaMalloc((void**)&g->d_model, flat.size() * sizeof(double)));
+    RB_CUDA(cudaMemcpy(g->d_model, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // persistent grid: 8 blocks of RB_BLOCK threads per SM; scratch sized for the largest user (rollout)
+    g->scratch_threads = (size_t)g->sm_count * 8 * RB_BLOCK;
+    const size_t slots = (size_t)12 * n + (size_t)n * n;
+    int rc = g->scratch.ensure(slots * g->scratch_threads * sizeof(double));
+    if (rc != RB_OK) return rc;
+    RbNParamHost P{g->d_model, n, g->scratch.p, g->scratch_threads, slots};
+    g->param.assign(sizeof(P), 0);
+    if (g->ops->param_bytes != sizeof(P)) return fail(RB_ERR_ARG, "internal: RbNParam size mismatch");
+    memcpy(g->param.data(), &P, sizeof(P));
+    return RB_OK;
+}
+
+int gpu_create(const RbHostModel& model, int device, RbGpu** out) {
+    if (!out) return fail(RB_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                     "); this engine has no CPU fallback");
+    if (device < 0 || device >= count) return fail(RB_ERR_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    RB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(RB_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; kernels are built for sm_100a only");
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
+    RbGpu* g = new (std::nothrow) RbGpu();
+    if (!g) return fail(RB_ERR_CUDA, "out of host memory");
+    g->device = device;
+    g->sm_count = prop.multiProcessorCount;
+    g->model = model;
+    auto bail = [&](int rc) { multibody_gpu_free(g); return rc; };
+    if ((e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
+    if ((e = cudaStreamCreateWithFlags(&g->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
+    if ((e = cudaStreamCreateWithFlags(&g->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
+    for (int k = 0; k < kSlots; ++k) {
+        if ((e = cudaEventCreateWithFlags(&g->ev_h2d[k], cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+        if ((e = cudaEventCreateWithFlags(&g->ev_comp[k], cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+        if ((e = cudaEventCreateWithFlags(&g->ev_d2h[k], cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+    }
+    if ((e = cudaMalloc((void**)&g->d_status, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(status)"));
+    if ((e = cudaMemset(g->d_status, 0, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset(status)"));
+    if ((e = cudaMallocHost((void**)&g->h_status, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMallocHost(status)"));
+    *g->h_status = 0;
+    int rc = pick_ops(g);
+    if (rc != RB_OK) return bail(rc);
+    *out = g;
+    return RB_OK;
+}
+
+// Reads and clears the device status word; maps it to an RbStatus.  Stream must be idle.
+int fetch_status(RbGpu* g) {
+    RB_CUDA(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    RB_CUDA(cudaMemsetAsync(g->d_status, 0, sizeof(int), g->stream));
+    RB_CUDA(cudaStreamSynchronize(g->stream));
+    if (*g->h_status & RB_STATUS_NOT_SPD) {
+        *g->h_status = 0;
+        return fail(RB_ERR_NOT_SPD, "forward dynamics: mass matrix not positive definite for at least one state (its qdd is NaN)");
+    }
+    return RB_OK;
+}
+
+// ---- a batched op, described once, run from device or host memory ----
+struct OpDesc {
+    int n_in;                    // number of input state arrays
+    const double* in[3];
+    int in_per[3];               // doubles per state of each input
+    double* out;
+    int out_per;                 // doubles per state of the output
+    // launch on SoA device buffers with leading dimension ld
+    cudaError_t (*launch)(RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st);
+};
+
+int check_common(RbGpu* g, const OpDesc& op, size_t n_states, size_t& ld, RbLayout layout, RbMem mem) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    if (layout != RB_LAYOUT_SOA && layout != RB_LAYOUT_AOS) return fail(RB_ERR_ARG, "bad layout");
+    if (mem != RB_MEM_HOST && mem != RB_MEM_DEVICE) return fail(RB_ERR_ARG, "bad mem");
+    if (n_states == 0) return RB_OK;
+    for (int k = 0; k < op.n_in; ++k) if (!op.in[k]) return fail(RB_ERR_NULL, "input pointer is NULL");
+    if (!op.out) return fail(RB_ERR_NULL, "output pointer is NULL");
+    if (layout == RB_LAYOUT_SOA) {
+        if (ld == 0) ld = n_states;
+        if (ld < n_states) return fail(RB_ERR_ARG, "ld < n_states");
+    }
+    return RB_OK;
+}
+
+int run_device(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout, cudaStream_t st) {
+    if (layout == RB_LAYOUT_SOA) {
+        cudaError_t e = op.launch(g, op.in, op.out, B, ld, st);
+        g->launches += 1;
+        if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+        return RB_OK;
+    }
+    // AoS device pointers: transpose into per-call SoA scratch, compute, transpose back (stream-ordered).
+    std::lock_guard<std::mutex> lk(g->mu);
+    size_t in_d = 0;
+    for (int k = 0; k < op.n_in; ++k) in_d += (size_t)op.in_per[k];
+    int rc = g->in[0].ensure(in_d * B * sizeof(double)); if (rc) return rc;
+    rc = g->out[0].ensure((size_t)op.out_per * B * sizeof(double)); if (rc) return rc;
+    const double* soa_in[3]; size_t off = 0;
+    for (int k = 0; k < op.n_in; ++k) {
+        double* dst = g->in[0].p + off * B;
+        cudaError_t e = rb_launch_aos_to_soa(op.in[k], dst, op.in_per[k], B, B, st);
+        g->launches += 1;
+        if (e != cudaSuccess) return fail_cuda(e, "aos_to_soa launch");
+        soa_in[k] = dst; off += (size_t)op.in_per[k];
+    }
+    cudaError_t e = op.launch(g, soa_in, g->out[0].p, B, B, st);
+    g->launches += 1;
+    if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+    e = rb_launch_soa_to_aos(g->out[0].p, op.out, op.out_per, B, B, st);
+    g->launches += 1;
+    if (e != cudaSuccess) return fail_cuda(e, "soa_to_aos launch");
+    return RB_OK;
+}
+
+// Host batch: chunks flow H2D -> compute -> D2H on three streams through kSlots staging slots.
+int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    size_t in_d = 0;
+    for (int k = 0; k < op.n_in; ++k) in_d += (size_t)op.in_per[k];
+    const size_t per_state = (in_d + (size_t)op.out_per) * sizeof(double);
+    size_t chunk = (size_t)(192u << 20) / per_state;                 // ~192 MiB of state per slot
+    chunk = std::max<size_t>(1024, std::min<size_t>(chunk, (size_t)1 << 20));
+    chunk = std::min(chunk, B);
+    const bool aos = layout == RB_LAYOUT_AOS;
+    for (int s = 0; s < kSlots; ++s) {
+        int rc = g->in[s].ensure(in_d * chunk * sizeof(double)); if (rc) return rc;
+        rc = g->out[s].ensure((size_t)op.out_per * chunk * sizeof(double)); if (rc) return rc;
+        if (aos) { rc = g->tmp[s].ensure(std::max(in_d, (size_t)op.out_per) * chunk * sizeof(double)); if (rc) return rc; }
+    }
+    size_t done = 0; int c = 0;
+    for (; done < B; done += chunk, ++c) {
+        const int s = c % kSlots;
+        const size_t cnt = std::min(chunk, B - done);
+        // inputs of this slot were last read by the compute of chunk c-kSlots
+        if (c >= kSlots) RB_CUDA(cudaStreamWaitEvent(g->s_h2d, g->ev_comp[s], 0));
+        // AoS: the landing zone tmp[s] also carried chunk c-kSlots' output to the host
+        if (c >= kSlots && aos) RB_CUDA(cudaStreamWaitEvent(g->s_h2d, g->ev_d2h[s], 0));
+        const double* soa_in[3]; size_t off = 0;
+        for (int k = 0; k < op.n_in; ++k) {
+            double* dst = g->in[s].p + off * chunk;
+            if (!aos) {
+                RB_CUDA(cudaMemcpy2DAsync(dst, cnt * sizeof(double), op.in[k] + done, ld * sizeof(double),
+                                          cnt * sizeof(double), (size_t)op.in_per[k], cudaMemcpyHostToDevice, g->s_h2d));
+            } else {
+                // AoS chunk is one contiguous run; land it in tmp, transpose on the compute stream
+                RB_CUDA(cudaMemcpyAsync(g->tmp[s].p + off * chunk, op.in[k] + done * (size_t)op.in_per[k],
+                                        cnt * (size_t)op.in_per[k] * sizeof(double), cudaMemcpyHostToDevice, g->s_h2d));
+            }
+            soa_in[k] = dst; off += (size_t)op.in_per[k];
+        }
+        RB_CUDA(cudaEventRecord(g->ev_h2d[s], g->s_h2d));
+        RB_CUDA(cudaStreamWaitEvent(g->stream, g->ev_h2d[s], 0));
+        if (c >= kSlots) RB_CUDA(cudaStreamWaitEvent(g->stream, g->ev_d2h[s], 0));   // output slot drained
+        if (aos) {
+            off = 0;
+            for (int k = 0; k < op.n_in; ++k) {
+                cudaError_t e = rb_launch_aos_to_soa(g->tmp[s].p + off * chunk, g->in[s].p + off * chunk, op.in_per[k], cnt, cnt, g->stream);
+                g->launches += 1;
+                if (e != cudaSuccess) return fail_cuda(e, "aos_to_soa launch");
+                off += (size_t)op.in_per[k];
+            }
+            // SoA views inside the slot use ld = cnt
+            off = 0;
+            for (int k = 0; k < op.n_in; ++k) { soa_in[k] = g->in[s].p + off * chunk; off += (size_t)op.in_per[k]; }
+        }
+        cudaError_t e = op.launch(g, soa_in, g->out[s].p, cnt, cnt, g->stream);
+        g->launches += 1;
+        if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+        if (aos) {
+            e = rb_launch_soa_to_aos(g->out[s].p, g->tmp[s].p, op.out_per, cnt, cnt, g->stream);
+            g->launches += 1;
+            if (e != cudaSuccess) return fail_cuda(e, "soa_to_aos launch");
+        }
+        RB_CUDA(cudaEventRecord(g->ev_comp[s], g->stream));
+        RB_CUDA(cudaStreamWaitEvent(g->s_d2h, g->ev_comp[s], 0));
+        if (!aos) {
+            RB_CUDA(cudaMemcpy2DAsync(op.out + done, ld * sizeof(double), g->out[s].p, cnt * sizeof(double),
+                                      cnt * sizeof(double), (size_t)op.out_per, cudaMemcpyDeviceToHost, g->s_d2h));
+        } else {
+            RB_CUDA(cudaMemcpyAsync(op.out + done * (size_t)op.out_per, g->tmp[s].p, cnt * (size_t)op.out_per * sizeof(double),
+                                    cudaMemcpyDeviceToHost, g->s_d2h));
+        }
+        RB_CUDA(cudaEventRecord(g->ev_d2h[s], g->s_d2h));
+    }
+    RB_CUDA(cudaStreamSynchronize(g->s_d2h));
+    RB_CUDA(cudaStreamSynchronize(g->stream));
+    return RB_OK;
+}
+
+int run_op(RbGpu* g, OpDesc& op, size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream, bool has_status) {
+    int rc = check_common(g, op, n_states, ld, layout, mem);
+    if (rc != RB_OK || n_states == 0) return rc;
+    DeviceGuard dg(g->device);
+    if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
+    if (mem == RB_MEM_DEVICE)
+        return run_device(g, op, n_states, ld, layout, stream ? (cudaStream_t)stream : g->stream);
+    rc = run_host(g, op, n_states, ld, layout);
+    if (rc != RB_OK) return rc;
+    return has_status ? fetch_status(g) : RB_OK;
+}
+
+}  // namespace
+
+// ===================================================================== construction
+extern "C" int multibody_gpu_new(const RbChainDesc* desc, int device, RbGpu** out) {
+    try {
+        RbHostModel m; std::string err;
+        int rc = rb_model_from_desc(desc, m, err);
+        if (rc != RB_OK) { if (out) *out = nullptr; return fail(rc, err); }
+        return gpu_create(m, device, out);
+    } catch (const std::exception& e) { return fail(RB_ERR_ARG, std::string("exception: ") + e.what()); }
+}
+
+extern "C" int multibody_gpu_new_from_urdf(const char* urdf_path, int device, RbGpu** out) {
+    try {
+        RbHostModel m; std::string err;
+        int rc = rb_model_from_urdf(urdf_path, m, err);
+        if (rc != RB_OK) { if (out) *out = nullptr; return fail(rc, err); }
+        return gpu_create(m, device, out);
+    } catch (const std::exception& e) { return fail(RB_ERR_ARG, std::string("exception: ") + e.what()); }
+}
+
+extern "C" int multibody_gpu_from_multibody(const Multibody* mb, int device, RbGpu** out) {
+    if (!mb) return fail(RB_ERR_NULL, "Multibody handle is NULL");
+    try { return gpu_create(mb->model, device, out); }
+    catch (const std::exception& e) { return fail(RB_ERR_ARG, std::string("exception: ") + e.what()); }
+}
+
+extern "C" void multibody_gpu_free(RbGpu* g) {
+    if (!g) return;
+    DeviceGuard dg(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    for (int k = 0; k < kSlots; ++k) {
+        g->in[k].release(); g->out[k].release(); g->tmp[k].release();
+        if (g->ev_h2d[k]) cudaEventDestroy(g->ev_h2d[k]);
+        if (g->ev_comp[k]) cudaEventDestroy(g->ev_comp[k]);
+        if (g->ev_d2h[k]) cudaEventDestroy(g->ev_d2h[k]);
+    }
+    g->scratch.release();
+    if (g->d_model) cudaFree(g->d_model);
+    if (g->d_status) cudaFree(g->d_status);
+    if (g->h_status) cudaFreeHost(g->h_status);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    if (g->s_h2d) cudaStreamDestroy(g->s_h2d);
+    if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
+    delete g;
+}
+
+// ===================================================================== introspection
+extern "C" int multibody_gpu_n_joints(const RbGpu* g) { return g ? g->model.n : fail(RB_ERR_NULL, "engine handle is NULL"); }
+extern "C" int multibody_gpu_device(const RbGpu* g) { return g ? g->device : fail(RB_ERR_NULL, "engine handle is NULL"); }
+extern "C" const char* multibody_gpu_kernel_variant(const RbGpu* g) { return g && g->ops ? g->ops->name : ""; }
+extern "C" const char* multibody_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t multibody_gpu_launch_count(const RbGpu* g) { return g ? g->launches : 0; }
+
+static void copy_model(const RbHostModel& m, double* parent_rot, double* parent_trans, double* mass, double* h,
+                       double* inertia_origin) {
+    for (int i = 0; i < m.n; ++i) {
+        const RbJointK& j = m.jt[i];
+        if (parent_rot) memcpy(parent_rot + 9 * i, j.R, sizeof j.R);
+        if (parent_trans) memcpy(parent_trans + 3 * i, j.t, sizeof j.t);
+        if (mass) mass[i] = j.m;
+        if (h) memcpy(h + 3 * i, j.h, sizeof j.h);
+        if (inertia_origin) memcpy(inertia_origin + 6 * i, j.I, sizeof j.I);
+    }
+}
+
+extern "C" int multibody_gpu_get_model(const RbGpu* g, double* parent_rot, double* parent_trans, double* mass,
+                                       double* h, double* inertia_origin) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    copy_model(g->model, parent_rot, parent_trans, mass, h, inertia_origin);
+    return RB_OK;
+}
+
+extern "C" int multibody_n_joints(const Multibody* mb) { return mb ? mb->model.n : fail(RB_ERR_NULL, "Multibody handle is NULL"); }
+
+extern "C" int multibody_get_model(const Multibody* mb, double* parent_rot, double* parent_trans, double* mass,
+                                   double* h, double* inertia_origin) {
+    if (!mb) return fail(RB_ERR_NULL, "Multibody handle is NULL");
+    copy_model(mb->model, parent_rot, parent_trans, mass, h, inertia_origin);
+    return RB_OK;
+}
+
+extern "C" int multibody_gpu_get_limits(const RbGpu* g, RbJointLimits* out) {
+    if (!g || !out) return fail(RB_ERR_NULL, "NULL argument");
+    *out = g->model.lim;
+    return RB_OK;
+}
+
+// ===================================================================== the batched hot path
+extern "C" int multibody_rnea_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, double* tau,
+                                    size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    const int n = g->model.n;
+    OpDesc op{3, {q, dq, ddq}, {n, n, n}, tau, n,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  return g->ops->rnea(g->param.data(), in[0], in[1], in[2], out, B, ld, st);
+              }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, false);
+}
+
+extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const double* dq, const double* tau, double* qdd,
+                                                size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    const int n = g->model.n;
+    OpDesc op{3, {q, dq, tau}, {n, n, n}, qdd, n,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  return g->ops->fd(g->param.data(), in[0], in[1], in[2], out, B, ld, g->d_status, st);
+              }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, true);
+}
+
+extern "C" int multibody_crba_batch(RbGpu* g, const double* q, double* H, size_t n_states, size_t ld, RbLayout layout,
+                                    RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    const int n = g->model.n;
+    OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, H, n * n,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  return g->ops->crba(g->param.data(), in[0], out, B, ld, st);
+              }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, false);
+}
+
+extern "C" int multibody_fwd_kin_batch(RbGpu* g, const double* q, double* xyz, size_t n_states, size_t ld, RbLayout layout,
+                                       RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    const int n = g->model.n;
+    OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, xyz, 3,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  return g->ops->fwd_kin(g->param.data(), in[0], out, B, ld, st);
+              }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, false);
+}
+
+extern "C" int multibody_jac_batch(RbGpu* g, const double* q, double* J, size_t n_states, size_t ld, RbLayout layout,
+                                   RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    const int n = g->model.n;
+    OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, J, 6 * n,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  return g->ops->jac(g->param.data(), in[0], out, B, ld, st);
+              }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, false);
+}
+
+extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
+                                 double* q_traj, double* dq_traj, double* q_final, double* dq_final,
+                                 size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    if (layout != RB_LAYOUT_SOA && layout != RB_LAYOUT_AOS) return fail(RB_ERR_ARG, "bad layout");
+    if (mem != RB_MEM_HOST && mem != RB_MEM_DEVICE) return fail(RB_ERR_ARG, "bad mem");
+    if (horizon < 0) return fail(RB_ERR_ARG, "horizon < 0");
+    if (!std::isfinite(dt)) return fail(RB_ERR_ARG, "dt must be finite");
+    if (n_traj == 0 || horizon == 0) return RB_OK;
+    if (!q0 || !dq0 || !tau) return fail(RB_ERR_NULL, "input pointer is NULL");
+    if (layout == RB_LAYOUT_SOA) { if (ld == 0) ld = n_traj; if (ld < n_traj) return fail(RB_ERR_ARG, "ld < n_traj"); }
+    const int n = g->model.n;
+    DeviceGuard dg(g->device);
+    if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (mem == RB_MEM_DEVICE && stream) ? (cudaStream_t)stream : g->stream;
+    if (mem == RB_MEM_DEVICE && layout == RB_LAYOUT_SOA) {
+        cudaError_t e = g->ops->rollout(g->param.data(), q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_final, dq_final,
+                                        n_traj, ld, g->d_status, st);
+        g->launches += 1;
+        if (e != cudaSuccess) return fail_cuda(e, "rollout launch");
+        return RB_OK;
+    }
+    // Host pointers and/or AoS: stage everything on the device as SoA with ld = n_traj, run once, bring results back.
+    std::lock_guard<std::mutex> lk(g->mu);
+    const size_t B = n_traj, one = (size_t)n * B, H = (size_t)horizon;
+    const bool aos = layout == RB_LAYOUT_AOS, host = mem == RB_MEM_HOST;
+    // in[0]: q0 | dq0 | tau[H]      out[0]: q_traj[H] | dq_traj[H] | q_fin | dq_fin      tmp[0]: AoS landing zone
+    int rc = g->in[0].ensure((2 + H) * one * sizeof(double)); if (rc) return rc;
+    rc = g->out[0].ensure((2 * H + 2) * one * sizeof(double)); if (rc) return rc;
+    if (aos) { rc = g->tmp[0].ensure(std::max<size_t>(2 + H, 2 * H + 2) * one * sizeof(double)); if (rc) return rc; }
+    double* d_in = g->in[0].p; double* d_out = g->out[0].p; double* d_tmp = g->tmp[0].p;
+    auto bring_in = [&](const double* src, double* dst, size_t arrays) -> int {
+        // `arrays` consecutive state arrays
+        for (size_t a = 0; a < arrays; ++a) {
+            const double* s_a = src + a * (aos ? one : (size_t)n * ld);
+            double* d_a = dst + a * one;
+            if (!aos) {
+                RB_CUDA(cudaMemcpy2DAsync(d_a, B * sizeof(double), s_a, ld * sizeof(double), B * sizeof(double), (size_t)n,
+                                          host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+            } else {
+                const double* a_src = s_a;
+                if (host) {
+                    double* land = d_tmp + a * one;
+                    RB_CUDA(cudaMemcpyAsync(land, s_a, one * sizeof(double), cudaMemcpyHostToDevice, st));
+                    a_src = land;
+                }
+                cudaError_t e = rb_launch_aos_to_soa(a_src, d_a, n, B, B, st);
+                g->launches += 1;
+                if (e != cudaSuccess) return fail_cuda(e, "aos_to_soa launch");
+            }
+        }
+        return RB_OK;
+    };
+    rc = bring_in(q0, d_in, 1); if (rc) return rc;
+    rc = bring_in(dq0, d_in + one, 1); if (rc) return rc;
+    rc = bring_in(tau, d_in + 2 * one, H); if (rc) return rc;
+    double* d_qt = d_out; double* d_dqt = d_out + H * one; double* d_qf = d_out + 2 * H * one; double* d_dqf = d_qf + one;
+    cudaError_t e = g->ops->rollout(g->param.data(), d_in, d_in + one, d_in + 2 * one, dt, horizon,
+                                    q_traj ? d_qt : nullptr, dq_traj ? d_dqt : nullptr, q_final ? d_qf : nullptr,
+                                    dq_final ? d_dqf : nullptr, B, B, g->d_status, st);
+    g->launches += 1;
+    if (e != cudaSuccess) return fail_cuda(e, "rollout launch");
+    auto bring_out = [&](const double* src, double* dst, size_t arrays) -> int {
+        if (!dst) return RB_OK;
+        for (size_t a = 0; a < arrays; ++a) {
+            const double* s_a = src + a * one;
+            double* d_a = dst + a * (aos ? one : (size_t)n * ld);
+            if (!aos) {
+                RB_CUDA(cudaMemcpy2DAsync(d_a, ld * sizeof(double), s_a, B * sizeof(double), B * sizeof(double), (size_t)n,
+                                          host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+            } else {
+                double* a_dst = host ? d_tmp + a * one : d_a;
+                cudaError_t e2 = rb_launch_soa_to_aos(s_a, a_dst, n, B, B, st);
+                g->launches += 1;
+                if (e2 != cudaSuccess) return fail_cuda(e2, "soa_to_aos launch");
+                if (host) RB_CUDA(cudaMemcpyAsync(d_a, a_dst, one * sizeof(double), cudaMemcpyDeviceToHost, st));
+            }
+        }
+        return RB_OK;
+    };
+    // the AoS landing zone is reused per output array group, so drain between groups
+    rc = bring_out(d_qt, q_traj, H); if (rc) return rc;
+    if (aos && host) RB_CUDA(cudaStreamSynchronize(st));
+    rc = bring_out(d_dqt, dq_traj, H); if (rc) return rc;
+    if (aos && host) RB_CUDA(cudaStreamSynchronize(st));
+    rc = bring_out(d_qf, q_final, 1); if (rc) return rc;
+    if (aos && host) RB_CUDA(cudaStreamSynchronize(st));
+    rc = bring_out(d_dqf, dq_final, 1); if (rc) return rc;
+    if (host) {
+        RB_CUDA(cudaStreamSynchronize(st));
+        return fetch_status(g);
+    }
+    return RB_OK;
+}
+
+// ===================================================================== helpers
+extern "C" int multibody_gpu_fill(RbGpu* g, double* dev_out, uint64_t seed, uint32_t field, const double* lo, const double* hi,
+                                  size_t first_index, size_t count, size_t ld, void* stream) {
+    if (!g || !dev_out || !lo || !hi) return fail(RB_ERR_NULL, "NULL argument");
+    if (ld == 0) ld = count;
+    if (ld < count) return fail(RB_ERR_ARG, "ld < count");
+    if (field >= 64) return fail(RB_ERR_ARG, "field must be < 64");
+    DeviceGuard dg(g->device);
+    RbFillRange rg;
+    for (int i = 0; i < g->model.n; ++i) { rg.lo[i] = lo[i]; rg.hi[i] = hi[i]; }
+    cudaError_t e = rb_launch_fill(dev_out, seed, field, g->model.n, rg, first_index, count, ld,
+                                   stream ? (cudaStream_t)stream : g->stream);
+    g->launches += 1;
+    if (e != cudaSuccess) return fail_cuda(e, "fill launch");
+    return RB_OK;
+}
+
+extern "C" int multibody_gpu_sync(RbGpu* g) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    DeviceGuard dg(g->device);
+    RB_CUDA(cudaStreamSynchronize(g->stream));
+    return fetch_status(g);
+}
+
+extern "C" int multibody_gpu_status(RbGpu* g) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    DeviceGuard dg(g->device);
+    RB_CUDA(cudaDeviceSynchronize());
+    return fetch_status(g);
+}
+
+extern "C" int multibody_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(RB_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    RB_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return RB_OK;
+}
+extern "C" void multibody_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int multibody_gpu_measure_fp64_peak(RbGpu* g, int millis, double* tflops) {
+    if (!g || !tflops) return fail(RB_ERR_NULL, "NULL argument");
+    DeviceGuard dg(g->device);
+    double* d_out = nullptr;
+    RB_CUDA(cudaMalloc((void**)&d_out, sizeof(double)));
+    cudaEvent_t a, b;
+    RB_CUDA(cudaEventCreate(&a)); RB_CUDA(cudaEventCreate(&b));
+    const int blocks = g->sm_count * 8;
+    auto run = [&](int iters, float* ms) -> int {
+        RB_CUDA(cudaEventRecord(a, g->stream));
+        RB_CUDA(rb_launch_fp64_peak(d_out, blocks, iters, g->stream));
+        g->launches += 1;
+        RB_CUDA(cudaEventRecord(b, g->stream));
+        RB_CUDA(cudaEventSynchronize(b));
+        RB_CUDA(cudaEventElapsedTime(ms, a, b));
+        return RB_OK;
+    };
+    float ms = 0.f;
+    int rc = run(200, &ms);                                  // warm-up + calibration
+    if (rc == RB_OK) rc = run(200, &ms);
+    if (rc == RB_OK) {
+        int iters = (int)std::max(200.0, 200.0 * (millis > 0 ? millis : 50) / std::max(ms, 1e-3f));
+        rc = run(iters, &ms);
+        if (rc == RB_OK) {
+            const double flops = (double)blocks * 256.0 * 8.0 * RB_PEAK_INNER * (double)iters * 2.0;
+            *tflops = flops / (ms * 1e-3) / 1e12;
+        }
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d_out);
+    return rc;
+}
+
+// ===================================================================== Part 1: the reference's six symbols
+static Multibody* mb_load(const char* path) {
+    try {
+        Multibody* mb = new (std::nothrow) Multibody();
+        if (!mb) { fail(RB_ERR_CUDA, "out of host memory"); return nullptr; }
+        std::string err;
+        int rc = rb_model_from_urdf(path, mb->model, err);
+        if (rc != RB_OK) { fail(rc, err); delete mb; return nullptr; }
+        return mb;
+    } catch (const std::exception& e) { fail(RB_ERR_ARG, std::string("exception: ") + e.what()); return nullptr; }
+}
+
+extern "C" Multibody* multibody_new(void) {
+    const char* p = getenv("RIGIDBODY_URDF");
+    return mb_load(p ? p : "assets/fr3.urdf");
+}
+extern "C" Multibody* multibody_new_from_urdf(const char* urdf_path) { return mb_load(urdf_path); }
+
+extern "C" void multibody_free(Multibody* mb) {
+    if (!mb) return;
+    if (mb->gpu) multibody_gpu_free(mb->gpu);
+    delete mb;
+}
+extern "C" void multibody_free_result(double* p) { free(p); }
+
+static RbGpu* mb_engine(const Multibody* cmb) {
+    Multibody* mb = const_cast<Multibody*>(cmb);
+    std::lock_guard<std::mutex> lk(mb->mu);
+    if (!mb->gpu) {
+        const char* d = getenv("RIGIDBODY_DEVICE");
+        if (gpu_create(mb->model, d ? atoi(d) : 0, &mb->gpu) != RB_OK) return nullptr;
+    }
+    return mb->gpu;
+}
+
+template <class F>
+static double* mb_single(const Multibody* mb, size_t out_count, F&& call) {
+    if (!mb) { fail(RB_ERR_NULL, "Multibody handle is NULL"); return nullptr; }
+    RbGpu* g = mb_engine(mb);
+    if (!g) return nullptr;
+    double* out = (double*)malloc(out_count * sizeof(double));
+    if (!out) { fail(RB_ERR_CUDA, "out of host memory"); return nullptr; }
+    if (call(g, out) != RB_OK) { free(out); return nullptr; }
+    return out;
+}
+
+extern "C" double* multibody_rnea(const Multibody* mb, const double* q, const double* dq, const double* ddq) {
+    return mb_single(mb, mb ? mb->model.n : 0, [&](RbGpu* g, double* out) {
+        return multibody_rnea_batch(g, q, dq, ddq, out, 1, 0, RB_LAYOUT_AOS, RB_MEM_HOST, nullptr);
+    });
+}
+extern "C" double* multibody_crba(const Multibody* mb, const double* q) {
+    return mb_single(mb, mb ? (size_t)mb->model.n * mb->model.n : 0, [&](RbGpu* g, double* out) {
+        return multibody_crba_batch(g, q, out, 1, 0, RB_LAYOUT_AOS, RB_MEM_HOST, nullptr);
+    });
+}
+extern "C" double* multibody_fwd_kin(const Multibody* mb, const double* q) {
+    return mb_single(mb, 3, [&](RbGpu* g, double* out) {
+        return multibody_fwd_kin_batch(g, q, out, 1, 0, RB_LAYOUT_AOS, RB_MEM_HOST, nullptr);
+    });
+}
+extern "C" double* multibody_jac(const Multibody* mb, const double* q) {
+    return mb_single(mb, mb ? (size_t)6 * mb->model.n : 0, [&](RbGpu* g, double* out) {
+        return multibody_jac_batch(g, q, out, 1, 0, RB_LAYOUT_AOS, RB_MEM_HOST, nullptr);
+    });
+}

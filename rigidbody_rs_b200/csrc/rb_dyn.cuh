@@ -1,0 +1,396 @@
+// rb_dyn.cuh -- device-side rigid-body algebra, one thread per state, everything in registers.
+//
+// What is computed follows the reference line by line (citations relative to the reference checkout);
+// how it is computed does not: rotations are 3x3 (R_i = R_p * Rz(q_i)) instead of unit quaternions,
+// inertias are the 10-parameter (m, h, I_o) form, the joint loop is unrolled at compile time through a
+// model *policy* M so that a model known at compile time (CtModel) drops every multiplication by an
+// exact 0 or +-1 of its fixed transforms, while a model known only at run time (RtModel) reads the same
+// numbers from the kernel-parameter constant bank.  All arithmetic is fp64 (Real = f64, lib.rs:15).
+#pragma once
+#include "rb_model.h"
+
+#define RB_DI __device__ __forceinline__
+
+template <int V> struct RbIC { static constexpr int value = V; };
+
+// f(RbIC<I>) for I = 0..N-1 (ascending) / N-1..0 (descending), fully unrolled.
+template <int I, int N, class F> RB_DI void rb_for_up(F&& f) {
+    if constexpr (I < N) { f(RbIC<I>{}); rb_for_up<I + 1, N>(f); }
+}
+template <int I, class F> RB_DI void rb_for_down(F&& f) {
+    if constexpr (I >= 0) { f(RbIC<I>{}); rb_for_down<I - 1>(f); }
+}
+
+// ------------------------------------------------------------------ class-tagged scalar ops
+template <int C> RB_DI double k_mul(double k, double x) {
+    if constexpr (C == RB_ZERO) return 0.0;
+    else if constexpr (C == RB_ONE) return x;
+    else if constexpr (C == RB_NEG1) return -x;
+    else return k * x;
+}
+template <int C> RB_DI double k_fma(double k, double x, double acc) {        // acc + k*x
+    if constexpr (C == RB_ZERO) return acc;
+    else if constexpr (C == RB_ONE) return acc + x;
+    else if constexpr (C == RB_NEG1) return acc - x;
+    else return fma(k, x, acc);
+}
+template <int C> RB_DI double k_fnma(double k, double x, double acc) {       // acc - k*x
+    if constexpr (C == RB_ZERO) return acc;
+    else if constexpr (C == RB_ONE) return acc - x;
+    else if constexpr (C == RB_NEG1) return acc + x;
+    else return fma(-k, x, acc);
+}
+template <int C0, int C1, int C2>
+RB_DI double k_dot3(double k0, double k1, double k2, double x0, double x1, double x2) {
+    if constexpr (C0 != RB_ZERO) return k_fma<C2>(k2, x2, k_fma<C1>(k1, x1, k_mul<C0>(k0, x0)));
+    else if constexpr (C1 != RB_ZERO) return k_fma<C2>(k2, x2, k_mul<C1>(k1, x1));
+    else return k_mul<C2>(k2, x2);
+}
+template <int C0, int C1, int C2>
+RB_DI double k_dot3_acc(double acc, double k0, double k1, double k2, double x0, double x1, double x2) {
+    return k_fma<C2>(k2, x2, k_fma<C1>(k1, x1, k_fma<C0>(k0, x0, acc)));
+}
+
+// ------------------------------------------------------------------ model policies
+// Run-time model: values from the kernel parameter (constant bank), nothing known at compile time.
+template <int N_>
+struct RtModel {
+    static constexpr int N = N_;
+    using Param = RbModelK<N_>;
+    template <int I, int F, int K> static constexpr int cls() { return RB_GEN; }
+    template <int I, int F, int K> static RB_DI double val(const Param& p) {
+        if constexpr (F == RB_F_R) return p.jt[I].R[K];
+        else if constexpr (F == RB_F_T) return p.jt[I].t[K];
+        else if constexpr (F == RB_F_M) return K == 0 ? p.jt[I].m : p.jt[I].mc;
+        else if constexpr (F == RB_F_H) return p.jt[I].h[K];
+        else return p.jt[I].I[K];
+    }
+    template <int K> static constexpr int gcls() { return RB_GEN; }
+    template <int K> static RB_DI double g(const Param& p) { return p.g[K]; }
+};
+
+// Compile-time model: Tab supplies `static constexpr int N; static constexpr double T[N][24]; G[3]`
+// with each row laid out exactly like RbJointK (R9 t3 m mc h3 I6 + pad).
+struct RbEmptyParam { int unused; };
+constexpr int rb_classify(double v) { return v == 0.0 ? RB_ZERO : (v == 1.0 ? RB_ONE : (v == -1.0 ? RB_NEG1 : RB_GEN)); }
+template <class Tab>
+struct CtModel {
+    static constexpr int N = Tab::N;
+    using Param = RbEmptyParam;
+    template <int F, int K> static constexpr int off() {
+        return F == RB_F_R ? K : F == RB_F_T ? 9 + K : F == RB_F_M ? 12 + K : F == RB_F_H ? 14 + K : 17 + K;
+    }
+    template <int I, int F, int K> static constexpr int cls() { return rb_classify(Tab::T[I][off<F, K>()]); }
+    template <int I, int F, int K> static RB_DI double val(const Param&) {
+        constexpr double v = Tab::T[I][off<F, K>()];
+        return v;
+    }
+    template <int K> static constexpr int gcls() { return rb_classify(Tab::G[K]); }
+    template <int K> static RB_DI double g(const Param&) { constexpr double v = Tab::G[K]; return v; }
+};
+
+#define KV(I, F, K) M::template val<I, F, K>(p)
+#define KC(I, F, K) M::template cls<I, F, K>()
+
+// ------------------------------------------------------------------ spatial transforms
+// Motion vector parent -> child across joint I (spatial.rs:110-116 applied with X_I = parent o Rz(q)):
+//   rot' = E rot, lin' = E (lin - t x rot), E = Rz(q)^T R_p^T.
+template <class M, int I>
+RB_DI void rb_motion(const typename M::Param& p, double s, double c, double (&lin)[3], double (&rot)[3]) {
+    const double t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
+    const double d0 = k_fma<KC(I, RB_F_T, 2)>(t2, rot[1], k_fnma<KC(I, RB_F_T, 1)>(t1, rot[2], lin[0]));
+    const double d1 = k_fma<KC(I, RB_F_T, 0)>(t0, rot[2], k_fnma<KC(I, RB_F_T, 2)>(t2, rot[0], lin[1]));
+    const double d2 = k_fma<KC(I, RB_F_T, 1)>(t1, rot[0], k_fnma<KC(I, RB_F_T, 0)>(t0, rot[1], lin[2]));
+    // y = R_p^T x : y_j = sum_k R[k][j] x_k
+    const double y0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), d0, d1, d2);
+    const double y1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), d0, d1, d2);
+    const double y2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), d0, d1, d2);
+    const double w0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), rot[0], rot[1], rot[2]);
+    const double w1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), rot[0], rot[1], rot[2]);
+    const double w2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), rot[0], rot[1], rot[2]);
+    // Rz(q)^T
+    lin[0] = fma(c, y0, s * y1);  lin[1] = fma(c, y1, -(s * y0));  lin[2] = y2;
+    rot[0] = fma(c, w0, s * w1);  rot[1] = fma(c, w1, -(s * w0));  rot[2] = w2;
+}
+
+// Force child -> parent across joint I (spatial.rs:242-248 applied to X_I^-1, as multibody.rs:147,165 do):
+//   lin' = R lin, rot' = R rot + t x (R lin), R = R_p Rz(q).   Result written to (ol, orr).
+template <class M, int I>
+RB_DI void rb_force(const typename M::Param& p, double s, double c, const double (&lin)[3], const double (&rot)[3],
+                    double (&ol)[3], double (&orr)[3]) {
+    const double y0 = fma(c, lin[0], -(s * lin[1])), y1 = fma(s, lin[0], c * lin[1]), y2 = lin[2];
+    const double w0 = fma(c, rot[0], -(s * rot[1])), w1 = fma(s, rot[0], c * rot[1]), w2 = rot[2];
+    const double L0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), y0, y1, y2);
+    const double L1 = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), y0, y1, y2);
+    const double L2 = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), y0, y1, y2);
+    const double t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
+    double r0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), w0, w1, w2);
+    double r1 = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), w0, w1, w2);
+    double r2 = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), w0, w1, w2);
+    r0 = k_fnma<KC(I, RB_F_T, 2)>(t2, L1, k_fma<KC(I, RB_F_T, 1)>(t1, L2, r0));
+    r1 = k_fnma<KC(I, RB_F_T, 0)>(t0, L2, k_fma<KC(I, RB_F_T, 2)>(t2, L0, r1));
+    r2 = k_fnma<KC(I, RB_F_T, 1)>(t1, L0, k_fma<KC(I, RB_F_T, 0)>(t0, L1, r2));
+    ol[0] = L0; ol[1] = L1; ol[2] = L2;
+    orr[0] = r0; orr[1] = r1; orr[2] = r2;
+}
+
+// f = I_I * a  (inertia.rs:107-117):  lin = m a.lin - h x a.rot ; rot = I_o a.rot + h x a.lin
+template <class M, int I>
+RB_DI void rb_inertia_mul(const typename M::Param& p, const double (&al)[3], const double (&ar)[3],
+                          double (&fl)[3], double (&fr)[3]) {
+    const double m = KV(I, RB_F_M, 0);
+    const double h0 = KV(I, RB_F_H, 0), h1 = KV(I, RB_F_H, 1), h2 = KV(I, RB_F_H, 2);
+    fl[0] = fma(h2, ar[1], fma(-h1, ar[2], m * al[0]));
+    fl[1] = fma(h0, ar[2], fma(-h2, ar[0], m * al[1]));
+    fl[2] = fma(h1, ar[0], fma(-h0, ar[1], m * al[2]));
+    const double Ixx = KV(I, RB_F_I, 0), Ixy = KV(I, RB_F_I, 1), Ixz = KV(I, RB_F_I, 2);
+    const double Iyy = KV(I, RB_F_I, 3), Iyz = KV(I, RB_F_I, 4), Izz = KV(I, RB_F_I, 5);
+    fr[0] = fma(-h2, al[1], fma(h1, al[2], fma(Ixz, ar[2], fma(Ixy, ar[1], Ixx * ar[0]))));
+    fr[1] = fma(-h0, al[2], fma(h2, al[0], fma(Iyz, ar[2], fma(Iyy, ar[1], Ixy * ar[0]))));
+    fr[2] = fma(-h1, al[0], fma(h0, al[1], fma(Izz, ar[2], fma(Iyz, ar[1], Ixz * ar[0]))));
+}
+
+// sin/cos of every joint angle (joint.rs:48-50 builds the same rotation as a quaternion).
+template <int N>
+RB_DI void rb_sincos_all(const double (&q)[N], double (&s)[N], double (&c)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) sincos(q[i], &s[i], &c[i]);
+}
+
+// ------------------------------------------------------------------ RNEA  (multibody.rs:111-153)
+// tau = ID(q, dq, ddq).  HAS_DDQ = false is the bias-force call rnea(q, dq, 0) used by forward dynamics.
+template <class M, bool HAS_DDQ>
+RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
+                   const double (&dq)[M::N], const double (&ddq)[M::N], double (&tau)[M::N]) {
+    constexpr int N = M::N;
+    double fl[N][3], fr[N][3];
+    double vl[3] = {0.0, 0.0, 0.0}, vr[3] = {0.0, 0.0, 0.0};                        // :116
+    double al[3] = {M::template g<0>(p), M::template g<1>(p), M::template g<2>(p)}; // :117-120
+    double ar[3] = {0.0, 0.0, 0.0};
+    rb_for_up<0, N>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        if constexpr (I == 0) {
+            // v_in = 0, a_in = (g, 0): only the gravity vector needs transforming.
+            double zr[3] = {0.0, 0.0, 0.0};
+            rb_motion<M, I>(p, s[I], c[I], al, zr);
+            vr[2] = dq[I];                                                           // :130
+            if constexpr (HAS_DDQ) ar[2] = ddq[I];                                   // :133  (:135-138 vanish: v = (0; 0,0,dq))
+        } else {
+            rb_motion<M, I>(p, s[I], c[I], vl, vr);                                  // :129
+            vr[2] += dq[I];                                                          // :130
+            rb_motion<M, I>(p, s[I], c[I], al, ar);                                  // :132
+            if constexpr (HAS_DDQ) ar[2] += ddq[I];                                  // :133
+            al[0] = fma(vl[1], dq[I], al[0]);                                        // :135-138
+            al[1] = fma(-vl[0], dq[I], al[1]);
+            ar[0] = fma(vr[1], dq[I], ar[0]);
+            ar[1] = fma(-vr[0], dq[I], ar[1]);
+        }
+        double Il[3], Ir[3];
+        rb_inertia_mul<M, I>(p, al, ar, fl[I], fr[I]);                               // :140  I a
+        rb_inertia_mul<M, I>(p, vl, vr, Il, Ir);                                     //       I v
+        // + v x* (I v)  (spatial.rs:129-134): lin = w x Il ; rot = w x Ir + vl x Il
+        fl[I][0] = fma(vr[1], Il[2], fma(-vr[2], Il[1], fl[I][0]));
+        fl[I][1] = fma(vr[2], Il[0], fma(-vr[0], Il[2], fl[I][1]));
+        fl[I][2] = fma(vr[0], Il[1], fma(-vr[1], Il[0], fl[I][2]));
+        fr[I][0] = fma(vl[1], Il[2], fma(-vl[2], Il[1], fma(vr[1], Ir[2], fma(-vr[2], Ir[1], fr[I][0]))));
+        fr[I][1] = fma(vl[2], Il[0], fma(-vl[0], Il[2], fma(vr[2], Ir[0], fma(-vr[0], Ir[2], fr[I][1]))));
+        fr[I][2] = fma(vl[0], Il[1], fma(-vl[1], Il[0], fma(vr[0], Ir[1], fma(-vr[1], Ir[0], fr[I][2]))));
+    });
+    rb_for_down<N - 1>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        tau[I] = fr[I][2];                                                           // :144
+        if constexpr (I > 0) {
+            double tl[3], tr[3];
+            rb_force<M, I>(p, s[I], c[I], fl[I], fr[I], tl, tr);                     // :147
+            fl[I - 1][0] += tl[0]; fl[I - 1][1] += tl[1]; fl[I - 1][2] += tl[2];     // :148
+            fr[I - 1][0] += tr[0]; fr[I - 1][1] += tr[1]; fr[I - 1][2] += tr[2];
+        }
+    });
+}
+
+// ------------------------------------------------------------------ CRBA  (multibody.rs:155-174)
+// H[j][i] for j <= i (row j, column i): diagonal + strict upper triangle, exactly what the reference writes.
+// Composite inertia kept as (h, I_o) in the frame of link i; its mass is the model constant mc_i.
+// The reference carries (m, com, I_c) and rebuilds I_o with from_com/from_origin (inertia.rs:21-51,81-105);
+// the 10-parameter update below is the same map: with R = R_p Rz(q), u = R h + (m/2) t,
+//   h' = R h + m t,   I_o' = R I_o R^T - (t u^T + u t^T) + 2 (t.u) Id,   then add link i-1's own (h, I_o).
+template <class M>
+RB_DI void rb_crba(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
+                   double (&H)[M::N][M::N]) {
+    constexpr int N = M::N;
+    double h[3] = {KV(N - 1, RB_F_H, 0), KV(N - 1, RB_F_H, 1), KV(N - 1, RB_F_H, 2)};            // :157
+    double Ixx = KV(N - 1, RB_F_I, 0), Ixy = KV(N - 1, RB_F_I, 1), Ixz = KV(N - 1, RB_F_I, 2);
+    double Iyy = KV(N - 1, RB_F_I, 3), Iyz = KV(N - 1, RB_F_I, 4), Izz = KV(N - 1, RB_F_I, 5);
+    rb_for_down<N - 1>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        H[I][I] = Izz;                                                               // :161
+        double Fl[3] = {-h[1], h[0], 0.0};                                           // :162  F = I^c * S_z
+        double Fr[3] = {Ixz, Iyz, Izz};
+        rb_for_down<I - 1>([&](auto jc) {
+            constexpr int J = decltype(jc)::value;
+            double ol[3], orr[3];
+            rb_force<M, J + 1>(p, s[J + 1], c[J + 1], Fl, Fr, ol, orr);              // :165
+            Fl[0] = ol[0]; Fl[1] = ol[1]; Fl[2] = ol[2];
+            Fr[0] = orr[0]; Fr[1] = orr[1]; Fr[2] = orr[2];
+            H[J][I] = Fr[2];                                                         // :166
+        });
+        if constexpr (I > 0) {                                                       // :169-171
+            const double si = s[I], ci = c[I];
+            // Rz(q): h, I_o
+            const double g0 = fma(ci, h[0], -(si * h[1])), g1 = fma(si, h[0], ci * h[1]), g2 = h[2];
+            const double cs = ci * si, s2 = cs + cs, c2 = fma(ci, ci, -(si * si));
+            const double hm = 0.5 * (Ixx - Iyy), hp = 0.5 * (Ixx + Iyy);
+            const double u_ = fma(hm, c2, -(Ixy * s2));
+            const double a = hp + u_, e = hp - u_, b = fma(hm, s2, Ixy * c2);
+            const double d = fma(ci, Ixz, -(si * Iyz)), f = fma(si, Ixz, ci * Iyz), g = Izz;
+            // R_p: h'' = R_p g ; I'' = R_p A R_p^T with A = [[a,b,d],[b,e,f],[d,f,g]]
+#define RR(r, k) KV(I, RB_F_R, 3 * (r) + (k))
+#define RC(r, k) KC(I, RB_F_R, 3 * (r) + (k))
+            const double q0 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), g0, g1, g2);
+            const double q1 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), g0, g1, g2);
+            const double q2 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), g0, g1, g2);
+            // P = R_p A (rows of R_p against columns of symmetric A)
+            const double P00 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), a, b, d);
+            const double P01 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), b, e, f);
+            const double P02 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), d, f, g);
+            const double P10 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), a, b, d);
+            const double P11 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), b, e, f);
+            const double P12 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), d, f, g);
+            const double P20 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), a, b, d);
+            const double P21 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), b, e, f);
+            const double P22 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), d, f, g);
+            // I'' = P R_p^T, six unique entries: I''[r][c] = sum_k P[r][k] R_p[c][k]
+            double Jxx = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), P00, P01, P02);
+            double Jxy = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), P00, P01, P02);
+            double Jxz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P00, P01, P02);
+            double Jyy = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), P10, P11, P12);
+            double Jyz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P10, P11, P12);
+            double Jzz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P20, P21, P22);
+#undef RR
+#undef RC
+            // translation by t with composite mass mc_I:  u = h'' + (mc/2) t
+            const double mc = KV(I, RB_F_M, 1);
+            const double t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
+            constexpr int T0 = KC(I, RB_F_T, 0), T1 = KC(I, RB_F_T, 1), T2 = KC(I, RB_F_T, 2);
+            const double hmc = 0.5 * mc;
+            const double u0 = k_fma<T0>(t0, hmc, q0), u1 = k_fma<T1>(t1, hmc, q1), u2 = k_fma<T2>(t2, hmc, q2);
+            const double tu0 = k_mul<T0>(t0, u0), tu1 = k_mul<T1>(t1, u1), tu2 = k_mul<T2>(t2, u2);
+            // diag: + 2 (t.u - t_k u_k);  off-diag: - (t_r u_c + t_c u_r);  then add link I-1's own inertia
+            Ixx = fma(2.0, tu1 + tu2, Jxx) + KV(I - 1, RB_F_I, 0);
+            Iyy = fma(2.0, tu0 + tu2, Jyy) + KV(I - 1, RB_F_I, 3);
+            Izz = fma(2.0, tu0 + tu1, Jzz) + KV(I - 1, RB_F_I, 5);
+            Ixy = k_fnma<T1>(t1, u0, k_fnma<T0>(t0, u1, Jxy)) + KV(I - 1, RB_F_I, 1);
+            Ixz = k_fnma<T2>(t2, u0, k_fnma<T0>(t0, u2, Jxz)) + KV(I - 1, RB_F_I, 2);
+            Iyz = k_fnma<T2>(t2, u1, k_fnma<T1>(t1, u2, Jyz)) + KV(I - 1, RB_F_I, 4);
+            h[0] = k_fma<T0>(t0, mc, q0) + KV(I - 1, RB_F_H, 0);
+            h[1] = k_fma<T1>(t1, mc, q1) + KV(I - 1, RB_F_H, 1);
+            h[2] = k_fma<T2>(t2, mc, q2) + KV(I - 1, RB_F_H, 2);
+        }
+    });
+}
+
+// ------------------------------------------------------------------ solve  H x = b, H SPD given by its upper triangle
+// In-place right-looking LDL^T (the square-root-free Cholesky), then the two triangular solves.
+// Returns false if a pivot is not positive (H not SPD).
+template <int N>
+RB_DI bool rb_ldlt_solve(double (&A)[N][N], double (&x)[N]) {
+    double dinv[N];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double d = A[j][j];
+        ok = ok && (d > 0.0);
+        dinv[j] = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            const double l = A[j][i] * dinv[j];
+#pragma unroll
+            for (int k = i; k < N; ++k) A[i][k] = fma(-l, A[j][k], A[i][k]);
+            A[j][i] = l;                     // U[j][i] = L[i][j]
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {            // L y = b
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) x[i] = fma(-A[j][i], x[j], x[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] *= dinv[j];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {       // L^T x = z
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) x[i] = fma(-A[i][k], x[k], x[i]);
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------ forward dynamics
+// qdd = solve(sym(crba(q)), tau - rnea(q, dq, 0)); sin/cos computed once and shared by both halves.
+template <class M>
+RB_DI bool rb_forward_dynamics(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
+                               const double (&dq)[M::N], const double (&tau)[M::N], double (&qdd)[M::N]) {
+    constexpr int N = M::N;
+    {
+        double bias[N];
+        rb_rnea<M, false>(p, s, c, dq, dq /*unused*/, bias);
+#pragma unroll
+        for (int i = 0; i < N; ++i) qdd[i] = tau[i] - bias[i];
+    }
+    double H[N][N];
+    rb_crba<M>(p, s, c, H);
+    return rb_ldlt_solve<N>(H, qdd);
+}
+
+// ------------------------------------------------------------------ forward kinematics / Jacobian
+// Tip pose in the base frame, composed tip -> base as multibody.rs:87-93 does: p <- R_i p + t_i.
+template <class M>
+RB_DI void rb_fwd_kin(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N], double (&pos)[3]) {
+    constexpr int N = M::N;
+    pos[0] = 0.0; pos[1] = 0.0; pos[2] = 0.0;
+    rb_for_down<N - 1>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        const double y0 = fma(c[I], pos[0], -(s[I] * pos[1])), y1 = fma(s[I], pos[0], c[I] * pos[1]), y2 = pos[2];
+        pos[0] = k_dot3_acc<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_T, 0), KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), y0, y1, y2);
+        pos[1] = k_dot3_acc<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_T, 1), KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), y0, y1, y2);
+        pos[2] = k_dot3_acc<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_T, 2), KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), y0, y1, y2);
+    });
+}
+
+// Tip-frame Jacobian (multibody.rs:95-108): column i = S_z carried from frame i to the tip frame by the
+// motion transform of the accumulated pose (A, r) of the tip in frame i:  rot = A^T z, lin = A^T (-(r x z)).
+// J is [N][6]: J[i][0..2] lin, J[i][3..5] rot.
+template <class M>
+RB_DI void rb_jac(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N], double (&J)[M::N][6]) {
+    constexpr int N = M::N;
+    double A[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
+    double r[3] = {0.0, 0.0, 0.0};
+    rb_for_down<N - 1>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        // -(r x z) = (-r1, r0, 0)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            J[I][k] = fma(A[1][k], r[0], -(A[0][k] * r[1]));
+            J[I][3 + k] = A[2][k];
+        }
+        if constexpr (I > 0) {
+            // (A, r) <- X_I o (A, r):  A <- R_p Rz A,  r <- R_p Rz r + t
+            double B[3][3], y[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                B[0][k] = fma(c[I], A[0][k], -(s[I] * A[1][k]));
+                B[1][k] = fma(s[I], A[0][k], c[I] * A[1][k]);
+                B[2][k] = A[2][k];
+            }
+            y[0] = fma(c[I], r[0], -(s[I] * r[1])); y[1] = fma(s[I], r[0], c[I] * r[1]); y[2] = r[2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                A[0][k] = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), B[0][k], B[1][k], B[2][k]);
+                A[1][k] = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), B[0][k], B[1][k], B[2][k]);
+                A[2][k] = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), B[0][k], B[1][k], B[2][k]);
+            }
+            r[0] = k_dot3_acc<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_T, 0), KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), y[0], y[1], y[2]);
+            r[1] = k_dot3_acc<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_T, 1), KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), y[0], y[1], y[2]);
+            r[2] = k_dot3_acc<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_T, 2), KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), y[0], y[1], y[2]);
+        }
+    });
+}

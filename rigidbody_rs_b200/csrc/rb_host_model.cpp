@@ -1,0 +1,324 @@
+// rb_host_model.cpp -- see rb_host_model.h.  Plain C++17, no CUDA.
+#include "rb_host_model.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+namespace {
+
+// ------------------------------------------------------------------ a very small XML reader
+// Enough for URDF: elements, attributes, comments, declarations.  No entities, no CDATA.
+struct XmlNode {
+    std::string tag;
+    std::map<std::string, std::string> attr;
+    std::vector<XmlNode> kids;
+    const XmlNode* child(const char* t) const {
+        for (const auto& k : kids) if (k.tag == t) return &k;
+        return nullptr;
+    }
+    const char* get(const char* a) const {
+        auto it = attr.find(a);
+        return it == attr.end() ? nullptr : it->second.c_str();
+    }
+};
+
+struct XmlParser {
+    const std::string& s;
+    size_t i = 0;
+    std::string err;
+    explicit XmlParser(const std::string& src) : s(src) {}
+
+    void skip_ws() { while (i < s.size() && isspace((unsigned char)s[i])) ++i; }
+    bool starts(const char* lit) const { return s.compare(i, strlen(lit), lit) == 0; }
+
+    // Skips text, comments, <? ?> and <! > until the next real tag.  Returns false at end of input.
+    bool next_tag() {
+        while (i < s.size()) {
+            size_t lt = s.find('<', i);
+            if (lt == std::string::npos) { i = s.size(); return false; }
+            i = lt;
+            if (starts("<!--")) {
+                size_t e = s.find("-->", i + 4);
+                if (e == std::string::npos) { err = "unterminated comment"; return false; }
+                i = e + 3;
+            } else if (starts("<?")) {
+                size_t e = s.find("?>", i + 2);
+                if (e == std::string::npos) { err = "unterminated declaration"; return false; }
+                i = e + 2;
+            } else if (starts("<!")) {
+                size_t e = s.find('>', i + 2);
+                if (e == std::string::npos) { err = "unterminated <!"; return false; }
+                i = e + 1;
+            } else {
+                return true;
+            }
+        }
+        return false;
+    }
+
+    static bool name_char(char c) { return isalnum((unsigned char)c) || c == '_' || c == '-' || c == ':' || c == '.'; }
+
+    // Parses the element starting at s[i] == '<'.  On return i is just past its end tag.
+    bool element(XmlNode& out) {
+        ++i;  // '<'
+        size_t b = i;
+        while (i < s.size() && name_char(s[i])) ++i;
+        out.tag = s.substr(b, i - b);
+        if (out.tag.empty()) { err = "empty tag name"; return false; }
+        for (;;) {
+            skip_ws();
+            if (i >= s.size()) { err = "unterminated tag <" + out.tag; return false; }
+            if (s[i] == '/') {
+                if (i + 1 < s.size() && s[i + 1] == '>') { i += 2; return true; }
+                err = "stray '/' in <" + out.tag; return false;
+            }
+            if (s[i] == '>') { ++i; break; }
+            size_t ab = i;
+            while (i < s.size() && name_char(s[i])) ++i;
+            std::string an = s.substr(ab, i - ab);
+            skip_ws();
+            if (an.empty() || i >= s.size() || s[i] != '=') { err = "bad attribute in <" + out.tag; return false; }
+            ++i; skip_ws();
+            if (i >= s.size() || (s[i] != '"' && s[i] != '\'')) { err = "unquoted attribute in <" + out.tag; return false; }
+            char qc = s[i++];
+            size_t vb = i;
+            while (i < s.size() && s[i] != qc) ++i;
+            if (i >= s.size()) { err = "unterminated attribute value in <" + out.tag; return false; }
+            out.attr[an] = s.substr(vb, i - vb);
+            ++i;
+        }
+        // children until </tag>
+        for (;;) {
+            if (!next_tag()) { if (err.empty()) err = "missing </" + out.tag + ">"; return false; }
+            if (s[i + 1] == '/') {
+                size_t e = s.find('>', i);
+                if (e == std::string::npos) { err = "unterminated end tag"; return false; }
+                std::string en = s.substr(i + 2, e - i - 2);
+                while (!en.empty() && isspace((unsigned char)en.back())) en.pop_back();
+                if (en != out.tag) { err = "mismatched </" + en + "> for <" + out.tag + ">"; return false; }
+                i = e + 1;
+                return true;
+            }
+            XmlNode k;
+            if (!element(k)) return false;
+            out.kids.push_back(std::move(k));
+        }
+    }
+};
+
+bool parse_floats(const char* s, int n, double* out) {
+    if (!s) { for (int k = 0; k < n; ++k) out[k] = 0.0; return true; }   // xurdf: missing attribute -> zeros
+    const char* p = s;
+    for (int k = 0; k < n; ++k) {
+        char* e = nullptr;
+        out[k] = strtod(p, &e);
+        if (e == p) return false;
+        p = e;
+    }
+    while (*p && isspace((unsigned char)*p)) ++p;
+    return *p == 0;
+}
+
+double snap(double x) {
+    // A roll of +-pi/2 in fp64 leaves cos = 6.1e-17 instead of 0 (and the reference's quaternion round trip
+    // leaves ~2e-16): treat entries within 2^-50 of 0 / +-1 as exact so the specialised kernels can drop them.
+    const double eps = 8.881784197001252e-16;
+    if (std::fabs(x) < eps) return 0.0;
+    if (std::fabs(x - 1.0) < eps) return 1.0;
+    if (std::fabs(x + 1.0) < eps) return -1.0;
+    return x;
+}
+
+void finish_model(RbHostModel& m) {
+    // composite masses, tip to base (multibody.rs:157,170: masses only ever add)
+    double acc = 0.0;
+    for (int i = m.n - 1; i >= 0; --i) { acc += m.jt[i].m; m.jt[i].mc = acc; }
+}
+
+// I_o = I_c + m [c]x [c]x^T  (inertia.rs:31-32), six unique entries
+void origin_inertia(double mass, const double c[3], const double Ic[9], double I6[6]) {
+    const double cx = c[0], cy = c[1], cz = c[2];
+    // [c]x [c]x^T = (c.c) Id - c c^T
+    const double cc = cx * cx + cy * cy + cz * cz;
+    I6[0] = Ic[0] + mass * (cc - cx * cx);
+    I6[1] = Ic[1] + mass * (-cx * cy);
+    I6[2] = Ic[2] + mass * (-cx * cz);
+    I6[3] = Ic[4] + mass * (cc - cy * cy);
+    I6[4] = Ic[5] + mass * (-cy * cz);
+    I6[5] = Ic[8] + mass * (cc - cz * cz);
+}
+
+}  // namespace
+
+int rb_model_from_urdf(const char* path, RbHostModel& out, std::string& err) {
+    if (!path) { err = "urdf path is NULL"; return RB_ERR_NULL; }
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { err = std::string("cannot open URDF '") + path + "'"; return RB_ERR_URDF; }
+    std::stringstream ss; ss << f.rdbuf();
+    const std::string src = ss.str();
+    XmlParser xp(src);
+    XmlNode robot;
+    bool found = false;
+    while (xp.next_tag()) {
+        XmlNode n;
+        if (!xp.element(n)) { err = "URDF parse error: " + xp.err; return RB_ERR_URDF; }
+        if (n.tag == "robot") { robot = std::move(n); found = true; break; }
+    }
+    if (!found) { err = xp.err.empty() ? "no <robot> element" : "URDF parse error: " + xp.err; return RB_ERR_URDF; }
+
+    // xurdf: `links` and `joints` are the <robot>'s direct children in document order
+    struct L { double mass = 0.0, com[3] = {0, 0, 0}, six[6] = {0, 0, 0, 0, 0, 0}; };
+    struct J { std::string name, type; double xyz[3], rpy[3], axis[3], lim[4]; };
+    std::vector<L> links; std::vector<J> joints;
+    for (const auto& el : robot.kids) {
+        if (el.tag == "link") {
+            L l;
+            if (const XmlNode* in = el.child("inertial")) {
+                const XmlNode* o = in->child("origin");
+                const XmlNode* ms = in->child("mass");
+                const XmlNode* ie = in->child("inertia");
+                if (!parse_floats(o ? o->get("xyz") : nullptr, 3, l.com)) { err = "bad inertial origin"; return RB_ERR_URDF; }
+                if (!ms || !ms->get("value") || !parse_floats(ms->get("value"), 1, &l.mass)) { err = "bad <mass>"; return RB_ERR_URDF; }
+                static const char* keys[6] = {"ixx", "ixy", "ixz", "iyy", "iyz", "izz"};
+                for (int k = 0; k < 6; ++k)
+                    if (!ie || !ie->get(keys[k]) || !parse_floats(ie->get(keys[k]), 1, &l.six[k])) { err = "bad <inertia>"; return RB_ERR_URDF; }
+            }
+            links.push_back(l);
+        } else if (el.tag == "joint") {
+            J j;
+            j.name = el.get("name") ? el.get("name") : "";
+            j.type = el.get("type") ? el.get("type") : "";
+            const XmlNode* o = el.child("origin");
+            const XmlNode* a = el.child("axis");
+            const XmlNode* lm = el.child("limit");
+            if (!parse_floats(o ? o->get("xyz") : nullptr, 3, j.xyz) || !parse_floats(o ? o->get("rpy") : nullptr, 3, j.rpy)) {
+                err = "bad joint origin in '" + j.name + "'"; return RB_ERR_URDF;
+            }
+            j.axis[0] = 1.0; j.axis[1] = 0.0; j.axis[2] = 0.0;
+            if (a && a->get("xyz") && !parse_floats(a->get("xyz"), 3, j.axis)) { err = "bad joint axis in '" + j.name + "'"; return RB_ERR_URDF; }
+            static const char* lk[4] = {"lower", "upper", "velocity", "effort"};
+            for (int k = 0; k < 4; ++k) { j.lim[k] = 0.0; if (lm && lm->get(lk[k])) parse_floats(lm->get(lk[k]), 1, &j.lim[k]); }
+            joints.push_back(j);
+        }
+    }
+
+    out = RbHostModel();
+    const size_t pairs = std::min(links.size(), joints.size());          // zip (multibody.rs:70)
+    for (size_t k = 0; k < pairs; ++k) {
+        const J& j = joints[k];
+        const L& l = links[k];
+        if (j.type.find("fixed") != std::string::npos) continue;          // multibody.rs:71
+        if (out.n >= RB_MAX_JOINTS) { err = "more than RB_MAX_JOINTS movable joints"; return RB_ERR_UNSUPPORTED; }
+        const double an = std::sqrt(j.axis[0] * j.axis[0] + j.axis[1] * j.axis[1] + j.axis[2] * j.axis[2]);
+        // rnea/crba hard-code the z motion subspace (multibody.rs:29,130); parity exists only for z axes.
+        if (!(an > 0.0) || std::fabs(j.axis[0] / an) > 1e-12 || std::fabs(j.axis[1] / an) > 1e-12 || j.axis[2] / an < 0.0) {
+            err = "joint '" + j.name + "': only +z revolute axes are supported (the reference hard-codes z)";
+            return RB_ERR_UNSUPPORTED;
+        }
+        RbJointK r{};
+        // Rotation3::from_euler_angles(roll, pitch, yaw) = Rz(yaw) Ry(pitch) Rx(roll)   (joint.rs:59-63)
+        const double sr = std::sin(j.rpy[0]), cr = std::cos(j.rpy[0]);
+        const double sp = std::sin(j.rpy[1]), cp = std::cos(j.rpy[1]);
+        const double sy = std::sin(j.rpy[2]), cy = std::cos(j.rpy[2]);
+        const double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                             sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                             -sp,     cp * sr,                cp * cr};
+        for (int e = 0; e < 9; ++e) r.R[e] = snap(R[e]);
+        for (int e = 0; e < 3; ++e) r.t[e] = j.xyz[e];
+        r.m = l.mass;
+        for (int e = 0; e < 3; ++e) r.h[e] = l.mass * l.com[e];
+        const double Ic[9] = {l.six[0], l.six[1], l.six[2], l.six[1], l.six[3], l.six[4], l.six[2], l.six[4], l.six[5]};
+        origin_inertia(l.mass, l.com, Ic, r.I);                            // joint.rs:66
+        out.jt.push_back(r);
+        out.lim.lower[out.n] = j.lim[0]; out.lim.upper[out.n] = j.lim[1];
+        out.lim.velocity[out.n] = j.lim[2]; out.lim.effort[out.n] = j.lim[3];
+        out.names.push_back(j.name);
+        ++out.n;
+    }
+    if (out.n == 0) { err = "URDF holds no movable joint"; return RB_ERR_URDF; }
+    finish_model(out);
+    return RB_OK;
+}
+
+int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err) {
+    if (!d) { err = "descriptor is NULL"; return RB_ERR_NULL; }
+    if (d->n_joints < 1) { err = "n_joints must be >= 1"; return RB_ERR_ARG; }
+    if (d->n_joints > RB_MAX_JOINTS) { err = "n_joints exceeds RB_MAX_JOINTS"; return RB_ERR_UNSUPPORTED; }
+    if (!d->parent_rot || !d->parent_trans || !d->mass || !d->com || !d->inertia_com) {
+        err = "descriptor array is NULL"; return RB_ERR_NULL;
+    }
+    out = RbHostModel();
+    out.n = d->n_joints;
+    for (int i = 0; i < out.n; ++i) {
+        if (d->parent && d->parent[i] != i - 1) {
+            err = "only serial chains are supported (parent[i] must be i-1; the reference is serial-only)";
+            return RB_ERR_UNSUPPORTED;
+        }
+        if (d->axis) {
+            const double* a = d->axis + 3 * i;
+            if (std::fabs(a[0]) > 1e-12 || std::fabs(a[1]) > 1e-12 || std::fabs(a[2] - 1.0) > 1e-12) {
+                err = "only +z joint axes are supported (the reference hard-codes z)";
+                return RB_ERR_UNSUPPORTED;
+            }
+        }
+        RbJointK r{};
+        const double* R = d->parent_rot + 9 * i;
+        // must be a rotation: R R^T = Id within 1e-9
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                double dot = 0.0;
+                for (int k = 0; k < 3; ++k) dot += R[3 * a + k] * R[3 * b + k];
+                if (!(std::fabs(dot - (a == b ? 1.0 : 0.0)) < 1e-9)) { err = "parent_rot is not a rotation matrix"; return RB_ERR_ARG; }
+            }
+        for (int e = 0; e < 9; ++e) r.R[e] = snap(R[e]);
+        for (int e = 0; e < 3; ++e) r.t[e] = d->parent_trans[3 * i + e];
+        r.m = d->mass[i];
+        if (!(r.m > 0.0) || !std::isfinite(r.m)) { err = "link mass must be positive and finite"; return RB_ERR_ARG; }
+        for (int e = 0; e < 3; ++e) r.h[e] = r.m * d->com[3 * i + e];
+        origin_inertia(r.m, d->com + 3 * i, d->inertia_com + 9 * i, r.I);
+        out.jt.push_back(r);
+        out.lim.lower[i] = -3.141592653589793; out.lim.upper[i] = 3.141592653589793;
+        out.lim.velocity[i] = 2.0; out.lim.effort[i] = 50.0;
+        out.names.push_back("joint" + std::to_string(i + 1));
+    }
+    for (int k = 0; k < 3; ++k) {
+        if (!std::isfinite(d->gravity[k])) { err = "gravity must be finite"; return RB_ERR_ARG; }
+        out.g[k] = d->gravity[k];
+    }
+    finish_model(out);
+    return RB_OK;
+}
+
+std::vector<double> rb_model_flat(const RbHostModel& m) {
+    std::vector<double> v((size_t)m.n * 24 + 3);
+    static_assert(sizeof(RbJointK) == 24 * sizeof(double), "RbJointK must be 24 doubles");
+    memcpy(v.data(), m.jt.data(), (size_t)m.n * sizeof(RbJointK));
+    for (int k = 0; k < 3; ++k) v[(size_t)m.n * 24 + k] = m.g[k];
+    return v;
+}
+
+std::string rb_model_emit_header(const RbHostModel& m, const char* tab_name) {
+    std::vector<double> flat = rb_model_flat(m);
+    std::string o;
+    char buf[96];
+    o += "// generated by rb_modelgen -- do not edit\n#pragma once\n";
+    o += std::string("struct ") + tab_name + " {\n";
+    snprintf(buf, sizeof buf, "    static constexpr int N = %d;\n", m.n); o += buf;
+    o += "    static constexpr double T[N][24] = {\n";
+    for (int i = 0; i < m.n; ++i) {
+        o += "        {";
+        for (int k = 0; k < 24; ++k) {
+            snprintf(buf, sizeof buf, "%a%s", flat[(size_t)i * 24 + k], k == 23 ? "" : ", "); o += buf;
+        }
+        o += "},\n";
+    }
+    o += "    };\n";
+    snprintf(buf, sizeof buf, "    static constexpr double G[3] = {%a, %a, %a};\n", m.g[0], m.g[1], m.g[2]); o += buf;
+    o += "};\n";
+    return o;
+}

@@ -1,0 +1,30 @@
+// rb_host_model.h -- host-side model loading: URDF / RbChainDesc -> flattened RbJointK rows.
+//
+// Mirrors what the reference does once at load time:
+//   Multibody::from_urdf           rigidbody/src/multibody.rs:65-77   (zip k-th joint with k-th link, drop "fixed")
+//   RevoluteJoint::from_xurdf_joint rigidbody/src/joint.rs:53-68      (axis, parent isometry, Inertia::from_com)
+//   Inertia::from_com              rigidbody/src/inertia.rs:21-35     (I_o = I_c + m [c]x [c]x^T)
+#pragma once
+#include <string>
+#include <vector>
+#include "rb_model.h"
+#include "../../include/rigidbody.h"
+
+struct RbHostModel {
+    int n = 0;
+    std::vector<RbJointK> jt;
+    double g[3] = {0.0, 0.0, 9.81};          // multibody.rs:118
+    RbJointLimits lim{};
+    std::vector<std::string> names;
+};
+
+// Returns RB_OK or an RbStatus error with a message in `err`.
+int rb_model_from_urdf(const char* path, RbHostModel& out, std::string& err);
+int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err);
+
+// Emits a C++ header defining `struct <tab_name> { N, T[N][24], G[3] }` with exact (hex-float) constants:
+// the compile-time table CtModel<> specialises the kernels on.
+std::string rb_model_emit_header(const RbHostModel& m, const char* tab_name);
+
+// Flattens the model into the layout of RbModelK<n> (n rows of 24 doubles then g[3]).
+std::vector<double> rb_model_flat(const RbHostModel& m);

@@ -1,0 +1,15 @@
+// rb_util.cuh -- utility kernels of the engine (defined in rb_kernels_n.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rb_model.h"
+
+struct RbFillRange { double lo[RB_MAX_N]; double hi[RB_MAX_N]; };
+#define RB_PEAK_INNER 64
+
+cudaError_t rb_launch_fill(double* out, uint64_t seed, uint32_t field, int n, const RbFillRange& rg,
+                           size_t first, size_t count, size_t ld, cudaStream_t st);
+// `per_state` doubles per state: [B][per_state] <-> [per_state][ld]
+cudaError_t rb_launch_aos_to_soa(const double* aos, double* soa, int per_state, size_t B, size_t ld, cudaStream_t st);
+cudaError_t rb_launch_soa_to_aos(const double* soa, double* aos, int per_state, size_t B, size_t ld, cudaStream_t st);
+cudaError_t rb_launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t st);

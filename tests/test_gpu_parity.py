@@ -1,0 +1,259 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): fp64, per state max_i|x_i - ref_i| <= 1e-10 * max(1, ||ref||_inf).
+Small/medium sizes compare against the oracle directly and against the frozen golden vectors; the full
+BASELINE.json sizes use size-independent properties (FD round trip, the CRBA/RNEA identity, a strided oracle
+sample) because the oracle would need minutes there.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CHAIN32, FR3, TOL, load_golden, state_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _states(orc, B, seed=0x5EED0001, first=0):
+    lim = orc.model
+    q = orc.fill(seed, 0, lim.lower, lim.upper, first, B)
+    dq = orc.fill(seed, 1, -lim.velocity, lim.velocity, first, B)
+    ddq = orc.fill(seed, 2, -10.0, 10.0, first, B)
+    tau = orc.fill(seed + 1, 3, -lim.effort, lim.effort, first, B)
+    return q, dq, ddq, tau
+
+
+def _variants(rb, urdf):
+    """Every kernel family able to serve the chain (selected via RIGIDBODY_B200_VARIANT)."""
+    out = []
+    for v in ("auto", "generic-7", "generic-n"):
+        os.environ["RIGIDBODY_B200_VARIANT"] = v
+        try:
+            out.append(rb.Multibody.from_urdf(urdf))
+        except rb.RigidBodyError:
+            pass
+        finally:
+            os.environ.pop("RIGIDBODY_B200_VARIANT", None)
+    return out
+
+
+def test_kernel_families_selected(rb, mb_fr3, mb_chain32):
+    assert mb_fr3.kernel_variant == "fr3-specialised"
+    assert mb_chain32.kernel_variant == "generic-n"
+    names = [m.kernel_variant for m in _variants(rb, FR3)]
+    assert names == ["fr3-specialised", "generic-7", "generic-n"]
+
+
+def test_golden_vectors_fr3_all_families(rb):
+    g = load_golden("fr3_oracle.json")
+    q, dq, ddq, tau = (np.array(g[k]) for k in ("q", "dq", "ddq", "tau_in"))
+    for mb in _variants(rb, FR3):
+        assert state_err(mb.rnea(q, dq, ddq, layout="aos"), np.array(g["rnea"]), 1).max() < TOL, mb.kernel_variant
+        assert state_err(mb.forward_dynamics(q, dq, tau, layout="aos"), np.array(g["fd"]), 1).max() < TOL
+        assert state_err(mb.crba(q[:8], layout="aos"), np.array(g["crba_colmajor"]), 1).max() < TOL
+        assert np.abs(mb.fwd_kin(q[:8], layout="aos") - np.array(g["fwd_kin"])).max() < TOL
+        assert np.abs(mb.jac(q[:8], layout="aos") - np.array(g["jac_colmajor"])).max() < TOL
+
+
+def test_golden_vectors_chain32(mb_chain32):
+    g = load_golden("chain32_oracle.json")
+    q, dq, ddq, tau = (np.array(g[k]) for k in ("q", "dq", "ddq", "tau_in"))
+    assert state_err(mb_chain32.rnea(q, dq, ddq, layout="aos"), np.array(g["rnea"]), 1).max() < TOL
+    assert state_err(mb_chain32.forward_dynamics(q, dq, tau, layout="aos"), np.array(g["fd"]), 1).max() < 1e-9
+    assert state_err(mb_chain32.crba(q, layout="aos"), np.array(g["crba_colmajor"])[:4], 1).max() < TOL
+
+
+def test_survey_kats_and_single_state_calls(rb, mb_fr3):
+    """One state through the batched entry points = the reference's single-state FFI calls (lib.rs:15-70)."""
+    k = load_golden("survey_kat.json")
+    for key in ("rnea_zero", "main_cpp", "generic"):
+        c = k[key]
+        np.testing.assert_allclose(mb_fr3.rnea(c["q"], c["dq"], c["ddq"]), c["tau"], rtol=0, atol=2e-12)
+    c = k["main_cpp"]
+    H = mb_fr3.crba(c["q"])
+    np.testing.assert_allclose(np.diag(H), c["crba_diag"], rtol=1e-12)
+    np.testing.assert_allclose([H[0, 1], H[1, 3], H[5, 6]], [c["H01"], c["H13"], c["H56"]], rtol=1e-11)
+    assert np.all(np.tril(H, -1) == 0.0)
+    np.testing.assert_allclose(mb_fr3.fwd_kin(np.zeros(7)), k["fwd_kin_zero"], atol=1e-15)
+
+
+def test_reference_symbols_single_state(rb, oracle_fr3):
+    """Part 1 of the header: multibody_new_from_urdf / multibody_rnea / crba / fwd_kin / jac / free."""
+    from rigidbody_rs_b200 import _lib
+    lib = _lib.lib
+    mb = lib.multibody_new_from_urdf(FR3.encode())
+    assert mb
+    arr = lambda v: (C.c_double * len(v))(*v)
+    q, dq, ddq = [0, 0, 1, 0, 1, 0, 0], [0, 0, 0, 0, 1, 0, 0], [1, 0, 0, 0, 0, 1, 0]      # main.cpp:103-105
+    p = lib.multibody_rnea(mb, arr(q), arr(dq), arr(ddq))
+    assert p, lib.multibody_last_error()
+    np.testing.assert_allclose(p[:7], oracle_fr3.rnea(q, dq, ddq), rtol=0, atol=1e-12)
+    lib.multibody_free_result(p)
+    p = lib.multibody_crba(mb, arr(q))
+    H = np.array(p[:49]).reshape(7, 7).T                                                   # H[i+7*j], main.cpp:91-95
+    np.testing.assert_allclose(H, oracle_fr3.crba(q), rtol=0, atol=1e-12)
+    lib.multibody_free_result(p)
+    p = lib.multibody_fwd_kin(mb, arr(q))
+    np.testing.assert_allclose(p[:3], oracle_fr3.fwd_kin(q), rtol=0, atol=1e-13)
+    lib.multibody_free_result(p)
+    p = lib.multibody_jac(mb, arr(q))
+    J = np.array(p[:42]).reshape(7, 6).T                                                   # J[6*i+j], main.cpp:76-79
+    np.testing.assert_allclose(J, oracle_fr3.jac(q), rtol=0, atol=1e-13)
+    lib.multibody_free_result(p)
+    lib.multibody_free(mb)
+
+
+@pytest.mark.parametrize("B", [1, 31, 128, 129, 5000])
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_rnea_fd_host_batches(mb_fr3, oracle_fr3, B, layout):
+    q, dq, ddq, tau = _states(oracle_fr3, B)
+    ax = 0
+    want_t = oracle_fr3.rnea_batch(q, dq, ddq)
+    want_a = oracle_fr3.forward_dynamics_batch(q, dq, tau)
+    if layout == "aos":
+        q, dq, ddq, tau, want_t, want_a = (np.ascontiguousarray(x.T) for x in (q, dq, ddq, tau, want_t, want_a))
+        ax = 1
+    assert state_err(mb_fr3.rnea(q, dq, ddq, layout=layout), want_t, ax).max() < TOL
+    assert state_err(mb_fr3.forward_dynamics(q, dq, tau, layout=layout), want_a, ax).max() < TOL
+
+
+def test_empty_batch_and_bad_shapes(mb_fr3):
+    z = np.zeros((7, 0))
+    assert mb_fr3.rnea(z, z, z).shape == (7, 0)
+    with pytest.raises(ValueError):
+        mb_fr3.rnea(np.zeros((6, 4)), np.zeros((6, 4)), np.zeros((6, 4)))
+    with pytest.raises(ValueError):
+        mb_fr3.rnea(np.zeros(6), np.zeros(6), np.zeros(6))
+
+
+def test_ragged_leading_dimension_device(rb, mb_fr3, oracle_fr3):
+    """SoA with ld > n_states through the raw C ABI on device pointers (views into a wider allocation)."""
+    import torch
+    from rigidbody_rs_b200 import _lib
+    B, ld = 1000, 1536
+    q, dq, ddq, _ = _states(oracle_fr3, B)
+    dev = torch.device("cuda:0")
+    bufs = [torch.full((7, ld), float("nan"), dtype=torch.float64, device=dev) for _ in range(4)]
+    for b, x in zip(bufs, (q, dq, ddq)):
+        b[:, :B] = torch.from_numpy(x).to(dev)
+    torch.cuda.synchronize()
+    rc = _lib.lib.multibody_rnea_batch(mb_fr3._h, *[C.c_void_p(b.data_ptr()) for b in bufs], B, ld,
+                                       _lib.RB_LAYOUT_SOA, _lib.RB_MEM_DEVICE, None)
+    assert rc == 0, _lib.lib.multibody_last_error()
+    mb_fr3.sync()
+    out = bufs[3].cpu().numpy()
+    assert state_err(out[:, :B], oracle_fr3.rnea_batch(q, dq, ddq), 0).max() < TOL
+    assert np.isnan(out[:, B:]).all()                       # padding untouched
+    # ld < n_states is rejected
+    rc = _lib.lib.multibody_rnea_batch(mb_fr3._h, *[C.c_void_p(b.data_ptr()) for b in bufs], B, B - 1,
+                                       _lib.RB_LAYOUT_SOA, _lib.RB_MEM_DEVICE, None)
+    assert rc == _lib.RB_ERR_ARG
+
+
+def test_device_tensors_all_ops_medium_batch(rb, oracle_fr3):
+    import torch
+    B = 200_000
+    q, dq, ddq, tau = _states(oracle_fr3, B)
+    dev = torch.device("cuda:0")
+    tq, tdq, tddq, ttau = (torch.from_numpy(x).to(dev) for x in (q, dq, ddq, tau))
+    want_t = oracle_fr3.rnea_batch(q, dq, ddq)
+    want_a = oracle_fr3.forward_dynamics_batch(q, dq, tau)
+    want_H = oracle_fr3.crba_batch(q[:, :20000])
+    for mb in _variants(rb, FR3):
+        assert state_err(mb.rnea(tq, tdq, tddq).cpu().numpy(), want_t, 0).max() < TOL, mb.kernel_variant
+        assert state_err(mb.forward_dynamics(tq, tdq, ttau).cpu().numpy(), want_a, 0).max() < TOL, mb.kernel_variant
+        assert state_err(mb.crba(tq[:, :20000].contiguous()).cpu().numpy(), want_H, 0).max() < TOL
+        fk = mb.fwd_kin(tq[:, :2000].contiguous()).cpu().numpy()
+        jc = mb.jac(tq[:, :2000].contiguous()).cpu().numpy()
+        for s in range(0, 2000, 97):
+            assert np.abs(fk[:, s] - oracle_fr3.fwd_kin(q[:, s])).max() < TOL
+            assert np.abs(jc[:, s].reshape(7, 6).T - oracle_fr3.jac(q[:, s])).max() < TOL
+
+
+def test_device_sampler_bit_identical_to_oracle(mb_fr3, oracle_fr3):
+    import torch
+    lim = mb_fr3.limits()
+    out = torch.empty((7, 4096), dtype=torch.float64, device="cuda:0")
+    mb_fr3.fill(out, 0x5EED0001, 0, lim["lower"], lim["upper"], first_index=123456)
+    mb_fr3.sync()
+    want = oracle_fr3.fill(0x5EED0001, 0, lim["lower"], lim["upper"], 123456, 4096)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)              # bit-exact: integer mixing + one fma
+
+
+def test_rollout_matches_oracle(rb, oracle_fr3):
+    B, H, dt = 64, 64, 1e-3
+    q, dq, _, _ = _states(oracle_fr3, B, seed=0x5EED0003)
+    lim = oracle_fr3.model
+    tau = np.stack([oracle_fr3.fill(0x5EED0003, 4 + t % 32, -lim.effort, lim.effort, t * B, B) for t in range(H)])
+    oq, odq = oracle_fr3.rollout_batch(q, dq, tau, dt)
+    for mb in _variants(rb, FR3):
+        qt, dqt, qf, dqf = mb.rollout(q, dq, tau, dt, final=True)
+        assert state_err(qt, oq, 1).max() < TOL and state_err(dqt, odq, 1).max() < TOL, mb.kernel_variant
+        np.testing.assert_array_equal(qf, qt[-1]); np.testing.assert_array_equal(dqf, dqt[-1])
+        # AoS front end gives the same numbers
+        qa, dqa = mb.rollout(np.ascontiguousarray(q.T), np.ascontiguousarray(dq.T),
+                             np.ascontiguousarray(tau.transpose(0, 2, 1)), dt, layout="aos")
+        np.testing.assert_array_equal(qa.transpose(0, 2, 1), qt)
+
+
+def test_chain32_medium_batch(mb_chain32, oracle_chain32):
+    B = 4096
+    o = oracle_chain32
+    q = o.fill(0x5EED0005, 0, -np.pi, np.pi, 0, B); dq = o.fill(0x5EED0005, 1, -2.0, 2.0, 0, B)
+    ddq = o.fill(0x5EED0005, 2, -10.0, 10.0, 0, B); tau = o.fill(0x5EED0005, 3, -50.0, 50.0, 0, B)
+    assert state_err(mb_chain32.rnea(q, dq, ddq), o.rnea_batch(q, dq, ddq), 0).max() < TOL
+    # cond(H) reaches ~3e4 on this chain: FD is held to 1e-9 here, the round trip below to 1e-8
+    assert state_err(mb_chain32.forward_dynamics(q, dq, tau), o.forward_dynamics_batch(q, dq, tau), 0).max() < 1e-9
+    t = mb_chain32.rnea(q, dq, ddq)
+    assert state_err(mb_chain32.forward_dynamics(q, dq, t), ddq, 0).max() < 1e-8
+
+
+def test_not_spd_is_reported(rb):
+    """A physically impossible chain (negative rotational inertia) makes H indefinite: host calls return
+    RB_ERR_NOT_SPD and NaN rows instead of garbage."""
+    n = 2
+    R = np.tile(np.eye(3), (n, 1, 1)); t = np.zeros((n, 3)); t[1] = [0.1, 0, 0]
+    m = np.array([1.0, 1.0]); c = np.zeros((n, 3))
+    Ic = np.tile(np.diag([0.1, 0.1, -5.0]), (n, 1, 1))
+    mb = rb.Multibody.from_descriptor(R, t, m, c, Ic)
+    z = np.zeros((2, 4))
+    with pytest.raises(rb.NotPositiveDefinite):
+        mb.forward_dynamics(z, z, z)
+
+
+def test_descriptor_upload_equals_urdf_load(rb, mb_fr3, oracle_fr3):
+    """The RbChainDesc path (what the Rust side would call) selects the same specialised kernels and numbers."""
+    from oracle.rb_oracle_np import ChainNP
+    c = ChainNP(oracle_fr3.model)
+    mod = oracle_fr3.model
+    Ic = np.stack([[[s[0], s[1], s[2]], [s[1], s[3], s[4]], [s[2], s[4], s[5]]] for s in mod.inertia6])
+    mb = rb.Multibody.from_descriptor(c.Rp, mod.xyz, mod.mass, mod.com, Ic)
+    assert mb.kernel_variant in ("fr3-specialised", "generic-7")
+    q, dq, ddq, _ = _states(oracle_fr3, 512)
+    assert state_err(mb.rnea(q, dq, ddq), oracle_fr3.rnea_batch(q, dq, ddq), 0).max() < TOL
+
+
+def test_full_size_properties_16M(mb_fr3, oracle_fr3):
+    """BASELINE.json configs[1]/[2] at full size (2^24 states, device-resident, sampled on device):
+    FD(q, dq, RNEA(q, dq, ddq)) == ddq for every state, plus a strided oracle sample of both outputs."""
+    import torch
+    B = 1 << 24
+    dev = torch.device("cuda:0")
+    lim = mb_fr3.limits()
+    q = torch.empty((7, B), dtype=torch.float64, device=dev)
+    dq = torch.empty_like(q); ddq = torch.empty_like(q)
+    mb_fr3.fill(q, 0x5EED0001, 0, lim["lower"], lim["upper"])
+    mb_fr3.fill(dq, 0x5EED0001, 1, -lim["velocity"], lim["velocity"])
+    mb_fr3.fill(ddq, 0x5EED0001, 2, -10.0, 10.0)
+    tau = mb_fr3.rnea(q, dq, ddq)
+    back = mb_fr3.forward_dynamics(q, dq, tau)
+    mb_fr3.sync()
+    err = (back - ddq).abs().amax(0) / ddq.abs().amax(0).clamp_min(1.0)
+    assert float(err.max()) < 1e-9, float(err.max())          # cond(H) <= ~1e3
+    idx = torch.arange(0, B, 4099, device=dev)
+    qs, dqs, ddqs = (x[:, idx].cpu().numpy() for x in (q, dq, ddq))
+    assert state_err(tau[:, idx].cpu().numpy(), oracle_fr3.rnea_batch(qs, dqs, ddqs), 0).max() < TOL
+    want = oracle_fr3.fill(0x5EED0001, 0, lim["lower"], lim["upper"], 0, 8)
+    np.testing.assert_array_equal(q[:, :8].cpu().numpy(), want)
