@@ -133,8 +133,9 @@ const char* multibody_last_error(void);
 /*
  * Common arguments:  n_states states; `ld` = leading dimension in elements for RB_LAYOUT_SOA (>= n_states;
  * 0 means n_states), ignored for AOS; `mem` says where ALL pointers of the call live.
- * RB_MEM_DEVICE calls are asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the engine's own
- * stream) and return after the launch; call multibody_gpu_sync (or sync the stream yourself) before reading.
+ * RB_MEM_DEVICE calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the legacy default
+ * stream, as in every CUDA library) and return after the launch; sync the stream (or call multibody_gpu_sync)
+ * before reading.  `stream` is ignored by RB_MEM_HOST calls.
  * RB_MEM_HOST calls are synchronous: they stage through the engine's pinned buffers in chunks, overlapping
  * H2D, compute and D2H, and return when `out` is complete.
  * With n_states = 1, AOS, HOST these are the reference's single-state calls minus the leak.
@@ -178,9 +179,10 @@ int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, const doubl
  * splitmix64(seed + GOLDEN*(1 + (field<<58 | i<<50 | first_index+s))).  lo/hi are host arrays [n]. */
 int multibody_gpu_fill(RbGpu* g, double* dev_out, uint64_t seed, uint32_t field, const double* lo, const double* hi,
                        size_t first_index, size_t count, size_t ld, void* stream);
-/* Wait for the engine's stream and report a sticky device-side status (RB_ERR_NOT_SPD, RB_ERR_CUDA) once. */
+/* Wait for all work on the engine's device, then report (and clear) the device-side status word:
+ * RB_ERR_NOT_SPD if any forward-dynamics state since the last query met a non-SPD mass matrix. */
 int multibody_gpu_sync(RbGpu* g);
-int multibody_gpu_status(RbGpu* g);
+int multibody_gpu_status(RbGpu* g);     /* alias of multibody_gpu_sync */
 /* Kernel launches issued by this engine since creation (bench.py's `gpu_launches`). */
 uint64_t multibody_gpu_launch_count(const RbGpu* g);
 /* Pinned host allocations, so RB_MEM_HOST calls copy at full PCIe rate without a staging hop. */

@@ -316,7 +316,7 @@ int run_op(RbGpu* g, OpDesc& op, size_t n_states, size_t ld, RbLayout layout, Rb
     DeviceGuard dg(g->device);
     if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
     if (mem == RB_MEM_DEVICE)
-        return run_device(g, op, n_states, ld, layout, stream ? (cudaStream_t)stream : g->stream);
+        return run_device(g, op, n_states, ld, layout, (cudaStream_t)stream);
     rc = run_host(g, op, n_states, ld, layout);
     if (rc != RB_OK) return rc;
     return has_status ? fetch_status(g) : RB_OK;
@@ -480,7 +480,7 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     const int n = g->model.n;
     DeviceGuard dg(g->device);
     if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
-    cudaStream_t st = (mem == RB_MEM_DEVICE && stream) ? (cudaStream_t)stream : g->stream;
+    cudaStream_t st = mem == RB_MEM_DEVICE ? (cudaStream_t)stream : g->stream;
     if (mem == RB_MEM_DEVICE && layout == RB_LAYOUT_SOA) {
         cudaError_t e = g->ops->rollout(g->param.data(), q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_final, dq_final,
                                         n_traj, ld, g->d_status, st);
@@ -571,8 +571,7 @@ extern "C" int multibody_gpu_fill(RbGpu* g, double* dev_out, uint64_t seed, uint
     DeviceGuard dg(g->device);
     RbFillRange rg;
     for (int i = 0; i < g->model.n; ++i) { rg.lo[i] = lo[i]; rg.hi[i] = hi[i]; }
-    cudaError_t e = rb_launch_fill(dev_out, seed, field, g->model.n, rg, first_index, count, ld,
-                                   stream ? (cudaStream_t)stream : g->stream);
+    cudaError_t e = rb_launch_fill(dev_out, seed, field, g->model.n, rg, first_index, count, ld, (cudaStream_t)stream);
     g->launches += 1;
     if (e != cudaSuccess) return fail_cuda(e, "fill launch");
     return RB_OK;
@@ -581,16 +580,11 @@ extern "C" int multibody_gpu_fill(RbGpu* g, double* dev_out, uint64_t seed, uint
 extern "C" int multibody_gpu_sync(RbGpu* g) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     DeviceGuard dg(g->device);
-    RB_CUDA(cudaStreamSynchronize(g->stream));
+    RB_CUDA(cudaDeviceSynchronize());      // device calls run on caller streams: wait for all of them
     return fetch_status(g);
 }
 
-extern "C" int multibody_gpu_status(RbGpu* g) {
-    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
-    DeviceGuard dg(g->device);
-    RB_CUDA(cudaDeviceSynchronize());
-    return fetch_status(g);
-}
+extern "C" int multibody_gpu_status(RbGpu* g) { return multibody_gpu_sync(g); }
 
 extern "C" int multibody_host_alloc(void** out, size_t bytes) {
     if (!out) return fail(RB_ERR_NULL, "out is NULL");
