@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librigidbody_b200.so")
+# RIGIDBODY_B200_LIB lets tools/kbench.py time alternative builds of the same library (tuning experiments).
+LIB_PATH = os.environ.get("RIGIDBODY_B200_LIB") or os.path.join(_HERE, "librigidbody_b200.so")
 
 RB_OK = 0
 RB_ERR_NULL, RB_ERR_ARG, RB_ERR_URDF, RB_ERR_CUDA, RB_ERR_NOT_SPD, RB_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6

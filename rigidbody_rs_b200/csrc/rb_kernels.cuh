@@ -9,8 +9,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "rb_dyn.cuh"
+#include "rb_tma.cuh"
 
 #define RB_BLOCK 128
+// Minimum resident blocks per SM requested from ptxas (register cap = 65536 / (RB_BLOCK * min_blocks)).
+#ifndef RB_MINB_RNEA
+#define RB_MINB_RNEA 5
+#endif
+#ifndef RB_MINB_FD
+#define RB_MINB_FD 4
+#endif
+#ifndef RB_STREAM
+#define RB_STREAM 0        // 1 = route full tiles through the persistent TMA-fed kernels (measured slower)
+#endif
 
 struct RbOps {
     const char* name;
@@ -47,7 +58,7 @@ RB_DI void rb_store(double* __restrict__ x, size_t ld, size_t s, const double (&
 }
 
 template <class M>
-__global__ void __launch_bounds__(RB_BLOCK)
+__global__ void __launch_bounds__(RB_BLOCK, RB_MINB_RNEA)
 rb_rnea_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
                const double* __restrict__ ddq, double* __restrict__ tau, size_t B, size_t ld) {
     constexpr int N = M::N;
@@ -63,7 +74,7 @@ rb_rnea_kernel(const __grid_constant__ typename M::Param p, const double* __rest
 }
 
 template <class M>
-__global__ void __launch_bounds__(RB_BLOCK)
+__global__ void __launch_bounds__(RB_BLOCK, RB_MINB_FD)
 rb_fd_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
              const double* __restrict__ tau, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
@@ -81,6 +92,76 @@ rb_fd_kernel(const __grid_constant__ typename M::Param p, const double* __restri
         for (int i = 0; i < N; ++i) x[i] = __longlong_as_double(0x7ff8000000000000LL);
     }
     rb_store<N>(qdd, ld, s, x);
+}
+
+// ------------------------------------------------------------------ streaming (persistent, TMA-fed) RNEA / FD
+// The one-tile-per-block kernels above leave each warp's 21 input loads exposed at the start of its life, so
+// HBM latency is hidden only by other resident warps -- and registers cap those at 16-20 per SM.  Here a
+// persistent block walks tiles of RB_BLOCK states; one elected thread asks the TMA unit to bulk-copy the
+// next tile's 3N input rows (RB_BLOCK*8 = 1 KiB contiguous each) into a 2-stage shared-memory ring while all
+// warps compute the current tile, and an mbarrier (transaction bytes) says when a stage has landed.  The
+// FP64 pipe then sees compute-phase warps only.  Requires 16-byte aligned rows (pointers % 16, ld % 2).
+#define RB_STAGES 2
+template <class M, int MINB, bool IS_FD>
+__global__ void __launch_bounds__(RB_BLOCK, MINB)
+rb_stream_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ in0, const double* __restrict__ in1,
+                 const double* __restrict__ in2, double* __restrict__ out, unsigned num_tiles, size_t ld, int* __restrict__ status) {
+    constexpr int N = M::N, ROWS = 3 * N;
+    extern __shared__ __align__(128) double rb_stage[];      // [RB_STAGES][ROWS][RB_BLOCK]
+    __shared__ __align__(8) uint64_t bar[RB_STAGES];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < RB_STAGES; ++k) rb_mbar_init(&bar[k], 1);
+        rb_fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](unsigned tile, int st) {
+        const size_t s0 = (size_t)tile * RB_BLOCK;
+        double* dst = rb_stage + (size_t)st * ROWS * RB_BLOCK;
+        rb_mbar_expect_tx(&bar[st], ROWS * RB_BLOCK * (uint32_t)sizeof(double));
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const double* src = (r < N ? in0 : (r < 2 * N ? in1 : in2)) + (size_t)(r % N) * ld + s0;
+            rb_bulk_g2s(dst + r * RB_BLOCK, src, RB_BLOCK * (uint32_t)sizeof(double), &bar[st]);
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < RB_STAGES; ++k) {
+            const unsigned t = blockIdx.x + k * gridDim.x;
+            if (t < num_tiles) issue(t, k);
+        }
+    }
+    bool ok = true;
+    unsigned it = 0;
+    for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int st = it % RB_STAGES;
+        rb_mbar_wait(&bar[st], (it / RB_STAGES) & 1);
+        const double* src = rb_stage + (size_t)st * ROWS * RB_BLOCK + tid;
+        double a[N], b[N], c[N], sn[N], cs[N], x[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            a[i] = src[i * RB_BLOCK]; b[i] = src[(N + i) * RB_BLOCK]; c[i] = src[(2 * N + i) * RB_BLOCK];
+        }
+        __syncthreads();                                     // every thread has drained this stage
+        if (tid == 0) {
+            const unsigned nxt = tile + RB_STAGES * gridDim.x;
+            if (nxt < num_tiles) issue(nxt, st);
+        }
+        rb_sincos_all<N>(a, sn, cs);
+        if constexpr (IS_FD) {
+            if (!rb_forward_dynamics<M>(p, sn, cs, b, c, x)) {
+                ok = false;
+#pragma unroll
+                for (int i = 0; i < N; ++i) x[i] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+        } else {
+            rb_rnea<M, true>(p, sn, cs, b, c, x);
+        }
+        rb_store<N>(out, ld, (size_t)tile * RB_BLOCK + tid, x);
+    }
+    if constexpr (IS_FD) { if (!ok) atomicOr(status, RB_STATUS_NOT_SPD); }
 }
 
 // H out: reference convention, n*n entries per state, entry k = r + n*c, upper filled, strict lower 0.
@@ -178,16 +259,62 @@ template <class M>
 struct RbLaunch {
     using P = typename M::Param;
     static unsigned grid(size_t B) { return (unsigned)((B + RB_BLOCK - 1) / RB_BLOCK); }
+    // SM count of the current device (cached per device ordinal).
+    static int sm_count() {
+        static int cache[64] = {0};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+        if (cache[dev] == 0) {
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+            cache[dev] = v;
+        }
+        return cache[dev];
+    }
+    // Full tiles go through the persistent TMA-fed kernel when rows are 16-byte aligned; the ragged tail
+    // (and unaligned or tiny batches) through the one-tile-per-block kernel.
+    template <int MINB, bool IS_FD>
+    static cudaError_t stream3(const P& p, const double* a, const double* b, const double* c, double* out,
+                               size_t B, size_t ld, int* status, cudaStream_t st, size_t* done) {
+        *done = 0;
+#if RB_STREAM
+        const bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) == 0 && (ld & 1u) == 0;
+        const size_t tiles = B / RB_BLOCK;
+        const unsigned cap = (unsigned)sm_count() * MINB;
+        if (!aligned || tiles < 2 * (size_t)cap || tiles > 0xFFFFFFF0u) return cudaSuccess;
+        auto k = rb_stream_kernel<M, MINB, IS_FD>;
+        constexpr size_t smem = (size_t)RB_STAGES * 3 * M::N * RB_BLOCK * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        k<<<cap, RB_BLOCK, smem, st>>>(p, a, b, c, out, (unsigned)tiles, ld, status);
+        *done = tiles * RB_BLOCK;
+        return cudaGetLastError();
+#else
+        return cudaSuccess;
+#endif
+    }
     static cudaError_t rnea(const void* param, const double* q, const double* dq, const double* ddq, double* tau,
                             size_t B, size_t ld, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
-        rb_rnea_kernel<M><<<grid(B), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, ddq, tau, B, ld);
+        size_t done = 0;
+        cudaError_t e = stream3<RB_MINB_RNEA, false>(*(const P*)param, q, dq, ddq, tau, B, ld, nullptr, st, &done);
+        if (e != cudaSuccess || done == B) return e;
+        rb_rnea_kernel<M><<<grid(B - done), RB_BLOCK, 0, st>>>(*(const P*)param, q + done, dq + done, ddq + done, tau + done, B - done, ld);
         return cudaGetLastError();
     }
     static cudaError_t fd(const void* param, const double* q, const double* dq, const double* tau, double* qdd,
                           size_t B, size_t ld, int* status, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
-        rb_fd_kernel<M><<<grid(B), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, tau, qdd, B, ld, status);
+        size_t done = 0;
+        cudaError_t e = stream3<RB_MINB_FD, true>(*(const P*)param, q, dq, tau, qdd, B, ld, status, st, &done);
+        if (e != cudaSuccess || done == B) return e;
+        rb_fd_kernel<M><<<grid(B - done), RB_BLOCK, 0, st>>>(*(const P*)param, q + done, dq + done, tau + done, qdd + done, B - done, ld, status);
         return cudaGetLastError();
     }
     static cudaError_t crba(const void* param, const double* q, double* H, size_t B, size_t ld, cudaStream_t st) {

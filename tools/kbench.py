@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Kernel-only timing of the FR3 hot path for tuning experiments (CUDA events, device-resident inputs).
+usage: [RIGIDBODY_B200_LIB=path.so] python tools/kbench.py [--states N] [--iters K] [--tag name]"""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rigidbody_rs_b200 as rb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--states", type=int, default=1 << 24)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--tag", default="")
+ap.add_argument("--urdf", default="assets/fr3.urdf")
+ap.add_argument("--ops", default="rnea,fd")
+a = ap.parse_args()
+mb = rb.Multibody.from_urdf(a.urdf)
+n, B = mb.n, a.states
+lim = mb.limits()
+dev = torch.device("cuda:0")
+q = torch.empty((n, B), dtype=torch.float64, device=dev)
+dq, x3, out = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+mb.fill(q, 1, 0, lim["lower"], lim["upper"]); mb.fill(dq, 1, 1, -lim["velocity"], lim["velocity"]); mb.fill(x3, 1, 2, -10.0, 10.0)
+res = {"tag": a.tag, "variant": mb.kernel_variant, "states": B}
+for op in a.ops.split(","):
+    fn = {"rnea": lambda: mb.rnea(q, dq, x3, out=out), "fd": lambda: mb.forward_dynamics(q, dq, x3, out=out),
+          "crba": None}[op]
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(a.iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    med = ts[len(ts) // 2]
+    res[op] = {"ms_med": round(med, 4), "ms_min": round(ts[0], 4), "Geval_s": round(B / med / 1e6, 3)}
+print(json.dumps(res), flush=True)
