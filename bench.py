@@ -31,6 +31,27 @@ STATES_PER_GPU = 1 << 24
 # algorithmic work per evaluation (SURVEY.md 8d / BASELINE.md section 2), N = 7
 RNEA_FLOPS, FD_FLOPS, BYTES_PER_EVAL = 2026.0, 4180.0, 224.0
 SEED_RNEA, SEED_FD = 0x5EED0001, 0x5EED0002
+# FP64-pipe SASS instructions one thread (= one state) executes in the fr3-specialised kernels: static count of
+# the straight-line kernels (tools/sass_count.sh; tests/test_host.py checks these against the built library).
+FP64_INSTR = {"rb_rnea_kernel": 635, "rb_fd_kernel": 1154}
+FP64_LANES_PER_SM = 64
+
+
+def profiled_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not name.endswith("ncu_full_summary.json"):
+            continue
+        with open(os.path.join(pdir, name)) as f:
+            for row in json.load(f):
+                if kernel in row.get("kernel", "") and "dram__bytes_read.sum" in row:
+                    def gb(v):
+                        num, unit = v.split()[:2]
+                        return float(num) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+                    best = {"bytes": gb(row["dram__bytes_read.sum"]) + gb(row["dram__bytes_write.sum"]), "source": "profiles/" + name}
+    return best
 
 
 def measured_peaks():
@@ -83,12 +104,13 @@ def cpu_arm(sample_states, steps, warmup):
     from oracle.rb_oracle import Oracle
     orc = Oracle.from_urdf(os.path.join(ROOT, "assets", "fr3.urdf"), fast=True)   # rebuilt -march=native on this host
     m = orc.model
-    threads = orc.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1: size the team from the CPUs this process may run on instead
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if sample_states is None:       # calibrate to ~4 s of wall time per step
         S0 = 1 << 14
         q = orc.fill(SEED_RNEA, 0, m.lower, m.upper, 0, S0); dq = orc.fill(SEED_RNEA, 1, -m.velocity, m.velocity, 0, S0)
         t0 = time.perf_counter()
-        orc.rnea_batch(q, dq, q); orc.forward_dynamics_batch(q, dq, q)
+        orc.rnea_batch(q, dq, q, threads=threads); orc.forward_dynamics_batch(q, dq, q, threads=threads)
         per = (time.perf_counter() - t0) / S0
         sample_states = int(min(1 << 22, max(1 << 14, 4.0 / per)))
     S = sample_states
@@ -99,8 +121,8 @@ def cpu_arm(sample_states, steps, warmup):
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.rnea_batch(q, dq, ddq)
-        orc.forward_dynamics_batch(q, dq, tau)
+        orc.rnea_batch(q, dq, ddq, threads=threads)
+        orc.forward_dynamics_batch(q, dq, tau, threads=threads)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
@@ -205,11 +227,18 @@ def run_ours(args, rank, local_rank, world):
     hbm_peak, hbm_src = measured_peaks()
     rnea_s, fd_s = ms_rnea * 1e-3, ms_fd * 1e-3
 
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+
     def roof(kernel, flops, sec):
         tf = flops * B / sec / 1e12
         gbs = BYTES_PER_EVAL * B / sec / 1e9
+        tr = profiled_traffic(kernel) if B == STATES_PER_GPU else None
+        pipe = FP64_INSTR[kernel] * B / sec / (FP64_LANES_PER_SM * sm_count * sm_hz) if mb.kernel_variant == "fr3-specialised" else None
         return {"kernel": kernel, "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": tf / fp64_peak, "traffic": None, "evals_per_s": B / sec, "ms": sec * 1e3,
+                "frac": tf / fp64_peak, "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                "fp64_pipe_util": pipe, "fp64_instr_per_eval": FP64_INSTR[kernel],
+                "evals_per_s": B / sec, "ms": sec * 1e3,
                 "peak_source": "DFMA probe (multibody_gpu_measure_fp64_peak) on this GPU in this run; nominal 37.2",
                 "flops_per_eval": flops, "bytes_per_eval": BYTES_PER_EVAL,
                 "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}}

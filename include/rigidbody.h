@@ -115,6 +115,8 @@ int multibody_gpu_new_from_urdf(const char* urdf_path, int device, RbGpu** out);
 /* Engine for an existing reference-style handle. */
 int multibody_gpu_from_multibody(const Multibody* mb, int device, RbGpu** out);
 void multibody_gpu_free(RbGpu* g);
+/* The Rust crate rust/rigidbody_gpu_bindings additionally exports, for callers holding the Rust Multibody*:
+ *   int multibody_gpu_from_rust(const Multibody* mb, int device, RbGpu** out);    */
 
 /* ---- introspection ------------------------------------------------------------------------- */
 int multibody_gpu_n_joints(const RbGpu* g);

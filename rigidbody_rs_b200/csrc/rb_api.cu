@@ -627,6 +627,10 @@ extern "C" int multibody_gpu_measure_fp64_peak(RbGpu* g, int millis, double* tfl
 }
 
 // ===================================================================== Part 1: the reference's six symbols
+// When this library is linked next to the Rust cdylib `rigidbody_bindings` (which already exports these names,
+// rigidbody_bindings/src/lib.rs:8-78), build with -DRB_NO_REFERENCE_SYMBOLS and let
+// rust/rigidbody_gpu_bindings bridge its `Multibody` to multibody_gpu_new.
+#ifndef RB_NO_REFERENCE_SYMBOLS
 static Multibody* mb_load(const char* path) {
     try {
         Multibody* mb = new (std::nothrow) Multibody();
@@ -692,3 +696,4 @@ extern "C" double* multibody_jac(const Multibody* mb, const double* q) {
         return multibody_jac_batch(g, q, out, 1, 0, RB_LAYOUT_AOS, RB_MEM_HOST, nullptr);
     });
 }
+#endif  // RB_NO_REFERENCE_SYMBOLS

@@ -1,0 +1,223 @@
+//! Rust host side of the B200 batched engine: flattens a `rigidbody::multibody::Multibody` into the
+//! `RbChainDesc` of include/rigidbody.h, uploads it once, and exposes safe batched calls.
+//!
+//! Written against the reference at khaninger/rigidbody-rs:
+//!   * `Multibody::iter()`                      rigidbody/src/multibody.rs:79-81
+//!   * `RevoluteJoint { axis, parent, body }`   rigidbody/src/joint.rs:26-31   (all `pub`)
+//!   * `Inertia { mass, com, inertia_com, .. }` rigidbody/src/inertia.rs:12-17 (`inertia` about the origin is
+//!     private, so the C side recomputes it from mass/com/inertia_com exactly as `from_com` does, :31-32)
+//!
+//! NOT COMPILED in the build container of the CUDA repository (no cargo/rustc there).  Requires
+//! `pub use inertia::Inertia;` (or `pub mod inertia`) in rigidbody/src/lib.rs so the field types are nameable;
+//! the fields themselves are already public.
+use std::ffi::{c_char, c_int, c_void, CStr};
+use std::ptr;
+
+use rigidbody::multibody::Multibody;
+
+// ------------------------------------------------------------------ raw C ABI (include/rigidbody.h, Part 2)
+#[repr(C)]
+pub struct RbChainDesc {
+    pub n_joints: i32,
+    pub parent: *const i32,
+    pub axis: *const f64,
+    pub parent_rot: *const f64,
+    pub parent_trans: *const f64,
+    pub mass: *const f64,
+    pub com: *const f64,
+    pub inertia_com: *const f64,
+    pub gravity: [f64; 3],
+}
+
+#[repr(C)]
+pub struct RbGpu {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, PartialEq, Eq)]
+pub enum RbLayout {
+    Soa = 0,
+    Aos = 1,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, PartialEq, Eq)]
+pub enum RbMem {
+    Host = 0,
+    Device = 1,
+}
+
+extern "C" {
+    fn multibody_gpu_new(desc: *const RbChainDesc, device: c_int, out: *mut *mut RbGpu) -> c_int;
+    fn multibody_gpu_free(g: *mut RbGpu);
+    fn multibody_last_error() -> *const c_char;
+    fn multibody_rnea_batch(g: *mut RbGpu, q: *const f64, dq: *const f64, ddq: *const f64, tau: *mut f64,
+                            n_states: usize, ld: usize, layout: RbLayout, mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_forward_dynamics_batch(g: *mut RbGpu, q: *const f64, dq: *const f64, tau: *const f64, qdd: *mut f64,
+                                        n_states: usize, ld: usize, layout: RbLayout, mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_crba_batch(g: *mut RbGpu, q: *const f64, h: *mut f64, n_states: usize, ld: usize, layout: RbLayout,
+                            mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_rollout(g: *mut RbGpu, q0: *const f64, dq0: *const f64, tau: *const f64, dt: f64, horizon: c_int,
+                         q_traj: *mut f64, dq_traj: *mut f64, q_final: *mut f64, dq_final: *mut f64,
+                         n_traj: usize, ld: usize, layout: RbLayout, mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_gpu_sync(g: *mut RbGpu) -> c_int;
+}
+
+#[derive(Debug)]
+pub struct RbError {
+    pub code: i32,
+    pub message: String,
+}
+
+fn check(rc: c_int) -> Result<(), RbError> {
+    if rc == 0 {
+        return Ok(());
+    }
+    let message = unsafe { CStr::from_ptr(multibody_last_error()) }.to_string_lossy().into_owned();
+    Err(RbError { code: rc, message })
+}
+
+// ------------------------------------------------------------------ Multibody -> flattened descriptor
+/// Owned arrays behind an `RbChainDesc`; joint i's parent is joint i-1 (the reference is a serial chain).
+pub struct ChainArrays {
+    pub axis: Vec<f64>,
+    pub parent_rot: Vec<f64>,
+    pub parent_trans: Vec<f64>,
+    pub mass: Vec<f64>,
+    pub com: Vec<f64>,
+    pub inertia_com: Vec<f64>,
+}
+
+impl ChainArrays {
+    pub fn from_multibody(mb: &Multibody) -> Self {
+        let mut a = ChainArrays { axis: vec![], parent_rot: vec![], parent_trans: vec![], mass: vec![], com: vec![], inertia_com: vec![] };
+        for jt in mb.iter() {
+            a.axis.extend_from_slice(&[jt.axis[0], jt.axis[1], jt.axis[2]]);
+            let r = jt.parent.rotation.to_rotation_matrix();
+            for row in 0..3 {
+                for col in 0..3 {
+                    a.parent_rot.push(r[(row, col)]); // row-major
+                }
+            }
+            let t = jt.parent.translation.vector;
+            a.parent_trans.extend_from_slice(&[t[0], t[1], t[2]]);
+            a.mass.push(jt.body.mass);
+            a.com.extend_from_slice(&[jt.body.com[0], jt.body.com[1], jt.body.com[2]]);
+            for row in 0..3 {
+                for col in 0..3 {
+                    a.inertia_com.push(jt.body.inertia_com[(row, col)]);
+                }
+            }
+        }
+        a
+    }
+
+    pub fn desc(&self) -> RbChainDesc {
+        RbChainDesc {
+            n_joints: self.mass.len() as i32,
+            parent: ptr::null(), // serial chain
+            axis: self.axis.as_ptr(),
+            parent_rot: self.parent_rot.as_ptr(),
+            parent_trans: self.parent_trans.as_ptr(),
+            mass: self.mass.as_ptr(),
+            com: self.com.as_ptr(),
+            inertia_com: self.inertia_com.as_ptr(),
+            gravity: [0.0, 0.0, 9.81], // rigidbody/src/multibody.rs:118
+        }
+    }
+}
+
+// ------------------------------------------------------------------ safe wrapper
+/// One chain resident on one GPU.  `Send` but not `Sync`: host-batch calls share staging buffers.
+pub struct GpuMultibody {
+    raw: *mut RbGpu,
+    n: usize,
+}
+unsafe impl Send for GpuMultibody {}
+
+impl GpuMultibody {
+    pub fn new(mb: &Multibody, device: i32) -> Result<Self, RbError> {
+        let arrays = ChainArrays::from_multibody(mb);
+        let desc = arrays.desc();
+        let mut raw = ptr::null_mut();
+        check(unsafe { multibody_gpu_new(&desc, device, &mut raw) })?;
+        Ok(GpuMultibody { raw, n: arrays.mass.len() })
+    }
+
+    fn check_len(&self, what: &str, len: usize, per_state: usize, n_states: usize) -> Result<(), RbError> {
+        if len != per_state * n_states {
+            return Err(RbError { code: -2, message: format!("{what}: expected {} doubles, got {len}", per_state * n_states) });
+        }
+        Ok(())
+    }
+
+    /// Batched superset of `multibody_rnea` (rigidbody_bindings/src/lib.rs:15-30); host slices.
+    pub fn rnea_batch(&mut self, q: &[f64], dq: &[f64], ddq: &[f64], tau: &mut [f64], n_states: usize, layout: RbLayout) -> Result<(), RbError> {
+        for (w, s) in [("q", q.len()), ("dq", dq.len()), ("ddq", ddq.len()), ("tau", tau.len())] {
+            self.check_len(w, s, self.n, n_states)?;
+        }
+        check(unsafe { multibody_rnea_batch(self.raw, q.as_ptr(), dq.as_ptr(), ddq.as_ptr(), tau.as_mut_ptr(), n_states, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// qdd = solve(sym(crba(q)), tau - rnea(q, dq, 0)); host slices.
+    pub fn forward_dynamics_batch(&mut self, q: &[f64], dq: &[f64], tau: &[f64], qdd: &mut [f64], n_states: usize, layout: RbLayout) -> Result<(), RbError> {
+        for (w, s) in [("q", q.len()), ("dq", dq.len()), ("tau", tau.len()), ("qdd", qdd.len())] {
+            self.check_len(w, s, self.n, n_states)?;
+        }
+        check(unsafe { multibody_forward_dynamics_batch(self.raw, q.as_ptr(), dq.as_ptr(), tau.as_ptr(), qdd.as_mut_ptr(), n_states, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// Batched superset of `multibody_crba` (lib.rs:32-43): n*n entries per state, entry r + n*c.
+    pub fn crba_batch(&mut self, q: &[f64], h: &mut [f64], n_states: usize, layout: RbLayout) -> Result<(), RbError> {
+        self.check_len("q", q.len(), self.n, n_states)?;
+        self.check_len("h", h.len(), self.n * self.n, n_states)?;
+        check(unsafe { multibody_crba_batch(self.raw, q.as_ptr(), h.as_mut_ptr(), n_states, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// Semi-implicit Euler rollout; `tau` is `horizon` consecutive state arrays; returns the full trajectory.
+    #[allow(clippy::too_many_arguments)]
+    pub fn rollout(&mut self, q0: &[f64], dq0: &[f64], tau: &[f64], dt: f64, horizon: usize, q_traj: &mut [f64], dq_traj: &mut [f64],
+                   n_traj: usize, layout: RbLayout) -> Result<(), RbError> {
+        self.check_len("q0", q0.len(), self.n, n_traj)?;
+        self.check_len("dq0", dq0.len(), self.n, n_traj)?;
+        for (w, s) in [("tau", tau.len()), ("q_traj", q_traj.len()), ("dq_traj", dq_traj.len())] {
+            self.check_len(w, s, self.n * horizon, n_traj)?;
+        }
+        check(unsafe { multibody_rollout(self.raw, q0.as_ptr(), dq0.as_ptr(), tau.as_ptr(), dt, horizon as c_int, q_traj.as_mut_ptr(), dq_traj.as_mut_ptr(),
+                                         ptr::null_mut(), ptr::null_mut(), n_traj, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// Raw handle for device-pointer calls (RbMem::Device) from CUDA-aware callers.
+    pub fn raw(&mut self) -> *mut RbGpu {
+        self.raw
+    }
+
+    pub fn sync(&mut self) -> Result<(), RbError> {
+        check(unsafe { multibody_gpu_sync(self.raw) })
+    }
+}
+
+impl Drop for GpuMultibody {
+    fn drop(&mut self) {
+        unsafe { multibody_gpu_free(self.raw) }
+    }
+}
+
+// ------------------------------------------------------------------ the one new exported C symbol
+/// `int multibody_gpu_from_rust(const Multibody* mb, int device, RbGpu** out)`: lets a C/C++ program that holds
+/// the Rust `Multibody*` from `multibody_new()` (rigidbody_bindings/src/lib.rs:8-12) obtain an engine handle.
+/// Unlike the reference's exports it never unwinds across the boundary.
+#[no_mangle]
+pub unsafe extern "C" fn multibody_gpu_from_rust(mb: *const Multibody, device: c_int, out: *mut *mut RbGpu) -> c_int {
+    let result = std::panic::catch_unwind(|| {
+        let Some(mb) = mb.as_ref() else { return -1 };
+        if out.is_null() {
+            return -1;
+        }
+        let arrays = ChainArrays::from_multibody(mb);
+        let desc = arrays.desc();
+        multibody_gpu_new(&desc, device, out)
+    });
+    result.unwrap_or(-2)
+}

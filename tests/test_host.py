@@ -140,3 +140,18 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "rb_oracle" not in src and "oracle/" not in src and "import oracle" not in src, f
+
+
+def test_bench_fp64_instruction_counts_match_the_built_library(built):
+    """bench.py's executed-instruction roofline uses static SASS counts; keep them equal to the library's."""
+    import importlib.util
+    out = subprocess.run(["bash", os.path.join(ROOT, "tools", "sass_count.sh"),
+                          os.path.join(ROOT, "rigidbody_rs_b200", "librigidbody_b200.so")],
+                         capture_output=True, text=True, check=True).stdout
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    for kernel, want in bench.FP64_INSTR.items():
+        line = [l for l in out.splitlines() if l.startswith(kernel + "I7CtModel")]
+        assert len(line) == 1, out
+        got = int(line[0].split("FP64 total")[1].split()[0])
+        assert got == want, (kernel, got, want)

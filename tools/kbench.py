@@ -21,9 +21,24 @@ q = torch.empty((n, B), dtype=torch.float64, device=dev)
 dq, x3, out = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
 mb.fill(q, 1, 0, lim["lower"], lim["upper"]); mb.fill(dq, 1, 1, -lim["velocity"], lim["velocity"]); mb.fill(x3, 1, 2, -10.0, 10.0)
 res = {"tag": a.tag, "variant": mb.kernel_variant, "states": B}
+H = 64
 for op in a.ops.split(","):
-    fn = {"rnea": lambda: mb.rnea(q, dq, x3, out=out), "fd": lambda: mb.forward_dynamics(q, dq, x3, out=out),
-          "crba": None}[op]
+    units = B
+    if op == "rollout":
+        Bt = min(B, 65536)
+        tau = torch.empty((H, n, Bt), dtype=torch.float64, device=dev)
+        for t in range(H):
+            mb.fill(tau[t], 3, 4 + t % 32, -lim["effort"], lim["effort"], first_index=t * Bt)
+        q0, dq0 = q[:, :Bt].contiguous(), dq[:, :Bt].contiguous()
+        fn = lambda: mb.rollout(q0, dq0, tau, 1e-3)
+        units = Bt * H
+    elif op == "crba":
+        Bc = min(B, 1 << 22)
+        qc = q[:, :Bc].contiguous(); Hout = torch.empty((n * n, Bc), dtype=torch.float64, device=dev)
+        fn = lambda: mb.crba(qc, out=Hout)
+        units = Bc
+    else:
+        fn = {"rnea": lambda: mb.rnea(q, dq, x3, out=out), "fd": lambda: mb.forward_dynamics(q, dq, x3, out=out)}[op]
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -34,5 +49,5 @@ for op in a.ops.split(","):
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     med = ts[len(ts) // 2]
-    res[op] = {"ms_med": round(med, 4), "ms_min": round(ts[0], 4), "Geval_s": round(B / med / 1e6, 3)}
+    res[op] = {"ms_med": round(med, 4), "ms_min": round(ts[0], 4), "Geval_s": round(units / med / 1e6, 3)}
 print(json.dumps(res), flush=True)
