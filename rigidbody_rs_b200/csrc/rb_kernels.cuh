@@ -215,14 +215,20 @@ rb_jac_kernel(const __grid_constant__ typename M::Param p, const double* __restr
 
 // MPC rollout: the trajectory's (q, dq) stay in registers for the whole horizon; per step the
 // kernel reads tau[t] (n doubles) and writes the new (q, dq) (2n doubles).
+#ifndef RB_MINB_ROLLOUT
+#define RB_MINB_ROLLOUT 2   // measured on B200 (profiles/r1_kbench_rollout.jsonl): 255 regs, 2 blocks per SM is fastest
+#endif
+#ifndef RB_RO_BLOCK
+#define RB_RO_BLOCK 128     // threads per rollout block (smaller blocks balance the single wave across 148 SMs)
+#endif
 template <class M>
-__global__ void __launch_bounds__(RB_BLOCK)
+__global__ void __launch_bounds__(RB_RO_BLOCK, RB_MINB_ROLLOUT * (RB_BLOCK / RB_RO_BLOCK))
 rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q0, const double* __restrict__ dq0,
                   const double* __restrict__ tau, double dt, int horizon, double* __restrict__ q_traj,
                   double* __restrict__ dq_traj, double* __restrict__ q_fin, double* __restrict__ dq_fin,
                   size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
-    const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
+    const size_t s = (size_t)blockIdx.x * RB_RO_BLOCK + threadIdx.x;
     if (s >= B) return;
     double q[N], dq[N];
     rb_load<N>(q0, ld, s, q);
@@ -336,7 +342,7 @@ struct RbLaunch {
                                int horizon, double* q_traj, double* dq_traj, double* q_fin, double* dq_fin,
                                size_t B, size_t ld, int* status, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
-        rb_rollout_kernel<M><<<grid(B), RB_BLOCK, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
+        rb_rollout_kernel<M><<<(unsigned)((B + RB_RO_BLOCK - 1) / RB_RO_BLOCK), RB_RO_BLOCK, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
                                                           q_fin, dq_fin, B, ld, status);
         return cudaGetLastError();
     }
