@@ -35,10 +35,6 @@ int fail_cuda(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return fail_cuda(e__, #call);      \
     } while (0)
 
-struct RbNParamHost {           // must match RbNParam in rb_kernels_n.cu
-    const double* model; int n; double* scratch; size_t threads; size_t slots;
-};
-
 constexpr int kSlots = 3;       // depth of the host-batch pipeline
 
 struct DevBuf {
@@ -63,8 +59,12 @@ struct RbGpu {
     RbHostModel model;
     const RbOps* ops = nullptr;
     std::vector<unsigned char> param;     // host image of the kernel-parameter block `ops` expects
+    const RbOps* ops2 = nullptr;          // fallback table for entries `ops` leaves null (run-time-n family)
+    std::vector<unsigned char> param2;
+    size_t hpk_states = 0;
     double* d_model = nullptr;            // generic-n: model rows on the device
     DevBuf scratch;                       // generic-n: per-thread strided scratch
+    DevBuf hpk;                           // generic-n: packed H of one chunk of states (forward dynamics)
     size_t scratch_threads = 0;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
@@ -82,6 +82,10 @@ struct Multibody {
     std::mutex mu;
 };
 
+// Table / parameter block serving one entry point: the primary family, or the fallback where it has no kernel.
+#define RB_TABLE(g, fn) ((g)->ops->fn ? (g)->ops : (g)->ops2)
+#define RB_PARAM(g, fn) ((g)->ops->fn ? (const void*)(g)->param.data() : (const void*)(g)->param2.data())
+
 namespace {
 
 struct DeviceGuard {
@@ -93,12 +97,33 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Sets up the run-time-n family (model rows + scratch + H chunk on the device) as table `ops`/`param`.
+int setup_generic_n(RbGpu* g, const std::vector<double>& flat, const RbOps** ops, std::vector<unsigned char>* param) {
+    const int n = g->model.n;
+    *ops = rb_ops_generic_n();
+    RB_CUDA(cudaMalloc((void**)&g->d_model, flat.size() * sizeof(double)));
+    RB_CUDA(cudaMemcpy(g->d_model, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // persistent grid: 8 blocks of RB_BLOCK threads per SM; scratch sized for the largest user (rollout)
+    g->scratch_threads = (size_t)g->sm_count * 8 * RB_BLOCK;
+    const size_t slots = (size_t)12 * n + (size_t)n * n;
+    int rc = g->scratch.ensure(slots * g->scratch_threads * sizeof(double));
+    if (rc != RB_OK) return rc;
+    RbNParam P{g->d_model, n, g->scratch.p, g->scratch_threads, slots, g->hpk.p, g->hpk_states};
+    param->assign(sizeof(P), 0);
+    if ((*ops)->param_bytes != sizeof(P)) return fail(RB_ERR_ARG, "internal: RbNParam size mismatch");
+    memcpy(param->data(), &P, sizeof(P));
+    return RB_OK;
+}
+
+// Chooses the kernel family for the uploaded chain.  `ops` may leave entries null (long-chain families serve
+// rnea / fd / crba only); those calls go to the fallback table `ops2` (always the run-time-n family).
 int pick_ops(RbGpu* g) {
     const char* force = getenv("RIGIDBODY_B200_VARIANT");
     const std::string want = force ? force : "auto";
     const int n = g->model.n;
     std::vector<double> flat = rb_model_flat(g->model);
     const bool is_fr3 = n == 7 && memcmp(flat.data(), rb_fr3_table(), sizeof(double) * (7 * 24 + 3)) == 0;
+    const bool is_c32 = n == 32 && memcmp(flat.data(), rb_chain32_table(), sizeof(double) * (32 * 24 + 3)) == 0;
     if ((want == "auto" || want == "fr3-specialised") && is_fr3) {
         g->ops = rb_ops_fr3();
         g->param.assign(g->ops->param_bytes, 0);
@@ -113,20 +138,25 @@ int pick_ops(RbGpu* g) {
         return RB_OK;
     }
     if (want == "generic-7") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=generic-7 needs a 7-joint chain");
-    if (want != "auto" && want != "generic-n") return fail(RB_ERR_ARG, "unknown RIGIDBODY_B200_VARIANT '" + want + "'");
-    g->ops = rb_ops_generic_n();
-    RB_CUDA(cudaMalloc((void**)&g->d_model, flat.size() * sizeof(double)));
-    RB_CUDA(cudaMemcpy(g->d_model, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
-    // persistent grid: 8 blocks of RB_BLOCK threads per SM; scratch sized for the largest user (rollout)
-    g->scratch_threads = (size_t)g->sm_count * 8 * RB_BLOCK;
-    const size_t slots = (size_t)12 * n + (size_t)n * n;
-    int rc = g->scratch.ensure(slots * g->scratch_threads * sizeof(double));
+    if (want != "auto" && want != "generic-n" && want != "chain32-specialised")
+        return fail(RB_ERR_ARG, "unknown RIGIDBODY_B200_VARIANT '" + want + "'");
+    // forward dynamics of long chains: H (packed upper triangle) of one chunk of states lives in HBM between the
+    // kernel that builds it and the tile kernel that factorises it in shared memory (<= 1 GiB per chunk)
+    const size_t np = (size_t)n * (n + 1) / 2;
+    size_t chunk = ((size_t)1024 << 20) / (np * sizeof(double));
+    g->hpk_states = std::max<size_t>(1024, chunk / 1024 * 1024);
+    int rc = g->hpk.ensure(np * g->hpk_states * sizeof(double));
     if (rc != RB_OK) return rc;
-    RbNParamHost P{g->d_model, n, g->scratch.p, g->scratch_threads, slots};
-    g->param.assign(sizeof(P), 0);
-    if (g->ops->param_bytes != sizeof(P)) return fail(RB_ERR_ARG, "internal: RbNParam size mismatch");
-    memcpy(g->param.data(), &P, sizeof(P));
-    return RB_OK;
+    if ((want == "auto" || want == "chain32-specialised") && is_c32) {
+        g->ops = rb_ops_chain32();
+        struct { RbEmptyParam model; double* hpk; size_t hpk_states; } LP{{0}, g->hpk.p, g->hpk_states};
+        if (g->ops->param_bytes != sizeof(LP)) return fail(RB_ERR_ARG, "internal: RbLongParam size mismatch");
+        g->param.assign(sizeof(LP), 0);
+        memcpy(g->param.data(), &LP, sizeof(LP));
+        return setup_generic_n(g, flat, &g->ops2, &g->param2);
+    }
+    if (want == "chain32-specialised") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=chain32-specialised but the chain is not the compiled-in 32-joint model");
+    return setup_generic_n(g, flat, &g->ops, &g->param);
 }
 
 int gpu_create(const RbHostModel& model, int device, RbGpu** out) {
@@ -360,6 +390,7 @@ extern "C" void multibody_gpu_free(RbGpu* g) {
         if (g->ev_d2h[k]) cudaEventDestroy(g->ev_d2h[k]);
     }
     g->scratch.release();
+    g->hpk.release();
     if (g->d_model) cudaFree(g->d_model);
     if (g->d_status) cudaFree(g->d_status);
     if (g->h_status) cudaFreeHost(g->h_status);
@@ -417,7 +448,7 @@ extern "C" int multibody_rnea_batch(RbGpu* g, const double* q, const double* dq,
     const int n = g->model.n;
     OpDesc op{3, {q, dq, ddq}, {n, n, n}, tau, n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return g->ops->rnea(g->param.data(), in[0], in[1], in[2], out, B, ld, st);
+                  return RB_TABLE(g, rnea)->rnea(RB_PARAM(g, rnea), in[0], in[1], in[2], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
 }
@@ -428,7 +459,7 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
     const int n = g->model.n;
     OpDesc op{3, {q, dq, tau}, {n, n, n}, qdd, n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return g->ops->fd(g->param.data(), in[0], in[1], in[2], out, B, ld, g->d_status, st);
+                  return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[2], out, B, ld, g->d_status, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }
@@ -439,7 +470,7 @@ extern "C" int multibody_crba_batch(RbGpu* g, const double* q, double* H, size_t
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, H, n * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return g->ops->crba(g->param.data(), in[0], out, B, ld, st);
+                  return RB_TABLE(g, crba)->crba(RB_PARAM(g, crba), in[0], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
 }
@@ -450,7 +481,7 @@ extern "C" int multibody_fwd_kin_batch(RbGpu* g, const double* q, double* xyz, s
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, xyz, 3,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return g->ops->fwd_kin(g->param.data(), in[0], out, B, ld, st);
+                  return RB_TABLE(g, fwd_kin)->fwd_kin(RB_PARAM(g, fwd_kin), in[0], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
 }
@@ -461,7 +492,7 @@ extern "C" int multibody_jac_batch(RbGpu* g, const double* q, double* J, size_t 
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, J, 6 * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return g->ops->jac(g->param.data(), in[0], out, B, ld, st);
+                  return RB_TABLE(g, jac)->jac(RB_PARAM(g, jac), in[0], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
 }
@@ -482,7 +513,7 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = mem == RB_MEM_DEVICE ? (cudaStream_t)stream : g->stream;
     if (mem == RB_MEM_DEVICE && layout == RB_LAYOUT_SOA) {
-        cudaError_t e = g->ops->rollout(g->param.data(), q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_final, dq_final,
+        cudaError_t e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_final, dq_final,
                                         n_traj, ld, g->d_status, st);
         g->launches += 1;
         if (e != cudaSuccess) return fail_cuda(e, "rollout launch");
@@ -523,7 +554,7 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     rc = bring_in(dq0, d_in + one, 1); if (rc) return rc;
     rc = bring_in(tau, d_in + 2 * one, H); if (rc) return rc;
     double* d_qt = d_out; double* d_dqt = d_out + H * one; double* d_qf = d_out + 2 * H * one; double* d_dqf = d_qf + one;
-    cudaError_t e = g->ops->rollout(g->param.data(), d_in, d_in + one, d_in + 2 * one, dt, horizon,
+    cudaError_t e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), d_in, d_in + one, d_in + 2 * one, dt, horizon,
                                     q_traj ? d_qt : nullptr, dq_traj ? d_dqt : nullptr, q_final ? d_qf : nullptr,
                                     dq_final ? d_dqf : nullptr, B, B, g->d_status, st);
     g->launches += 1;

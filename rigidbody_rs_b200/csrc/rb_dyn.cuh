@@ -275,16 +275,16 @@ RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const do
 // The reference carries (m, com, I_c) and rebuilds I_o with from_com/from_origin (inertia.rs:21-51,81-105);
 // the 10-parameter update below is the same map: with R = R_p Rz(q), u = R h + (m/2) t,
 //   h' = R h + m t,   I_o' = R I_o R^T - (t u^T + u t^T) + 2 (t.u) Id,   then add link i-1's own (h, I_o).
-template <class M>
-RB_DI void rb_crba(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
-                   double (&H)[M::N][M::N]) {
+// `put(RbIC<J>, RbIC<I>, value)` receives every entry H(J, I), J <= I, once.
+template <class M, class Put>
+RB_DI void rb_crba_put(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N], Put&& put) {
     constexpr int N = M::N;
     double h[3] = {KV(N - 1, RB_F_H, 0), KV(N - 1, RB_F_H, 1), KV(N - 1, RB_F_H, 2)};            // :157
     double Ixx = KV(N - 1, RB_F_I, 0), Ixy = KV(N - 1, RB_F_I, 1), Ixz = KV(N - 1, RB_F_I, 2);
     double Iyy = KV(N - 1, RB_F_I, 3), Iyz = KV(N - 1, RB_F_I, 4), Izz = KV(N - 1, RB_F_I, 5);
     rb_for_down<N - 1>([&](auto ic) {
         constexpr int I = decltype(ic)::value;
-        H[I][I] = Izz;                                                               // :161
+        put(RbIC<I>{}, RbIC<I>{}, Izz);                                              // :161
         double Fl[3] = {-h[1], h[0], 0.0};                                           // :162  F = I^c * S_z
         double Fr[3] = {Ixz, Iyz, Izz};
         rb_for_down<I - 1>([&](auto jc) {
@@ -293,7 +293,7 @@ RB_DI void rb_crba(const typename M::Param& p, const double (&s)[M::N], const do
             rb_force<M, J + 1>(p, s[J + 1], c[J + 1], Fl, Fr, ol, orr);              // :165
             Fl[0] = ol[0]; Fl[1] = ol[1]; Fl[2] = ol[2];
             Fr[0] = orr[0]; Fr[1] = orr[1]; Fr[2] = orr[2];
-            H[J][I] = Fr[2];                                                         // :166
+            put(RbIC<J>{}, RbIC<I>{}, Fr[2]);                                        // :166
         });
         if constexpr (I > 0) {                                                       // :169-171
             const double si = s[I], ci = c[I];
@@ -348,6 +348,12 @@ RB_DI void rb_crba(const typename M::Param& p, const double (&s)[M::N], const do
             h[2] = k_fma<T2>(t2, mc, q2) + KV(I - 1, RB_F_H, 2);
         }
     });
+}
+
+template <class M>
+RB_DI void rb_crba(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
+                   double (&H)[M::N][M::N]) {
+    rb_crba_put<M>(p, s, c, [&](auto jc, auto ic, double v) { H[decltype(jc)::value][decltype(ic)::value] = v; });
 }
 
 // ------------------------------------------------------------------ solve  H x = b, H SPD given by its upper triangle

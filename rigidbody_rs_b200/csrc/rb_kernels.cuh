@@ -43,8 +43,21 @@ const RbOps* rb_ops_fr3();        // compile-time FR3 model (rb_kernels_fr3.cu)
 const RbOps* rb_ops_rt7();        // any 7-joint chain, run-time constants (rb_kernels_rt.cu)
 const RbOps* rb_ops_generic_n();  // any chain length (rb_kernels_n.cu)
 const double* rb_fr3_table();     // the 7x24 table + 3 gravity doubles the FR3 kernels were compiled for
+const RbOps* rb_ops_chain32();    // compile-time 32-joint chain, long-chain layout (rb_kernels_c32.cu)
+const double* rb_chain32_table();
 
 #define RB_STATUS_NOT_SPD 1
+
+// Parameter block of the run-time-n family (rb_kernels_n.cu); rb_api.cu fills it when a chain is uploaded.
+struct RbNParam {
+    const double* model;     // device: n rows of 24 doubles + g[3]
+    int n;
+    double* scratch;         // per-thread strided scratch: `slots` doubles per thread, element k at scratch[k*threads + tid]
+    size_t threads;          // threads the scratch was sized for (persistent grid * block)
+    size_t slots;
+    double* hpk;             // packed upper triangles of H for one chunk of states: [n(n+1)/2][hpk_states]
+    size_t hpk_states;       // states per chunk
+};
 
 template <int N>
 RB_DI void rb_load(const double* __restrict__ x, size_t ld, size_t s, double (&v)[N]) {

@@ -1,0 +1,22 @@
+// rb_kernels_c32.cu -- kernels specialised at compile time on the synthetic 32-joint chain of BASELINE.json
+// configs[4] (assets/chain32.urdf -> gen/model_chain32.h), long-chain layout (rb_kernels_long.cuh).
+// rb_api.cu selects this family only when an uploaded chain equals the table bit for bit.
+#include "rb_kernels_long.cuh"
+#include "gen/model_chain32.h"
+
+const RbOps* rb_ops_chain32() {
+    static const RbOps ops = RbLaunchLong<CtModel<TabChain32>>::ops("chain32-specialised");
+    return &ops;
+}
+
+const double* rb_chain32_table() {
+    static double flat[32 * 24 + 3];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 32; ++i)
+            for (int k = 0; k < 24; ++k) flat[i * 24 + k] = TabChain32::T[i][k];
+        for (int k = 0; k < 3; ++k) flat[32 * 24 + k] = TabChain32::G[k];
+        init = true;
+    }
+    return flat;
+}

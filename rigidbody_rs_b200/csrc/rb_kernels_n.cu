@@ -7,15 +7,6 @@
 #include "rb_dyn_n.cuh"
 #include "rb_util.cuh"
 
-// `param` for this family: { const double* model_dev; int n; double* scratch; size_t scratch_threads; }
-struct RbNParam {
-    const double* model;     // device: n rows of 24 doubles + g[3]
-    int n;
-    double* scratch;         // device scratch, `slots` doubles per thread, strided by `threads`
-    size_t threads;          // total threads the scratch was sized for (grid * block)
-    size_t slots;
-};
-
 __global__ void __launch_bounds__(RB_BLOCK)
 rbn_rnea_kernel(RbNParam P, const double* __restrict__ q, const double* __restrict__ dq, const double* __restrict__ ddq,
                 double* __restrict__ tau, size_t B, size_t ld) {
@@ -63,6 +54,135 @@ rbn_fd_kernel(RbNParam P, const double* __restrict__ q, const double* __restrict
         all_ok = all_ok && ok;
         for (int i = 0; i < n; ++i)
             __stcs(qdd + (size_t)i * ld + s, ok ? x[i] : __longlong_as_double(0x7ff8000000000000LL));
+    }
+    if (!all_ok) atomicOr(status, RB_STATUS_NOT_SPD);
+}
+
+// ---- forward dynamics for long chains, two kernels per chunk of states ----------------------------------------
+// A 32-joint mass matrix is 528 doubles: no thread can hold it, and factorising it in a per-thread global scratch
+// costs O(n^3) HBM accesses per state (the first version of this family: 0.027 G states/s for n = 32).  Instead:
+//   1. rbn_fd_prepare_kernel (thread per state, persistent): sin/cos, bias forces -> rhs = tau - rnea(q,dq,0)
+//      written into qdd, CRBA -> packed upper triangle of H streamed ONCE to HBM, coalesced ([k][state]);
+//   2. rbn_ldlt_tile_kernel: a warp pulls a tile of TS states (all n(n+1)/2 rows, 256-byte runs) into shared
+//      memory, lane = state, and runs the dot-product (Crout) LDL^T + both triangular solves entirely on chip:
+//      2 shared loads per FMA, no bank conflicts ([k][lane] layout), H read from HBM exactly once.
+// HBM traffic per state: 2 * n(n+1)/2 * 8 B for H (8.4 KB at n = 32) + the 32 n algorithmic bytes.
+__global__ void __launch_bounds__(RB_BLOCK)
+rbn_fd_prepare_kernel(RbNParam P, const double* __restrict__ q, const double* __restrict__ dq, const double* __restrict__ tau,
+                      double* __restrict__ qdd, size_t B, size_t ld) {
+    const size_t tid = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
+    const size_t nthr = (size_t)gridDim.x * RB_BLOCK;
+    const int n = P.n;
+    const RbJointK* jt = reinterpret_cast<const RbJointK*>(P.model);
+    const double* g = P.model + (size_t)n * 24;
+    RbScratch sc{P.scratch + tid, P.threads};
+    for (size_t s = tid; s < B; s += nthr) {          // B <= P.hpk_states: s doubles as the chunk-local index
+        for (int i = 0; i < n; ++i) {
+            double sn, cs;
+            sincos(__ldcs(q + (size_t)i * ld + s), &sn, &cs);
+            sc[i] = sn; sc[n + i] = cs;
+        }
+        RbScratch x{qdd + s, ld};
+        rbn_rnea(jt, g, n, sc, dq + s, nullptr, ld, x);                       // bias
+        for (int i = 0; i < n; ++i) x[i] = __ldcs(tau + (size_t)i * ld + s) - x[i];
+        double* hp = P.hpk + s;
+        const size_t hs = P.hpk_states;
+        rbn_crba(jt, n, sc, [&](int r, int c, double v) {
+            __stcs(hp + (size_t)(r * n - r * (r - 1) / 2 + (c - r)) * hs, v);
+        });
+    }
+}
+
+// One block = RB_TILE_WARPS warps sharing one tile of TS states; lane = state, warps split the columns.
+// Shared memory: S[np][TS] (packed upper, row j = entries (j, j..n-1)), M[n][TS], X[n][TS], DI[n][TS].
+// The tile arrives through cp.async (8 bytes per lane per row, every row of the tile in flight at once): a plain
+// load loop in one warp left ~528 dependent-latency round trips per tile and ran 20x slower.
+#define RB_TILE_WARPS 4
+// True iff every pivot of this lane's state was positive (DI holds 1/d_j; NaN and non-positive fail).
+__device__ __forceinline__ bool ok_all_lanes(bool, const double* DI, int n, int TS, int lane) {
+    bool ok = true;
+    for (int j = 0; j < n; ++j) ok = ok && (DI[j * TS + lane] > 0.0) && (DI[j * TS + lane] < 1.0e300);
+    return ok;
+}
+template <int TS>
+__global__ void __launch_bounds__(32 * RB_TILE_WARPS)
+rbn_ldlt_tile_kernel(int n, const double* __restrict__ hpk, size_t hpk_states, double* __restrict__ qdd, size_t B, size_t ld,
+                     int* __restrict__ status) {
+    extern __shared__ double rb_tile[];
+    const int np = n * (n + 1) / 2;
+    double* S = rb_tile;
+    double* Mv = S + (size_t)np * TS;
+    double* X = Mv + (size_t)n * TS;
+    double* DI = X + (size_t)n * TS;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t tiles = (B + TS - 1) / TS;
+    auto row = [&](int j) { return j * n - j * (j - 1) / 2 - j; };           // S(j, i) at (row(j) + i) * TS + lane
+    bool all_ok = true;
+    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const size_t s = tile * TS + lane;
+        const bool live = lane < TS && s < B;
+        if (live) {
+            for (int k = w; k < np; k += RB_TILE_WARPS) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S + (size_t)k * TS + lane);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(hpk + (size_t)k * hpk_states + s) : "memory");
+            }
+            for (int i = w; i < n; i += RB_TILE_WARPS) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(X + i * TS + lane);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qdd + (size_t)i * ld + s) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        bool ok = true;
+        // factorise: S(j, i) <- A(j, i) - sum_{k<j} (S(k, j) / d_k) S(k, i),  d_j = S(j, j).
+        // The right-hand side rides along as column n (same recurrence), which is the forward substitution:
+        // X_j <- b_j - sum_{k<j} (S(k, j) / d_k) X_k = (D U x)_j.
+        for (int j = 0; j < n; ++j) {
+            if (live)
+                for (int k = w; k < j; k += RB_TILE_WARPS) Mv[k * TS + lane] = S[(size_t)(row(k) + j) * TS + lane] * DI[k * TS + lane];
+            __syncthreads();
+            if (live) {
+                const int rj = row(j);
+                // warp w owns columns j + w, j + w + W, ... of row j; column n is the right-hand side
+                for (int i = j + w; i <= n; i += 2 * RB_TILE_WARPS) {
+                    const int i1 = i + RB_TILE_WARPS;
+                    const bool two = i1 <= n;
+                    double* p0 = i < n ? S + (size_t)(rj + i) * TS + lane : X + j * TS + lane;
+                    double* p1 = two ? (i1 < n ? S + (size_t)(rj + i1) * TS + lane : X + j * TS + lane) : p0;
+                    double a0 = *p0, a1 = *p1;
+                    int rk = 0;                                      // row(k), advanced incrementally
+#pragma unroll 4
+                    for (int k = 0; k < j; ++k) {
+                        const double m = Mv[k * TS + lane];
+                        const double s0 = i < n ? S[(size_t)(rk + i) * TS + lane] : X[k * TS + lane];
+                        const double s1 = i1 < n ? S[(size_t)(rk + (two ? i1 : i)) * TS + lane] : X[k * TS + lane];
+                        a0 = fma(-m, s0, a0);
+                        a1 = fma(-m, s1, a1);
+                        rk += n - k - 1;
+                    }
+                    *p0 = a0;
+                    if (two) *p1 = a1;
+                    if (i == j) { ok = ok && (a0 > 0.0); DI[j * TS + lane] = 1.0 / a0; }
+                }
+            }
+            __syncthreads();
+        }
+        // U x = z with z_k = X_k / d_k, column-oriented so the warps split the rows:
+        //   for k = n-1..0: x_k = X_k / d_k (final); every i < k: X_i -= S(i, k) x_k
+        const bool okv = live ? ok_all_lanes(ok, DI, n, TS, lane) : true;
+        for (int k = n - 1; k >= 0; --k) {
+            if (live) {
+                const double xk = X[k * TS + lane] * DI[k * TS + lane];
+                for (int i = w; i < k; i += RB_TILE_WARPS)
+                    X[i * TS + lane] = fma(-S[(size_t)(row(i) + k) * TS + lane], xk, X[i * TS + lane]);
+                if (w == (k & (RB_TILE_WARPS - 1)))
+                    __stcs(qdd + (size_t)k * ld + s, okv ? xk : __longlong_as_double(0x7ff8000000000000LL));
+            }
+            __syncthreads();
+        }
+        all_ok = all_ok && okv;
+        __syncthreads();                                             // tile buffers are reused by the next iteration
     }
     if (!all_ok) atomicOr(status, RB_STATUS_NOT_SPD);
 }
@@ -187,11 +307,50 @@ cudaError_t n_rnea(const void* param, const double* q, const double* dq, const d
     rbn_rnea_kernel<<<ngrid(P, B), RB_BLOCK, 0, st>>>(*P, q, dq, ddq, tau, B, ld);
     return cudaGetLastError();
 }
+template <int TS>
+cudaError_t launch_tile(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld, int* status,
+                        size_t smem, int dev, int sms, cudaStream_t st) {
+    static size_t configured[64] = {0};     // per device: largest dynamic shared-memory size opted into
+    if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(rbn_ldlt_tile_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = smem;
+    }
+    const size_t tiles = (cnt + TS - 1) / TS;
+    size_t per_sm = (size_t)(220 * 1024) / (smem + 1024);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm);
+    const size_t cap = (size_t)sms * per_sm;
+    rbn_ldlt_tile_kernel<TS><<<(unsigned)(tiles < cap ? tiles : cap), 32 * RB_TILE_WARPS, smem, st>>>(n, hpk, hpk_states, qdd, cnt, ld, status);
+    return cudaGetLastError();
+}
+}  // namespace
+
+// Solves H x = rhs for `cnt` states: H packed upper in hpk ([n(n+1)/2][hpk_states]), rhs in qdd (overwritten by x).
+cudaError_t rb_launch_ldlt_tiles(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld,
+                                 int* status, cudaStream_t st) {
+    if (cnt == 0) return cudaSuccess;
+    const size_t rows = (size_t)n * (n + 1) / 2 + 3 * (size_t)n;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // widest tile whose shared-memory footprint fits one SM
+    if (rows * 32 * sizeof(double) <= 200 * 1024) return launch_tile<32>(n, hpk, hpk_states, qdd, cnt, ld, status, rows * 32 * sizeof(double), dev, sms, st);
+    if (rows * 16 * sizeof(double) <= 200 * 1024) return launch_tile<16>(n, hpk, hpk_states, qdd, cnt, ld, status, rows * 16 * sizeof(double), dev, sms, st);
+    return launch_tile<8>(n, hpk, hpk_states, qdd, cnt, ld, status, rows * 8 * sizeof(double), dev, sms, st);
+}
+
+namespace {
 cudaError_t n_fd(const void* param, const double* q, const double* dq, const double* tau, double* qdd, size_t B, size_t ld, int* status, cudaStream_t st) {
     const RbNParam* P = (const RbNParam*)param;
-    if (B == 0) return cudaSuccess;
-    rbn_fd_kernel<<<ngrid(P, B), RB_BLOCK, 0, st>>>(*P, q, dq, tau, qdd, B, ld, status);
-    return cudaGetLastError();
+    for (size_t off = 0; off < B; off += P->hpk_states) {
+        const size_t cnt = (B - off < P->hpk_states) ? (B - off) : P->hpk_states;
+        rbn_fd_prepare_kernel<<<ngrid(P, cnt), RB_BLOCK, 0, st>>>(*P, q + off, dq + off, tau + off, qdd + off, cnt, ld);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = rb_launch_ldlt_tiles(P->n, P->hpk, P->hpk_states, qdd + off, cnt, ld, status, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 cudaError_t n_crba(const void* param, const double* q, double* H, size_t B, size_t ld, cudaStream_t st) {
     const RbNParam* P = (const RbNParam*)param;

@@ -41,7 +41,8 @@ def _variants(rb, urdf):
 
 def test_kernel_families_selected(rb, mb_fr3, mb_chain32):
     assert mb_fr3.kernel_variant == "fr3-specialised"
-    assert mb_chain32.kernel_variant == "generic-n"
+    assert mb_chain32.kernel_variant == "chain32-specialised"
+    assert [m.kernel_variant for m in _variants(rb, CHAIN32)] == ["chain32-specialised", "generic-n"]
     names = [m.kernel_variant for m in _variants(rb, FR3)]
     assert names == ["fr3-specialised", "generic-7", "generic-n"]
 
@@ -57,12 +58,13 @@ def test_golden_vectors_fr3_all_families(rb):
         assert np.abs(mb.jac(q[:8], layout="aos") - np.array(g["jac_colmajor"])).max() < TOL
 
 
-def test_golden_vectors_chain32(mb_chain32):
+def test_golden_vectors_chain32(rb):
     g = load_golden("chain32_oracle.json")
     q, dq, ddq, tau = (np.array(g[k]) for k in ("q", "dq", "ddq", "tau_in"))
-    assert state_err(mb_chain32.rnea(q, dq, ddq, layout="aos"), np.array(g["rnea"]), 1).max() < TOL
-    assert state_err(mb_chain32.forward_dynamics(q, dq, tau, layout="aos"), np.array(g["fd"]), 1).max() < 1e-9
-    assert state_err(mb_chain32.crba(q, layout="aos"), np.array(g["crba_colmajor"])[:4], 1).max() < TOL
+    for mb in _variants(rb, CHAIN32):
+        assert state_err(mb.rnea(q, dq, ddq, layout="aos"), np.array(g["rnea"]), 1).max() < TOL, mb.kernel_variant
+        assert state_err(mb.forward_dynamics(q, dq, tau, layout="aos"), np.array(g["fd"]), 1).max() < 1e-9, mb.kernel_variant
+        assert state_err(mb.crba(q, layout="aos"), np.array(g["crba_colmajor"])[:4], 1).max() < TOL, mb.kernel_variant
 
 
 def test_survey_kats_and_single_state_calls(rb, mb_fr3):
@@ -198,7 +200,7 @@ def test_rollout_matches_oracle(rb, oracle_fr3):
         np.testing.assert_array_equal(qa.transpose(0, 2, 1), qt)
 
 
-def test_chain32_medium_batch(mb_chain32, oracle_chain32):
+def test_chain32_medium_batch(rb, mb_chain32, oracle_chain32):
     B = 4096
     o = oracle_chain32
     q = o.fill(0x5EED0005, 0, -np.pi, np.pi, 0, B); dq = o.fill(0x5EED0005, 1, -2.0, 2.0, 0, B)
@@ -208,6 +210,17 @@ def test_chain32_medium_batch(mb_chain32, oracle_chain32):
     assert state_err(mb_chain32.forward_dynamics(q, dq, tau), o.forward_dynamics_batch(q, dq, tau), 0).max() < 1e-9
     t = mb_chain32.rnea(q, dq, ddq)
     assert state_err(mb_chain32.forward_dynamics(q, dq, t), ddq, 0).max() < 1e-8
+    # the run-time-n family on the same chain, plus fwd_kin / jac / rollout which the long-chain family delegates to it
+    gen = [m for m in _variants(rb, CHAIN32) if m.kernel_variant == "generic-n"][0]
+    assert state_err(gen.rnea(q, dq, ddq), o.rnea_batch(q, dq, ddq), 0).max() < TOL
+    assert state_err(gen.forward_dynamics(q, dq, tau), o.forward_dynamics_batch(q, dq, tau), 0).max() < 1e-9
+    fk = mb_chain32.fwd_kin(q[:, :64]); jc = mb_chain32.jac(q[:, :64])
+    for s in range(0, 64, 7):
+        assert np.abs(fk[:, s] - o.fwd_kin(q[:, s])).max() < TOL
+        assert np.abs(jc[:, s].reshape(32, 6).T - o.jac(q[:, s])).max() < TOL
+    qt, dqt = mb_chain32.rollout(q[:, :8], dq[:, :8], np.repeat(tau[None, :, :8], 4, axis=0), 1e-3)
+    oq, odq = o.rollout_batch(q[:, :8], dq[:, :8], np.repeat(tau[None, :, :8], 4, axis=0), 1e-3)
+    assert state_err(qt, oq, 1).max() < 1e-9 and state_err(dqt, odq, 1).max() < 1e-9
 
 
 def test_not_spd_is_reported(rb):
