@@ -64,23 +64,50 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe)."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md recipe).
+    NVML through pynvml (a query takes ~0.1 ms, so even a 20 ms timed region gets several samples); falls back to
+    polling nvidia-smi when pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            while not self._stop_evt.is_set():
+                try:
+                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)),
+                                      nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0,
+                                      int(self._reasons(self.handle))))
+                except Exception:
+                    pass
+                self._stop_evt.wait(0.002)
+            return
+        fields = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) == 7:
-                    self.rows.append(parts)
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={fields}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in out.strip().split(",")]
+                if len(p) == 7:
+                    mask = sum(bit for bit, k in zip((0x8, 0x40, 0x20, 0x4), range(3, 7)) if p[k].lower().startswith("active"))
+                    self.max_mhz = float(p[1])
+                    self.rows.append((float(p[0]), float(p[2]), mask))
             except Exception:
                 pass
             self._stop_evt.wait(0.1)
@@ -90,11 +117,14 @@ class ClockSampler(threading.Thread):
         self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": getattr(self, "max_mhz", None),
+                "reasons": [name for bit, name in self.REASONS.items() if mask & bit],
+                "power_w_max": max(r[1] for r in self.rows), "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle; test infrastructure)
@@ -126,7 +156,13 @@ def cpu_arm(sample_states, steps, warmup):
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return {"value": 2.0 * S / sec, "unit": UNIT, "cores": threads, "kind": "port",
+    # BASELINE.json configs[0]: one state, one core (the reference's bench_rnea input, multibody.rs:204-209)
+    z = np.zeros((7, 1)); reps = 20000
+    t0 = time.perf_counter()
+    for _ in range(3):
+        orc.rnea_batch(np.repeat(z, reps, 1), np.repeat(z, reps, 1), np.repeat(z, reps, 1), threads=1)
+    single_ns = (time.perf_counter() - t0) / (3 * reps) * 1e9
+    return {"value": 2.0 * S / sec, "unit": UNIT, "cores": threads, "kind": "port", "single_state_rnea_ns_one_core": single_ns,
             "sample": f"{S} FR3 states per step (RNEA + FD each), {steps} timed steps, OpenMP static over {threads} threads, "
                       f"oracle/rb_oracle.c -O3 -march=native"}, sec, S
 
@@ -267,6 +303,78 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
 
 
+def run_other(args, rank, local_rank, world):
+    """BASELINE.json configs[3] (FR3 MPC rollout, 65 536 trajectories x 64 steps, strong scaling: the trajectories
+    are split across ranks) and configs[4] (32-joint chain RNEA + FD, weak scaling).  Same JSON shape, kernel-only."""
+    import torch
+    import torch.distributed as dist
+    import rigidbody_rs_b200 as rb
+    from rigidbody_rs_b200.shard import max_over_ranks, shard_bounds, sum_over_ranks
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    rollout = args.workload == "rollout"
+    mb = rb.Multibody.from_urdf(os.path.join(ROOT, "assets", "fr3.urdf" if rollout else "chain32.urdf"), device=local_rank)
+    n, lim = mb.n, mb.limits()
+    H = 64
+    if rollout:
+        lo, hi = shard_bounds(65536, world, rank)
+        B, first, seed = hi - lo, lo, 0x5EED0003
+    else:
+        B = args.states if args.states != STATES_PER_GPU else 1 << 22
+        first, seed = rank * B, 0x5EED0005
+    q = torch.empty((n, B), dtype=torch.float64, device=dev)
+    dq, x3, out, out2 = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    mb.fill(q, seed, 0, lim["lower"], lim["upper"], first)
+    mb.fill(dq, seed, 1, -lim["velocity"], lim["velocity"], first)
+    if rollout:
+        tau = torch.empty((H, n, B), dtype=torch.float64, device=dev)
+        for t in range(H):
+            mb.fill(tau[t], seed, 4 + t % 32, -lim["effort"], lim["effort"], t * 65536 + first)
+        step = lambda: mb.rollout(q, dq, tau, 1e-3)
+        units_rank, flops, label = float(B * H), 4208.0, "rb_rollout_kernel"
+    else:
+        mb.fill(x3, seed, 2, -10.0, 10.0, first)
+        tau_in = torch.empty_like(q)
+        mb.fill(tau_in, seed, 3, -lim["effort"], lim["effort"], first)
+        def step():
+            mb.rnea(q, dq, x3, out=out)
+            mb.forward_dynamics(q, dq, tau_in, out=out2)
+        units_rank, flops, label = 2.0 * B, (9476.0 + 53800.0) / 2, "rb_long_rnea_kernel + rb_fd_prepare_kernel + rbn_ldlt_tile_kernel"
+    for _ in range(args.warmup):
+        step()
+    fp64_peak = mb.fp64_peak_tflops(100)
+    sampler = ClockSampler(local_rank); sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = mb.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+    units = sum_over_ranks(units_rank, dev)
+    tf = flops * units / world / (ms * 1e-3) / 1e12
+    line = {"metric": "FR3 MPC rollout FD steps/sec (fp64)" if rollout else "chain32 RNEA+FD evals/sec (fp64)",
+            "value": units / (ms * 1e-3), "unit": "steps/s" if rollout else UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if rollout else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "fr3_rollout_65536x64" if rollout else "chain32_rnea+fd", "states_per_gpu": B, "n_joints": n,
+                       "horizon": H if rollout else None, "dt": 1e-3 if rollout else None, "kernel_variant": mb.kernel_variant,
+                       "parallelism": f"dp{world}"},
+            "roofline": {"kernel": label, "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                         "traffic": None, "flops_per_unit": flops},
+            "gpu_launches": int(mb.launch_count - l0), "clocks": clocks}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +385,8 @@ def main():
     ap.add_argument("--e2e-states", type=int, default=STATES_PER_GPU, help="states per GPU per end-to-end step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="fr3", choices=["fr3", "rollout", "chain32"],
+                    help="fr3 = the headline RNEA+FD line (BASELINE.json configs[1]+[2]); rollout = configs[3]; chain32 = configs[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -293,7 +403,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, local_rank, world)
+        (run_ours if args.workload == "fr3" else run_other)(args, rank, local_rank, world)
     finally:
         if world > 1:
             dist.destroy_process_group()
