@@ -33,7 +33,7 @@ RNEA_FLOPS, FD_FLOPS, BYTES_PER_EVAL = 2026.0, 4180.0, 224.0
 SEED_RNEA, SEED_FD = 0x5EED0001, 0x5EED0002
 # FP64-pipe SASS instructions one thread (= one state) executes in the fr3-specialised kernels: static count of
 # the straight-line kernels (tools/sass_count.sh; tests/test_host.py checks these against the built library).
-FP64_INSTR = {"rb_rnea_kernel": 635, "rb_fd_kernel": 1154}
+FP64_INSTR = {"rb_rnea_kernel": 635, "rb_fd_kernel": 1130}
 FP64_LANES_PER_SM = 64
 
 

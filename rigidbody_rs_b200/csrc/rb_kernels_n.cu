@@ -27,40 +27,9 @@ rbn_rnea_kernel(RbNParam P, const double* __restrict__ q, const double* __restri
     }
 }
 
-// scratch slots: [0,2n) sincos, [2n,8n) f, [8n, 8n+n*n) H, then n for rhs/x, n for dinv
-__global__ void __launch_bounds__(RB_BLOCK)
-rbn_fd_kernel(RbNParam P, const double* __restrict__ q, const double* __restrict__ dq, const double* __restrict__ tau,
-              double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
-    const size_t tid = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    const size_t nthr = (size_t)gridDim.x * RB_BLOCK;
-    const int n = P.n;
-    const RbJointK* jt = reinterpret_cast<const RbJointK*>(P.model);
-    const double* g = P.model + (size_t)n * 24;
-    RbScratch sc{P.scratch + tid, P.threads};
-    RbScratch Hs{P.scratch + tid + (size_t)(8 * n) * P.threads, P.threads};
-    RbScratch x{P.scratch + tid + (size_t)(8 * n + n * n) * P.threads, P.threads};
-    RbScratch dinv{P.scratch + tid + (size_t)(9 * n + n * n) * P.threads, P.threads};
-    bool all_ok = true;
-    for (size_t s = tid; s < B; s += nthr) {
-        for (int i = 0; i < n; ++i) {
-            double sn, cs;
-            sincos(__ldcs(q + (size_t)i * ld + s), &sn, &cs);
-            sc[i] = sn; sc[n + i] = cs;
-        }
-        rbn_rnea(jt, g, n, sc, dq + s, nullptr, ld, x);                       // bias
-        for (int i = 0; i < n; ++i) x[i] = __ldcs(tau + (size_t)i * ld + s) - x[i];
-        rbn_crba(jt, n, sc, [&](int r, int c, double v) { Hs[r * n + c] = v; });
-        const bool ok = rbn_ldlt_solve(n, Hs, x, dinv);
-        all_ok = all_ok && ok;
-        for (int i = 0; i < n; ++i)
-            __stcs(qdd + (size_t)i * ld + s, ok ? x[i] : __longlong_as_double(0x7ff8000000000000LL));
-    }
-    if (!all_ok) atomicOr(status, RB_STATUS_NOT_SPD);
-}
-
 // ---- forward dynamics for long chains, two kernels per chunk of states ----------------------------------------
 // A 32-joint mass matrix is 528 doubles: no thread can hold it, and factorising it in a per-thread global scratch
-// costs O(n^3) HBM accesses per state (the first version of this family: 0.027 G states/s for n = 32).  Instead:
+// costs O(n^3) HBM accesses per state (the first version of this family did that: 0.027 G states/s for n = 32).  Instead:
 //   1. rbn_fd_prepare_kernel (thread per state, persistent): sin/cos, bias forces -> rhs = tau - rnea(q,dq,0)
 //      written into qdd, CRBA -> packed upper triangle of H streamed ONCE to HBM, coalesced ([k][state]);
 //   2. rbn_ldlt_tile_kernel: a warp pulls a tile of TS states (all n(n+1)/2 rows, 256-byte runs) into shared
@@ -249,7 +218,9 @@ rbn_fk_jac_kernel(RbNParam P, const double* __restrict__ q, double* __restrict__
     }
 }
 
-// scratch slots as rbn_fd_kernel, plus 2n for the carried (q, dq)
+// scratch slots: [0,2n) sincos, [2n,8n) f, [8n, 8n+n*n) H, n rhs/x, n dinv, 2n carried (q, dq).  The per-step solve
+// still factorises H in the per-thread global scratch (slow for long chains; rollouts of long chains are not a
+// BASELINE.json configuration).
 __global__ void __launch_bounds__(RB_BLOCK)
 rbn_rollout_kernel(RbNParam P, const double* __restrict__ q0, const double* __restrict__ dq0, const double* __restrict__ tau,
                    double dt, int horizon, double* __restrict__ q_traj, double* __restrict__ dq_traj,
