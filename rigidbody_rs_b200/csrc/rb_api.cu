@@ -219,6 +219,9 @@ struct OpDesc {
     int out_per;                 // doubles per state of the output
     // launch on SoA device buffers with leading dimension ld
     cudaError_t (*launch)(RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st);
+    // optional: launch directly on AoS device buffers (kernel stages through shared memory); null = transpose around `launch`
+    cudaError_t (*launch_aos)(RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) = nullptr;
+    bool (*has_aos)(RbGpu* g) = nullptr;
 };
 
 int check_common(RbGpu* g, const OpDesc& op, size_t n_states, size_t& ld, RbLayout layout, RbMem mem) {
@@ -238,6 +241,12 @@ int check_common(RbGpu* g, const OpDesc& op, size_t n_states, size_t& ld, RbLayo
 int run_device(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout, cudaStream_t st) {
     if (layout == RB_LAYOUT_SOA) {
         cudaError_t e = op.launch(g, op.in, op.out, B, ld, st);
+        g->launches += 1;
+        if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+        return RB_OK;
+    }
+    if (op.launch_aos && op.has_aos(g)) {
+        cudaError_t e = op.launch_aos(g, op.in, op.out, B, st);
         g->launches += 1;
         if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
         return RB_OK;
@@ -275,6 +284,7 @@ int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
     chunk = std::max<size_t>(1024, std::min<size_t>(chunk, (size_t)1 << 20));
     chunk = std::min(chunk, B);
     const bool aos = layout == RB_LAYOUT_AOS;
+    const bool direct_aos = aos && op.launch_aos && op.has_aos(g);
     for (int s = 0; s < kSlots; ++s) {
         int rc = g->in[s].ensure(in_d * chunk * sizeof(double)); if (rc) return rc;
         rc = g->out[s].ensure((size_t)op.out_per * chunk * sizeof(double)); if (rc) return rc;
@@ -304,6 +314,20 @@ int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
         RB_CUDA(cudaEventRecord(g->ev_h2d[s], g->s_h2d));
         RB_CUDA(cudaStreamWaitEvent(g->stream, g->ev_h2d[s], 0));
         if (c >= kSlots) RB_CUDA(cudaStreamWaitEvent(g->stream, g->ev_d2h[s], 0));   // output slot drained
+        if (aos && direct_aos) {
+            // inputs landed in tmp[s] as AoS; the kernel reads them there and writes AoS output into out[s]
+            const double* aos_in[3]; off = 0;
+            for (int k = 0; k < op.n_in; ++k) { aos_in[k] = g->tmp[s].p + off * chunk; off += (size_t)op.in_per[k]; }
+            cudaError_t e = op.launch_aos(g, aos_in, g->out[s].p, cnt, g->stream);
+            g->launches += 1;
+            if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+            RB_CUDA(cudaEventRecord(g->ev_comp[s], g->stream));
+            RB_CUDA(cudaStreamWaitEvent(g->s_d2h, g->ev_comp[s], 0));
+            RB_CUDA(cudaMemcpyAsync(op.out + done * (size_t)op.out_per, g->out[s].p, cnt * (size_t)op.out_per * sizeof(double),
+                                    cudaMemcpyDeviceToHost, g->s_d2h));
+            RB_CUDA(cudaEventRecord(g->ev_d2h[s], g->s_d2h));
+            continue;
+        }
         if (aos) {
             off = 0;
             for (int k = 0; k < op.n_in; ++k) {
@@ -449,7 +473,11 @@ extern "C" int multibody_rnea_batch(RbGpu* g, const double* q, const double* dq,
     OpDesc op{3, {q, dq, ddq}, {n, n, n}, tau, n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
                   return RB_TABLE(g, rnea)->rnea(RB_PARAM(g, rnea), in[0], in[1], in[2], out, B, ld, st);
-              }};
+              },
+              [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) {
+                  return g->ops->rnea_aos(g->param.data(), in[0], in[1], in[2], out, B, st);
+              },
+              [](RbGpu* g) { return g->ops->rnea_aos != nullptr; }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
 }
 
@@ -460,7 +488,11 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
     OpDesc op{3, {q, dq, tau}, {n, n, n}, qdd, n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
                   return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[2], out, B, ld, g->d_status, st);
-              }};
+              },
+              [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) {
+                  return g->ops->fd_aos(g->param.data(), in[0], in[1], in[2], out, B, g->d_status, st);
+              },
+              [](RbGpu* g) { return g->ops->fd_aos != nullptr; }};
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }
 

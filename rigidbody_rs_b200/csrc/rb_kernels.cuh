@@ -31,6 +31,11 @@ struct RbOps {
                         size_t B, size_t ld, cudaStream_t st);
     cudaError_t (*fd)(const void* param, const double* q, const double* dq, const double* tau, double* qdd,
                       size_t B, size_t ld, int* status, cudaStream_t st);
+    // optional: the same two on state-major AoS batches [B][n] (null = the API transposes around the SoA kernels)
+    cudaError_t (*rnea_aos)(const void* param, const double* q, const double* dq, const double* ddq, double* tau,
+                            size_t B, cudaStream_t st);
+    cudaError_t (*fd_aos)(const void* param, const double* q, const double* dq, const double* tau, double* qdd,
+                          size_t B, int* status, cudaStream_t st);
     cudaError_t (*crba)(const void* param, const double* q, double* H, size_t B, size_t ld, cudaStream_t st);
     cudaError_t (*fwd_kin)(const void* param, const double* q, double* xyz, size_t B, size_t ld, cudaStream_t st);
     cudaError_t (*jac)(const void* param, const double* q, double* J, size_t B, size_t ld, cudaStream_t st);
@@ -70,41 +75,95 @@ RB_DI void rb_store(double* __restrict__ x, size_t ld, size_t s, const double (&
     for (int i = 0; i < N; ++i) __stcs(x + (size_t)i * ld + s, v[i]);
 }
 
-template <class M>
+// AoS batches ([B][N], the reference's double[7] repeated): a block stages its RB_BLOCK states through shared
+// memory so the global accesses stay contiguous runs; thread t then reads its N values at stride N (odd N: no
+// bank conflicts).  No extra pass over HBM, unlike a separate transpose.
+template <int N>
+RB_DI void rb_aos_load3(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ x2,
+                        size_t B, double* buf, double (&a)[N], double (&b)[N], double (&c)[N]) {
+    const size_t base = (size_t)blockIdx.x * RB_BLOCK * N;
+    const size_t rest = B * N - base;
+    const int cnt = rest < (size_t)RB_BLOCK * N ? (int)rest : RB_BLOCK * N;
+    double* b0 = buf; double* b1 = buf + RB_BLOCK * N; double* b2 = buf + 2 * RB_BLOCK * N;
+    for (int k = threadIdx.x; k < cnt; k += RB_BLOCK) {
+        b0[k] = __ldcs(x0 + base + k); b1[k] = __ldcs(x1 + base + k); b2[k] = __ldcs(x2 + base + k);
+    }
+    __syncthreads();
+    const int o = threadIdx.x * N;
+    if (o < cnt) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a[i] = b0[o + i]; b[i] = b1[o + i]; c[i] = b2[o + i]; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a[i] = 0.0; b[i] = 0.0; c[i] = 0.0; }
+    }
+    __syncthreads();
+}
+template <int N>
+RB_DI void rb_aos_store(double* __restrict__ out, size_t B, double* buf, const double (&v)[N]) {
+    const size_t base = (size_t)blockIdx.x * RB_BLOCK * N;
+    const size_t rest = B * N - base;
+    const int cnt = rest < (size_t)RB_BLOCK * N ? (int)rest : RB_BLOCK * N;
+    const int o = threadIdx.x * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) buf[o + i] = v[i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt; k += RB_BLOCK) __stcs(out + base + k, buf[k]);
+}
+
+template <class M, bool AOS = false>
 __global__ void __launch_bounds__(RB_BLOCK, RB_MINB_RNEA)
 rb_rnea_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
                const double* __restrict__ ddq, double* __restrict__ tau, size_t B, size_t ld) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    if (s >= B) return;
     double a[N], b[N], c[N], sn[N], cs[N], t[N];
-    rb_load<N>(q, ld, s, a);
-    rb_load<N>(dq, ld, s, b);
-    rb_load<N>(ddq, ld, s, c);
-    rb_sincos_all<N>(a, sn, cs);
-    rb_rnea<M, true>(p, sn, cs, b, c, t);
-    rb_store<N>(tau, ld, s, t);
+    if constexpr (AOS) {
+        extern __shared__ double rb_aos_buf[];
+        rb_aos_load3<N>(q, dq, ddq, B, rb_aos_buf, a, b, c);
+        rb_sincos_all<N>(a, sn, cs);
+        rb_rnea<M, true>(p, sn, cs, b, c, t);
+        rb_aos_store<N>(tau, B, rb_aos_buf, t);
+    } else {
+        if (s >= B) return;
+        rb_load<N>(q, ld, s, a);
+        rb_load<N>(dq, ld, s, b);
+        rb_load<N>(ddq, ld, s, c);
+        rb_sincos_all<N>(a, sn, cs);
+        rb_rnea<M, true>(p, sn, cs, b, c, t);
+        rb_store<N>(tau, ld, s, t);
+    }
 }
 
-template <class M>
+template <class M, bool AOS = false>
 __global__ void __launch_bounds__(RB_BLOCK, RB_MINB_FD)
 rb_fd_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
              const double* __restrict__ tau, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    if (s >= B) return;
     double a[N], b[N], c[N], sn[N], cs[N], x[N];
-    rb_load<N>(q, ld, s, a);
-    rb_load<N>(dq, ld, s, b);
-    rb_load<N>(tau, ld, s, c);
+    if constexpr (AOS) {
+        extern __shared__ double rb_aos_buf[];
+        rb_aos_load3<N>(q, dq, tau, B, rb_aos_buf, a, b, c);
+    } else {
+        if (s >= B) return;
+        rb_load<N>(q, ld, s, a);
+        rb_load<N>(dq, ld, s, b);
+        rb_load<N>(tau, ld, s, c);
+    }
     rb_sincos_all<N>(a, sn, cs);
     const bool ok = rb_forward_dynamics<M>(p, sn, cs, b, c, x);
     if (!ok) {
-        atomicOr(status, RB_STATUS_NOT_SPD);
+        if (s < B) atomicOr(status, RB_STATUS_NOT_SPD);     // padding threads of an AoS tail block do not count
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = __longlong_as_double(0x7ff8000000000000LL);
     }
-    rb_store<N>(qdd, ld, s, x);
+    if constexpr (AOS) {
+        extern __shared__ double rb_aos_buf[];
+        rb_aos_store<N>(qdd, B, rb_aos_buf, x);
+    } else {
+        rb_store<N>(qdd, ld, s, x);
+    }
 }
 
 // ------------------------------------------------------------------ streaming (persistent, TMA-fed) RNEA / FD
@@ -336,6 +395,19 @@ struct RbLaunch {
         rb_fd_kernel<M><<<grid(B - done), RB_BLOCK, 0, st>>>(*(const P*)param, q + done, dq + done, tau + done, qdd + done, B - done, ld, status);
         return cudaGetLastError();
     }
+    static constexpr size_t aos_smem = (size_t)3 * RB_BLOCK * M::N * sizeof(double);
+    static cudaError_t rnea_aos(const void* param, const double* q, const double* dq, const double* ddq, double* tau,
+                                size_t B, cudaStream_t st) {
+        if (B == 0) return cudaSuccess;
+        rb_rnea_kernel<M, true><<<grid(B), RB_BLOCK, aos_smem, st>>>(*(const P*)param, q, dq, ddq, tau, B, 0);
+        return cudaGetLastError();
+    }
+    static cudaError_t fd_aos(const void* param, const double* q, const double* dq, const double* tau, double* qdd,
+                              size_t B, int* status, cudaStream_t st) {
+        if (B == 0) return cudaSuccess;
+        rb_fd_kernel<M, true><<<grid(B), RB_BLOCK, aos_smem, st>>>(*(const P*)param, q, dq, tau, qdd, B, 0, status);
+        return cudaGetLastError();
+    }
     static cudaError_t crba(const void* param, const double* q, double* H, size_t B, size_t ld, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
         rb_crba_kernel<M><<<grid(B), RB_BLOCK, 0, st>>>(*(const P*)param, q, H, B, ld);
@@ -362,7 +434,8 @@ struct RbLaunch {
     static RbOps ops(const char* name) {
         RbOps o;
         o.name = name; o.n = M::N; o.param_bytes = sizeof(P);
-        o.rnea = &rnea; o.fd = &fd; o.crba = &crba; o.fwd_kin = &fwd_kin; o.jac = &jac; o.rollout = &rollout;
+        o.rnea = &rnea; o.fd = &fd; o.rnea_aos = &rnea_aos; o.fd_aos = &fd_aos;
+        o.crba = &crba; o.fwd_kin = &fwd_kin; o.jac = &jac; o.rollout = &rollout;
         return o;
     }
 };

@@ -119,7 +119,7 @@ struct RbLaunchLong {
     static RbOps ops(const char* name) {
         RbOps o;
         o.name = name; o.n = M::N; o.param_bytes = sizeof(LP);
-        o.rnea = &rnea; o.fd = &fd; o.crba = &crba; o.fwd_kin = nullptr; o.jac = nullptr; o.rollout = nullptr;
+        o.rnea = &rnea; o.fd = &fd; o.rnea_aos = nullptr; o.fd_aos = nullptr; o.crba = &crba; o.fwd_kin = nullptr; o.jac = nullptr; o.rollout = nullptr;
         return o;
     }
 };

@@ -174,6 +174,28 @@ def test_device_tensors_all_ops_medium_batch(rb, oracle_fr3):
             assert np.abs(jc[:, s].reshape(7, 6).T - oracle_fr3.jac(q[:, s])).max() < TOL
 
 
+def test_aos_device_batches_equal_soa_bitwise(rb, oracle_fr3):
+    """AoS [B][7] device tensors go through the in-kernel shared-memory staging (no transposes) for the unrolled
+    families and must give exactly the SoA kernel's numbers, including a ragged last block."""
+    import torch
+    B = 100_003
+    q, dq, ddq, tau = _states(oracle_fr3, B)
+    dev = torch.device("cuda:0")
+    soa = [torch.from_numpy(x).to(dev) for x in (q, dq, ddq, tau)]
+    aos = [t.t().contiguous() for t in soa]
+    for mb in _variants(rb, FR3):
+        l0 = mb.launch_count
+        t_aos = mb.rnea(aos[0], aos[1], aos[2], layout="aos")
+        launches = mb.launch_count - l0
+        t_soa = mb.rnea(soa[0], soa[1], soa[2])
+        a_aos = mb.forward_dynamics(aos[0], aos[1], aos[3], layout="aos")
+        a_soa = mb.forward_dynamics(soa[0], soa[1], soa[3])
+        mb.sync()
+        assert torch.equal(t_aos.t(), t_soa) and torch.equal(a_aos.t(), a_soa), mb.kernel_variant
+        assert launches == (5 if mb.kernel_variant == "generic-n" else 1), (mb.kernel_variant, launches)
+    assert state_err(t_soa.cpu().numpy(), oracle_fr3.rnea_batch(q, dq, ddq), 0).max() < TOL
+
+
 def test_device_sampler_bit_identical_to_oracle(mb_fr3, oracle_fr3):
     import torch
     lim = mb_fr3.limits()

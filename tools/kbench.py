@@ -12,6 +12,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--tag", default="")
 ap.add_argument("--urdf", default="assets/fr3.urdf")
 ap.add_argument("--ops", default="rnea,fd")
+ap.add_argument("--layout", default="soa", choices=["soa", "aos"])
 a = ap.parse_args()
 mb = rb.Multibody.from_urdf(a.urdf)
 n, B = mb.n, a.states
@@ -20,7 +21,7 @@ dev = torch.device("cuda:0")
 q = torch.empty((n, B), dtype=torch.float64, device=dev)
 dq, x3, out = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
 mb.fill(q, 1, 0, lim["lower"], lim["upper"]); mb.fill(dq, 1, 1, -lim["velocity"], lim["velocity"]); mb.fill(x3, 1, 2, -10.0, 10.0)
-res = {"tag": a.tag, "variant": mb.kernel_variant, "states": B}
+res = {"tag": a.tag, "variant": mb.kernel_variant, "states": B, "layout": a.layout}
 H = 64
 for op in a.ops.split(","):
     units = B
@@ -38,7 +39,12 @@ for op in a.ops.split(","):
         fn = lambda: mb.crba(qc, out=Hout)
         units = Bc
     else:
-        fn = {"rnea": lambda: mb.rnea(q, dq, x3, out=out), "fd": lambda: mb.forward_dynamics(q, dq, x3, out=out)}[op]
+        if a.layout == "aos":
+            qa, dqa, x3a, outa = (t.t().contiguous() for t in (q, dq, x3, out))
+            fn = {"rnea": lambda: mb.rnea(qa, dqa, x3a, layout="aos", out=outa),
+                  "fd": lambda: mb.forward_dynamics(qa, dqa, x3a, layout="aos", out=outa)}[op]
+        else:
+            fn = {"rnea": lambda: mb.rnea(q, dq, x3, out=out), "fd": lambda: mb.forward_dynamics(q, dq, x3, out=out)}[op]
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
