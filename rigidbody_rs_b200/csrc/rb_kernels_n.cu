@@ -66,7 +66,9 @@ rbn_fd_prepare_kernel(RbNParam P, const double* __restrict__ q, const double* __
 // Shared memory: S[np][TS] (packed upper, row j = entries (j, j..n-1)), M[n][TS], X[n][TS], DI[n][TS].
 // The tile arrives through cp.async (8 bytes per lane per row, every row of the tile in flight at once): a plain
 // load loop in one warp left ~528 dependent-latency round trips per tile and ran 20x slower.
-#define RB_TILE_WARPS 4
+#ifndef RB_TILE_WARPS
+#define RB_TILE_WARPS 16
+#endif
 // True iff every pivot of this lane's state was positive (DI holds 1/d_j; NaN and non-positive fail).
 __device__ __forceinline__ bool ok_all_lanes(bool, const double* DI, int n, int TS, int lane) {
     bool ok = true;
