@@ -56,6 +56,7 @@ RB_DI double k_dot3_acc(double acc, double k0, double k1, double k2, double x0, 
 template <int N_>
 struct RtModel {
     static constexpr int N = N_;
+    static constexpr bool kSpecialised = false;
     using Param = RbModelK<N_>;
     template <int I, int F, int K> static constexpr int cls() { return RB_GEN; }
     template <int I, int F, int K> static RB_DI double val(const Param& p) {
@@ -76,6 +77,7 @@ constexpr int rb_classify(double v) { return v == 0.0 ? RB_ZERO : (v == 1.0 ? RB
 template <class Tab>
 struct CtModel {
     static constexpr int N = Tab::N;
+    static constexpr bool kSpecialised = true;
     using Param = RbEmptyParam;
     template <int F, int K> static constexpr int off() {
         return F == RB_F_R ? K : F == RB_F_T ? 9 + K : F == RB_F_M ? 12 + K : F == RB_F_H ? 14 + K : 17 + K;

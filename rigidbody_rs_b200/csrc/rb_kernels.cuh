@@ -19,6 +19,13 @@
 #ifndef RB_MINB_FD
 #define RB_MINB_FD 4
 #endif
+// The run-time-constant family executes ~1.7-2x the instructions with more live values: it wants more registers.
+#ifndef RB_MINB_RNEA_RT
+#define RB_MINB_RNEA_RT 3
+#endif
+#ifndef RB_MINB_FD_RT
+#define RB_MINB_FD_RT 2
+#endif
 #ifndef RB_STREAM
 #define RB_STREAM 0        // 1 = route full tiles through the persistent TMA-fed kernels (measured slower)
 #endif
@@ -112,7 +119,7 @@ RB_DI void rb_aos_store(double* __restrict__ out, size_t B, double* buf, const d
 }
 
 template <class M, bool AOS = false>
-__global__ void __launch_bounds__(RB_BLOCK, RB_MINB_RNEA)
+__global__ void __launch_bounds__(RB_BLOCK, M::kSpecialised ? RB_MINB_RNEA : RB_MINB_RNEA_RT)
 rb_rnea_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
                const double* __restrict__ ddq, double* __restrict__ tau, size_t B, size_t ld) {
     constexpr int N = M::N;
@@ -136,7 +143,7 @@ rb_rnea_kernel(const __grid_constant__ typename M::Param p, const double* __rest
 }
 
 template <class M, bool AOS = false>
-__global__ void __launch_bounds__(RB_BLOCK, RB_MINB_FD)
+__global__ void __launch_bounds__(RB_BLOCK, M::kSpecialised ? RB_MINB_FD : RB_MINB_FD_RT)
 rb_fd_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
              const double* __restrict__ tau, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
