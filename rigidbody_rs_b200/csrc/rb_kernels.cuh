@@ -67,7 +67,7 @@ struct RbNParam {
     double* scratch;         // per-thread strided scratch: `slots` doubles per thread, element k at scratch[k*threads + tid]
     size_t threads;          // threads the scratch was sized for (persistent grid * block)
     size_t slots;
-    double* hpk;             // packed upper triangles of H for one chunk of states: [n(n+1)/2][hpk_states]
+    double* hpk;             // packed upper triangles of H for one chunk of states, tile-major [state / 32][n(n+1)/2][state % 32]
     size_t hpk_states;       // states per chunk
 };
 

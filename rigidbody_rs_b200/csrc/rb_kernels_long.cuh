@@ -21,7 +21,7 @@
 template <class M>
 struct RbLongParam {
     typename M::Param model;
-    double* hpk;             // [N(N+1)/2][hpk_states]
+    double* hpk;             // packed upper triangles, tile-major [state / 32][N(N+1)/2][state % 32]
     size_t hpk_states;
 };
 
@@ -60,10 +60,10 @@ rb_fd_prepare_kernel(const __grid_constant__ typename M::Param p, const double* 
 #pragma unroll
         for (int i = 0; i < N; ++i) __stcs(qdd + (size_t)i * ld + s, __ldcs(tau + (size_t)i * ld + s) - bias[i]);
     }
-    double* hp = hpk + s;
+    double* hp = hpk + (s >> 5) * (size_t)(N * (N + 1) / 2) * 32 + (s & 31);      // tile-major: [s / 32][k][s % 32]
     rb_crba_put<M>(p, sn, cs, [&](auto jc, auto ic, double v) {
         constexpr int J = decltype(jc)::value, I = decltype(ic)::value;
-        __stcs(hp + (size_t)(J * N - J * (J - 1) / 2 + (I - J)) * hpk_states, v);
+        __stcs(hp + (size_t)(J * N - J * (J - 1) / 2 + (I - J)) * 32, v);
     });
 }
 

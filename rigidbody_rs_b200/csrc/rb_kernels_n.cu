@@ -31,7 +31,8 @@ rbn_rnea_kernel(RbNParam P, const double* __restrict__ q, const double* __restri
 // A 32-joint mass matrix is 528 doubles: no thread can hold it, and factorising it in a per-thread global scratch
 // costs O(n^3) HBM accesses per state (the first version of this family did that: 0.027 G states/s for n = 32).  Instead:
 //   1. rbn_fd_prepare_kernel (thread per state, persistent): sin/cos, bias forces -> rhs = tau - rnea(q,dq,0)
-//      written into qdd, CRBA -> packed upper triangle of H streamed ONCE to HBM, coalesced ([k][state]);
+//      written into qdd, CRBA -> packed upper triangle of H streamed ONCE to HBM, tile-major
+//      ([state / 32][k][state % 32]: a warp writes 256-byte runs and a tile's 135 KB are contiguous);
 //   2. rbn_ldlt_tile_kernel: a warp pulls a tile of TS states (all n(n+1)/2 rows, 256-byte runs) into shared
 //      memory, lane = state, and runs the dot-product (Crout) LDL^T + both triangular solves entirely on chip:
 //      2 shared loads per FMA, no bank conflicts ([k][lane] layout), H read from HBM exactly once.
@@ -54,106 +55,118 @@ rbn_fd_prepare_kernel(RbNParam P, const double* __restrict__ q, const double* __
         RbScratch x{qdd + s, ld};
         rbn_rnea(jt, g, n, sc, dq + s, nullptr, ld, x);                       // bias
         for (int i = 0; i < n; ++i) x[i] = __ldcs(tau + (size_t)i * ld + s) - x[i];
-        double* hp = P.hpk + s;
-        const size_t hs = P.hpk_states;
+        double* hp = P.hpk + (s >> 5) * (size_t)(n * (n + 1) / 2) * 32 + (s & 31);    // tile-major: [s / 32][k][s % 32]
         rbn_crba(jt, n, sc, [&](int r, int c, double v) {
-            __stcs(hp + (size_t)(r * n - r * (r - 1) / 2 + (c - r)) * hs, v);
+            __stcs(hp + (size_t)(r * n - r * (r - 1) / 2 + (c - r)) * 32, v);
         });
     }
 }
 
 // One block = RB_TILE_WARPS warps sharing one tile of TS states; lane = state, warps split the columns.
-// Shared memory: S[np][TS] (packed upper, row j = entries (j, j..n-1)), M[n][TS], X[n][TS], DI[n][TS].
-// The tile arrives through cp.async (8 bytes per lane per row, every row of the tile in flight at once): a plain
-// load loop in one warp left ~528 dependent-latency round trips per tile and ran 20x slower.
+// Shared memory, all [row][TS]:
+//   S : row j holds entries (j, j..n) of the augmented matrix [H | rhs] (column n = right-hand side), packed:
+//       entry (j, i) at rowp(j) + i with rowp(j) = j (n + 1) - j (j - 1) / 2 - j;
+//   M0, M1 : the multipliers of the current / next row (double-buffered), n each;   DI : 1 / d_j.
+// The tile arrives through cp.async (8 bytes per lane per row, every row of the tile in flight at once).
+// Factorisation (dot-product / Crout form of H = U^T D U, S = D U): for row j and every column i in [j, n]
+//   S(j, i) = A(j, i) - sum_{k<j} m_k S(k, i),   m_k = S(k, j) / d_k,   d_j = S(j, j)
+// so the rhs column comes out as D U x (forward substitution for free).  One block barrier per row: the
+// multipliers of row j+1 that do not depend on row j are produced while row j is being computed, the last one
+// (k = j) is recomputed by every warp after the barrier.
 #ifndef RB_TILE_WARPS
-#define RB_TILE_WARPS 16
+#define RB_TILE_WARPS 8
 #endif
-// True iff every pivot of this lane's state was positive (DI holds 1/d_j; NaN and non-positive fail).
-__device__ __forceinline__ bool ok_all_lanes(bool, const double* DI, int n, int TS, int lane) {
-    bool ok = true;
-    for (int j = 0; j < n; ++j) ok = ok && (DI[j * TS + lane] > 0.0) && (DI[j * TS + lane] < 1.0e300);
-    return ok;
-}
 template <int TS>
 __global__ void __launch_bounds__(32 * RB_TILE_WARPS)
 rbn_ldlt_tile_kernel(int n, const double* __restrict__ hpk, size_t hpk_states, double* __restrict__ qdd, size_t B, size_t ld,
                      int* __restrict__ status) {
     extern __shared__ double rb_tile[];
-    const int np = n * (n + 1) / 2;
-    double* S = rb_tile;
-    double* Mv = S + (size_t)np * TS;
-    double* X = Mv + (size_t)n * TS;
-    double* DI = X + (size_t)n * TS;
+    constexpr int W = RB_TILE_WARPS;
+    const int np1 = n * (n + 1) / 2 + n;                         // rows of S
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* S = rb_tile + lane;                                  // this lane's column of every row
+    double* Mb[2] = {S + (size_t)np1 * TS, S + (size_t)(np1 + n) * TS};
+    double* DI = S + (size_t)(np1 + 2 * n) * TS;
     const size_t tiles = (B + TS - 1) / TS;
-    auto row = [&](int j) { return j * n - j * (j - 1) / 2 - j; };           // S(j, i) at (row(j) + i) * TS + lane
+    auto rowp = [&](int j) { return j * (n + 1) - j * (j - 1) / 2 - j; };
     bool all_ok = true;
     for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const size_t s = tile * TS + lane;
         const bool live = lane < TS && s < B;
         if (live) {
-            for (int k = w; k < np; k += RB_TILE_WARPS) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S + (size_t)k * TS + lane);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(hpk + (size_t)k * hpk_states + s) : "memory");
-            }
-            for (int i = w; i < n; i += RB_TILE_WARPS) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(X + i * TS + lane);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qdd + (size_t)i * ld + s) : "memory");
+            for (int j = w; j < n; j += W) {                     // warp w fetches rows w, w + W, ...
+                // packed (j, j) of this state's 32-state tile: rows of one tile are contiguous in HBM
+                const double* src = hpk + ((s >> 5) * (size_t)(n * (n + 1) / 2) + (size_t)(j * n - j * (j - 1) / 2)) * 32 + (s & 31);
+                double* dst = S + (size_t)(rowp(j) + j) * TS;
+                for (int i = j; i < n; ++i, src += 32, dst += TS) {
+                    const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d32), "l"(src) : "memory");
+                }
+                const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d32), "l"(qdd + (size_t)j * ld + s) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         bool ok = true;
-        // factorise: S(j, i) <- A(j, i) - sum_{k<j} (S(k, j) / d_k) S(k, i),  d_j = S(j, j).
-        // The right-hand side rides along as column n (same recurrence), which is the forward substitution:
-        // X_j <- b_j - sum_{k<j} (S(k, j) / d_k) X_k = (D U x)_j.
         for (int j = 0; j < n; ++j) {
-            if (live)
-                for (int k = w; k < j; k += RB_TILE_WARPS) Mv[k * TS + lane] = S[(size_t)(row(k) + j) * TS + lane] * DI[k * TS + lane];
-            __syncthreads();
+            double* Mcur = Mb[j & 1];
+            double* Mnxt = Mb[(j + 1) & 1];
             if (live) {
-                const int rj = row(j);
-                // warp w owns columns j + w, j + w + W, ... of row j; column n is the right-hand side
-                for (int i = j + w; i <= n; i += 2 * RB_TILE_WARPS) {
-                    const int i1 = i + RB_TILE_WARPS;
-                    const bool two = i1 <= n;
-                    double* p0 = i < n ? S + (size_t)(rj + i) * TS + lane : X + j * TS + lane;
-                    double* p1 = two ? (i1 < n ? S + (size_t)(rj + i1) * TS + lane : X + j * TS + lane) : p0;
-                    double a0 = *p0, a1 = *p1;
-                    int rk = 0;                                      // row(k), advanced incrementally
+                // last multiplier of this row (depends on row j-1, finished at the barrier): every warp, redundantly
+                if (j > 0) {
+                    const double m = S[(size_t)(rowp(j - 1) + j) * TS] * DI[(size_t)(j - 1) * TS];
+                    // columns j + w, j + w + W, ... <= n, two per pass (independent accumulator chains)
+                    for (int i = j + w; i <= n; i += 2 * W) {
+                        const bool two = i + W <= n;
+                        const int off1 = two ? W * TS : 0;
+                        double* pj = S + (size_t)(rowp(j) + i) * TS;
+                        double a0 = pj[0], a1 = pj[off1];
+                        const double* pk = S + (size_t)i * TS;        // (0, i); row k+1 starts n - k doubles later
+                        const double* pm = Mcur;
+                        int step = n * TS;
 #pragma unroll 4
-                    for (int k = 0; k < j; ++k) {
-                        const double m = Mv[k * TS + lane];
-                        const double s0 = i < n ? S[(size_t)(rk + i) * TS + lane] : X[k * TS + lane];
-                        const double s1 = i1 < n ? S[(size_t)(rk + (two ? i1 : i)) * TS + lane] : X[k * TS + lane];
-                        a0 = fma(-m, s0, a0);
-                        a1 = fma(-m, s1, a1);
-                        rk += n - k - 1;
+                        for (int k = 0; k < j - 1; ++k) {
+                            const double mk = *pm;
+                            a0 = fma(-mk, pk[0], a0);
+                            a1 = fma(-mk, pk[off1], a1);
+                            pk += step; step -= TS; pm += TS;
+                        }
+                        a0 = fma(-m, pk[0], a0);                       // k = j - 1 with the freshly computed multiplier
+                        a1 = fma(-m, pk[off1], a1);
+                        pj[0] = a0;
+                        if (two) pj[off1] = a1;
+                        if (i == j) { ok = ok && (a0 > 0.0); DI[(size_t)j * TS] = 1.0 / a0; }
                     }
-                    *p0 = a0;
-                    if (two) *p1 = a1;
-                    if (i == j) { ok = ok && (a0 > 0.0); DI[j * TS + lane] = 1.0 / a0; }
+                } else if (w == 0) {
+                    const double d = S[0];
+                    ok = ok && (d > 0.0);
+                    DI[0] = 1.0 / d;
                 }
+                // multipliers of row j + 1 that only need rows < j:  m_k = S(k, j + 1) / d_k
+                if (j + 1 < n)
+                    for (int k = w; k < j; k += W) Mnxt[(size_t)k * TS] = S[(size_t)(rowp(k) + j + 1) * TS] * DI[(size_t)k * TS];
             }
             __syncthreads();
         }
-        // U x = z with z_k = X_k / d_k, column-oriented so the warps split the rows:
-        //   for k = n-1..0: x_k = X_k / d_k (final); every i < k: X_i -= S(i, k) x_k
-        const bool okv = live ? ok_all_lanes(ok, DI, n, TS, lane) : true;
+        // back substitution, column-oriented so the warps split the rows.  X_k := S(k, n) = (D U x)_k:
+        //   for k = n-1..0: x_k = X_k / d_k (final);  every i < k: X_i -= S(i, k) x_k
+        bool okv = true;
+        if (live)
+            for (int j = 0; j < n; ++j) { const double v = DI[(size_t)j * TS]; okv = okv && (v > 0.0) && (v < 1.0e300); }
         for (int k = n - 1; k >= 0; --k) {
             if (live) {
-                const double xk = X[k * TS + lane] * DI[k * TS + lane];
-                for (int i = w; i < k; i += RB_TILE_WARPS)
-                    X[i * TS + lane] = fma(-S[(size_t)(row(i) + k) * TS + lane], xk, X[i * TS + lane]);
-                if (w == (k & (RB_TILE_WARPS - 1)))
-                    __stcs(qdd + (size_t)k * ld + s, okv ? xk : __longlong_as_double(0x7ff8000000000000LL));
+                const double xk = S[(size_t)(rowp(k) + n) * TS] * DI[(size_t)k * TS];
+                for (int i = w; i < k; i += W) {
+                    double* xi = S + (size_t)(rowp(i) + n) * TS;
+                    *xi = fma(-S[(size_t)(rowp(i) + k) * TS], xk, *xi);
+                }
+                if (w == (k & (W - 1))) __stcs(qdd + (size_t)k * ld + s, okv ? xk : __longlong_as_double(0x7ff8000000000000LL));
             }
             __syncthreads();
         }
         all_ok = all_ok && okv;
-        __syncthreads();                                             // tile buffers are reused by the next iteration
     }
     if (!all_ok) atomicOr(status, RB_STATUS_NOT_SPD);
 }
@@ -302,7 +315,7 @@ cudaError_t launch_tile(int n, const double* hpk, size_t hpk_states, double* qdd
 cudaError_t rb_launch_ldlt_tiles(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld,
                                  int* status, cudaStream_t st) {
     if (cnt == 0) return cudaSuccess;
-    const size_t rows = (size_t)n * (n + 1) / 2 + 3 * (size_t)n;
+    const size_t rows = (size_t)n * (n + 1) / 2 + 4 * (size_t)n;      // S (with the rhs column) + M0 + M1 + DI
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
