@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -72,8 +73,10 @@ struct RbGpu {
     int* d_status = nullptr;
     int* h_status = nullptr;              // pinned
     int sticky = RB_OK;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
+    cudaEvent_t ev_scratch = nullptr;     // orders users of the engine-owned scratch (run-time-n / long-chain families) across streams
     std::mutex mu;                        // serialises host-batch calls that share the staging buffers
+    std::mutex mu_scratch;                // guards ev_scratch
 };
 
 struct Multibody {
@@ -88,6 +91,14 @@ struct Multibody {
 
 namespace {
 
+// Kernel families that work in engine-owned scratch (RbOps::shared_scratch) must not overlap with each other
+// across streams: every such launch waits for the previous one's event and records its own.
+struct ScratchOrder {
+    RbGpu* g; cudaStream_t st; bool on;
+    ScratchOrder(RbGpu* g_, const RbOps* t, cudaStream_t st_);
+    ~ScratchOrder();
+};
+
 struct DeviceGuard {
     int prev = -1; bool ok = true;
     explicit DeviceGuard(int dev) {
@@ -98,6 +109,13 @@ struct DeviceGuard {
 };
 
 // Sets up the run-time-n family (model rows + scratch + H chunk on the device) as table `ops`/`param`.
+ScratchOrder::ScratchOrder(RbGpu* g_, const RbOps* t, cudaStream_t st_) : g(g_), st(st_), on(t->shared_scratch) {
+    if (on) { g->mu_scratch.lock(); cudaStreamWaitEvent(st, g->ev_scratch, 0); }
+}
+ScratchOrder::~ScratchOrder() {
+    if (on) { cudaEventRecord(g->ev_scratch, st); g->mu_scratch.unlock(); }
+}
+
 int setup_generic_n(RbGpu* g, const std::vector<double>& flat, const RbOps** ops, std::vector<unsigned char>* param) {
     const int n = g->model.n;
     *ops = rb_ops_generic_n();
@@ -188,6 +206,7 @@ int gpu_create(const RbHostModel& model, int device, RbGpu** out) {
         if ((e = cudaEventCreateWithFlags(&g->ev_comp[k], cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
         if ((e = cudaEventCreateWithFlags(&g->ev_d2h[k], cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
     }
+    if ((e = cudaEventCreateWithFlags(&g->ev_scratch, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
     if ((e = cudaMalloc((void**)&g->d_status, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(status)"));
     if ((e = cudaMemset(g->d_status, 0, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset(status)"));
     if ((e = cudaMallocHost((void**)&g->h_status, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMallocHost(status)"));
@@ -271,6 +290,8 @@ int run_device(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout,
     e = rb_launch_soa_to_aos(g->out[0].p, op.out, op.out_per, B, B, st);
     g->launches += 1;
     if (e != cudaSuccess) return fail_cuda(e, "soa_to_aos launch");
+    // the transposes went through engine-owned staging: drain before another call may reuse it
+    RB_CUDA(cudaStreamSynchronize(st));
     return RB_OK;
 }
 
@@ -406,7 +427,8 @@ extern "C" int multibody_gpu_from_multibody(const Multibody* mb, int device, RbG
 extern "C" void multibody_gpu_free(RbGpu* g) {
     if (!g) return;
     DeviceGuard dg(g->device);
-    if (g->stream) cudaStreamSynchronize(g->stream);
+    cudaDeviceSynchronize();              // device calls may still be running on caller streams and use our scratch
+    if (g->ev_scratch) cudaEventDestroy(g->ev_scratch);
     for (int k = 0; k < kSlots; ++k) {
         g->in[k].release(); g->out[k].release(); g->tmp[k].release();
         if (g->ev_h2d[k]) cudaEventDestroy(g->ev_h2d[k]);
@@ -429,7 +451,7 @@ extern "C" int multibody_gpu_n_joints(const RbGpu* g) { return g ? g->model.n : 
 extern "C" int multibody_gpu_device(const RbGpu* g) { return g ? g->device : fail(RB_ERR_NULL, "engine handle is NULL"); }
 extern "C" const char* multibody_gpu_kernel_variant(const RbGpu* g) { return g && g->ops ? g->ops->name : ""; }
 extern "C" const char* multibody_last_error(void) { return g_err.c_str(); }
-extern "C" uint64_t multibody_gpu_launch_count(const RbGpu* g) { return g ? g->launches : 0; }
+extern "C" uint64_t multibody_gpu_launch_count(const RbGpu* g) { return g ? g->launches.load() : (uint64_t)0; }
 
 static void copy_model(const RbHostModel& m, double* parent_rot, double* parent_trans, double* mass, double* h,
                        double* inertia_origin) {
@@ -472,6 +494,7 @@ extern "C" int multibody_rnea_batch(RbGpu* g, const double* q, const double* dq,
     const int n = g->model.n;
     OpDesc op{3, {q, dq, ddq}, {n, n, n}, tau, n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  ScratchOrder so(g, RB_TABLE(g, rnea), st);
                   return RB_TABLE(g, rnea)->rnea(RB_PARAM(g, rnea), in[0], in[1], in[2], out, B, ld, st);
               },
               [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) {
@@ -487,6 +510,7 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
     const int n = g->model.n;
     OpDesc op{3, {q, dq, tau}, {n, n, n}, qdd, n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  ScratchOrder so(g, RB_TABLE(g, fd), st);
                   return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[2], out, B, ld, g->d_status, st);
               },
               [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) {
@@ -502,6 +526,7 @@ extern "C" int multibody_crba_batch(RbGpu* g, const double* q, double* H, size_t
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, H, n * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  ScratchOrder so(g, RB_TABLE(g, crba), st);
                   return RB_TABLE(g, crba)->crba(RB_PARAM(g, crba), in[0], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
@@ -513,6 +538,7 @@ extern "C" int multibody_fwd_kin_batch(RbGpu* g, const double* q, double* xyz, s
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, xyz, 3,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  ScratchOrder so(g, RB_TABLE(g, fwd_kin), st);
                   return RB_TABLE(g, fwd_kin)->fwd_kin(RB_PARAM(g, fwd_kin), in[0], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
@@ -524,6 +550,7 @@ extern "C" int multibody_jac_batch(RbGpu* g, const double* q, double* J, size_t 
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, J, 6 * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  ScratchOrder so(g, RB_TABLE(g, jac), st);
                   return RB_TABLE(g, jac)->jac(RB_PARAM(g, jac), in[0], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
@@ -545,6 +572,7 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = mem == RB_MEM_DEVICE ? (cudaStream_t)stream : g->stream;
     if (mem == RB_MEM_DEVICE && layout == RB_LAYOUT_SOA) {
+        ScratchOrder so(g, RB_TABLE(g, rollout), st);
         cudaError_t e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_final, dq_final,
                                         n_traj, ld, g->d_status, st);
         g->launches += 1;
@@ -586,9 +614,13 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     rc = bring_in(dq0, d_in + one, 1); if (rc) return rc;
     rc = bring_in(tau, d_in + 2 * one, H); if (rc) return rc;
     double* d_qt = d_out; double* d_dqt = d_out + H * one; double* d_qf = d_out + 2 * H * one; double* d_dqf = d_qf + one;
-    cudaError_t e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), d_in, d_in + one, d_in + 2 * one, dt, horizon,
+    cudaError_t e;
+    {
+        ScratchOrder so(g, RB_TABLE(g, rollout), st);
+        e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), d_in, d_in + one, d_in + 2 * one, dt, horizon,
                                     q_traj ? d_qt : nullptr, dq_traj ? d_dqt : nullptr, q_final ? d_qf : nullptr,
                                     dq_final ? d_dqf : nullptr, B, B, g->d_status, st);
+    }
     g->launches += 1;
     if (e != cudaSuccess) return fail_cuda(e, "rollout launch");
     auto bring_out = [&](const double* src, double* dst, size_t arrays) -> int {

@@ -34,6 +34,7 @@ struct RbOps {
     const char* name;
     int n;                 // joints this table serves (0 = any, run-time n)
     size_t param_bytes;    // bytes of model parameter the launchers expect behind `param`
+    bool shared_scratch;   // kernels work in engine-owned scratch: launches must be ordered across streams
     cudaError_t (*rnea)(const void* param, const double* q, const double* dq, const double* ddq, double* tau,
                         size_t B, size_t ld, cudaStream_t st);
     cudaError_t (*fd)(const void* param, const double* q, const double* dq, const double* tau, double* qdd,
@@ -440,7 +441,7 @@ struct RbLaunch {
     }
     static RbOps ops(const char* name) {
         RbOps o;
-        o.name = name; o.n = M::N; o.param_bytes = sizeof(P);
+        o.name = name; o.n = M::N; o.param_bytes = sizeof(P); o.shared_scratch = false;
         o.rnea = &rnea; o.fd = &fd; o.rnea_aos = &rnea_aos; o.fd_aos = &fd_aos;
         o.crba = &crba; o.fwd_kin = &fwd_kin; o.jac = &jac; o.rollout = &rollout;
         return o;

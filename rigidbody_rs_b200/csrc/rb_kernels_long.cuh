@@ -118,7 +118,7 @@ struct RbLaunchLong {
     // fwd_kin / jac / rollout are served by the run-time-n family (null here = use the fallback table).
     static RbOps ops(const char* name) {
         RbOps o;
-        o.name = name; o.n = M::N; o.param_bytes = sizeof(LP);
+        o.name = name; o.n = M::N; o.param_bytes = sizeof(LP); o.shared_scratch = true;      // the H chunk buffer
         o.rnea = &rnea; o.fd = &fd; o.rnea_aos = nullptr; o.fd_aos = nullptr; o.crba = &crba; o.fwd_kin = nullptr; o.jac = nullptr; o.rollout = nullptr;
         return o;
     }

@@ -299,6 +299,35 @@ def test_concurrent_streams_and_threads(rb, mb_fr3, oracle_fr3):
     assert state_err(res["fd"][:, idx], oracle_fr3.forward_dynamics_batch(q[:, idx], dq[:, idx], tau[:, idx]), 0).max() < TOL
 
 
+def test_concurrent_streams_share_engine_scratch_safely(mb_chain32, oracle_chain32):
+    """The long-chain and run-time-n families work in engine-owned scratch (H chunk buffer, per-thread scratch);
+    calls issued from two threads on two streams must be ordered by the engine, not race."""
+    import threading
+    import torch
+    o, B = oracle_chain32, 3000
+    q = o.fill(0x5EED0005, 0, -np.pi, np.pi, 0, B); dq = o.fill(0x5EED0005, 1, -2.0, 2.0, 0, B)
+    tau1 = o.fill(0x5EED0005, 3, -50.0, 50.0, 0, B); tau2 = o.fill(0x5EED0006, 3, -50.0, 50.0, 0, B)
+    dev = torch.device("cuda:0")
+    tq, tdq, t1, t2 = (torch.from_numpy(x).to(dev) for x in (q, dq, tau1, tau2))
+    torch.cuda.synchronize()
+    res = {}
+
+    def work(name, tt):
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            outs = [mb_chain32.forward_dynamics(tq, tdq, tt) for _ in range(6)]
+        st.synchronize()
+        res[name] = outs[-1].cpu().numpy()
+
+    th = [threading.Thread(target=work, args=("a", t1)), threading.Thread(target=work, args=("b", t2))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert state_err(res["a"], o.forward_dynamics_batch(q, dq, tau1), 0).max() < 1e-9
+    assert state_err(res["b"], o.forward_dynamics_batch(q, dq, tau2), 0).max() < 1e-9
+
+
 def test_descriptor_upload_equals_urdf_load(rb, mb_fr3, oracle_fr3):
     """The RbChainDesc path (what the Rust side would call) selects the same specialised kernels and numbers."""
     from oracle.rb_oracle_np import ChainNP
