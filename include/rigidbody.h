@@ -121,8 +121,16 @@ void multibody_gpu_free(RbGpu* g);
 /* ---- introspection ------------------------------------------------------------------------- */
 int multibody_gpu_n_joints(const RbGpu* g);
 int multibody_gpu_device(const RbGpu* g);
-/* Which kernel family serves this chain: "fr3-specialised", "generic-7", "generic-n", ... */
+/* Which kernel family serves this chain: "fr3-specialised" / "chain32-specialised" (compiled in), "jit-specialised"
+ * (the same kernels compiled for this chain's constants at load time with NVRTC, cached on disk), "generic-7",
+ * "generic-n" (run-time constants).  $RIGIDBODY_B200_VARIANT forces one, $RIGIDBODY_B200_JIT=0 disables the JIT,
+ * $RIGIDBODY_B200_CACHE moves the cache directory (default ~/.cache/rigidbody_b200; empty string = no cache). */
 const char* multibody_gpu_kernel_variant(const RbGpu* g);
+/* Human-readable note on that choice (e.g. why the run-time compiler was not used). */
+const char* multibody_gpu_family_note(const RbGpu* g);
+/* Compile and cache the specialised kernels of a chain ahead of time (descriptor, or URDF path when desc is NULL).
+ * Needs libnvrtc but no GPU; `log` (optional) receives the compiler log. */
+int multibody_jit_precompile(const RbChainDesc* desc, const char* urdf_path, char* log, size_t log_len);
 /* Copies the flattened descriptor the engine uploaded (tests compare it with the oracle's model):
  * parent_rot [9n], parent_trans [3n], mass [n], h = m*com [3n], inertia_origin [6n] (xx xy xz yy yz zz). */
 int multibody_gpu_get_model(const RbGpu* g, double* parent_rot, double* parent_trans, double* mass,

@@ -61,6 +61,18 @@ class ChainNP:
             Io.append(Ic + self.m[i] * C @ C.T)                                   # inertia.rs:31-32
         self.Io = np.stack(Io)
 
+    @classmethod
+    def from_arrays(cls, Rp, tp, mass, com, inertia_com):
+        """Chain given directly by its flattened descriptor (what RbChainDesc carries)."""
+        self = cls.__new__(cls)
+        self.n = len(mass)
+        self.Rp = np.array(Rp, dtype=np.float64); self.tp = np.array(tp, dtype=np.float64)
+        self.m = np.array(mass, dtype=np.float64)
+        c = np.array(com, dtype=np.float64)
+        self.h = self.m[:, None] * c
+        self.Io = np.stack([np.array(inertia_com[i]) + self.m[i] * _skew(c[i]) @ _skew(c[i]).T for i in range(self.n)])
+        return self
+
     # -- helpers, all batched over leading axis B
     def _R(self, i, q):
         """R_i(q) = R_p Rz(q): [B,3,3]"""

@@ -137,6 +137,10 @@ class Multibody:
         check(lib.multibody_gpu_get_limits(self._h, C.byref(L)))
         return {k: np.array(getattr(L, k)[: self.n]) for k in ("lower", "upper", "velocity", "effort")}
 
+    def _note(self):
+        """Why this kernel family serves the chain (e.g. 'kernels compiled with NVRTC')."""
+        return lib.multibody_gpu_family_note(self._h).decode()
+
     @property
     def launch_count(self):
         return int(lib.multibody_gpu_launch_count(self._h))

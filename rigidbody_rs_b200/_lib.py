@@ -50,6 +50,8 @@ PROTOTYPES = {
     "multibody_gpu_n_joints": (_i, [_vp]),
     "multibody_gpu_device": (_i, [_vp]),
     "multibody_gpu_kernel_variant": (C.c_char_p, [_vp]),
+    "multibody_gpu_family_note": (C.c_char_p, [_vp]),
+    "multibody_jit_precompile": (_i, [C.POINTER(RbChainDesc), C.c_char_p, C.c_char_p, _sz]),
     "multibody_gpu_get_model": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "multibody_gpu_get_limits": (_i, [_vp, C.POINTER(RbJointLimits)]),
     "multibody_last_error": (C.c_char_p, []),

@@ -18,6 +18,7 @@
 
 #include "../../include/rigidbody.h"
 #include "rb_host_model.h"
+#include "rb_jit.h"
 #include "rb_kernels.cuh"
 #include "rb_util.cuh"
 
@@ -63,6 +64,8 @@ struct RbGpu {
     const RbOps* ops2 = nullptr;          // fallback table for entries `ops` leaves null (run-time-n family)
     std::vector<unsigned char> param2;
     size_t hpk_states = 0;
+    RbJitParam jit{};                     // run-time compiled kernels (jit-specialised family); lib == nullptr if unused
+    std::string family_note;              // why this family was chosen (e.g. the JIT fallback reason)
     double* d_model = nullptr;            // generic-n: model rows on the device
     DevBuf scratch;                       // generic-n: per-thread strided scratch
     DevBuf hpk;                           // generic-n: packed H of one chunk of states (forward dynamics)
@@ -148,6 +151,25 @@ int pick_ops(RbGpu* g) {
         return RB_OK;
     }
     if (want == "fr3-specialised") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=fr3-specialised but the chain is not the compiled-in FR3 model");
+    // Any other short chain: compile the same templates for ITS constants at run time (NVRTC, disk-cached).
+    const char* jit_env = getenv("RIGIDBODY_B200_JIT");
+    const bool jit_on = !(jit_env && std::string(jit_env) == "0");
+    if ((want == "jit-specialised" || (want == "auto" && jit_on && !is_c32)) && n <= RB_JIT_MAX_N) {
+        RbJitImage img; std::string log;
+        int rc = rb_jit_compile(g->model, img, log);
+        if (rc == RB_OK) { std::string err; rc = rb_jit_load(img, n, g->jit, err); if (rc != RB_OK) log = err; }
+        if (rc == RB_OK) {
+            g->ops = rb_ops_jit();
+            g->param.assign(sizeof(RbJitParam), 0);
+            memcpy(g->param.data(), &g->jit, sizeof(RbJitParam));
+            g->family_note = img.from_cache ? "kernels from the disk cache" : "kernels compiled with NVRTC";
+            return RB_OK;
+        }
+        if (want == "jit-specialised") return fail(rc, "run-time specialisation failed: " + log);
+        g->family_note = "run-time specialisation unavailable (" + log.substr(0, 200) + "); using run-time-constant kernels";
+    } else if (want == "jit-specialised") {
+        return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-specialised needs a chain of at most 12 joints");
+    }
     if ((want == "auto" || want == "generic-7") && n == 7) {
         g->ops = rb_ops_rt7();
         g->param.assign(g->ops->param_bytes, 0);
@@ -156,7 +178,7 @@ int pick_ops(RbGpu* g) {
         return RB_OK;
     }
     if (want == "generic-7") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=generic-7 needs a 7-joint chain");
-    if (want != "auto" && want != "generic-n" && want != "chain32-specialised")
+    if (want != "auto" && want != "generic-n" && want != "chain32-specialised" && want != "jit-specialised")
         return fail(RB_ERR_ARG, "unknown RIGIDBODY_B200_VARIANT '" + want + "'");
     // forward dynamics of long chains: H (packed upper triangle) of one chunk of states lives in HBM between the
     // kernel that builds it and the tile kernel that factorises it in shared memory (<= 1 GiB per chunk)
@@ -437,6 +459,7 @@ extern "C" void multibody_gpu_free(RbGpu* g) {
     }
     g->scratch.release();
     g->hpk.release();
+    rb_jit_unload(g->jit);
     if (g->d_model) cudaFree(g->d_model);
     if (g->d_status) cudaFree(g->d_status);
     if (g->h_status) cudaFreeHost(g->h_status);
@@ -445,6 +468,21 @@ extern "C" void multibody_gpu_free(RbGpu* g) {
     if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
     delete g;
 }
+
+extern "C" int multibody_jit_precompile(const RbChainDesc* desc, const char* urdf_path, char* log, size_t log_len) {
+    try {
+        RbHostModel m; std::string err;
+        int rc = desc ? rb_model_from_desc(desc, m, err) : rb_model_from_urdf(urdf_path, m, err);
+        if (rc != RB_OK) return fail(rc, err);
+        RbJitImage img; std::string l;
+        rc = rb_jit_compile(m, img, l);
+        if (log && log_len) { snprintf(log, log_len, "%s", l.c_str()); }
+        if (rc != RB_OK) return fail(rc, "run-time specialisation failed: " + l);
+        return RB_OK;
+    } catch (const std::exception& e) { return fail(RB_ERR_ARG, std::string("exception: ") + e.what()); }
+}
+
+extern "C" const char* multibody_gpu_family_note(const RbGpu* g) { return g ? g->family_note.c_str() : ""; }
 
 // ===================================================================== introspection
 extern "C" int multibody_gpu_n_joints(const RbGpu* g) { return g ? g->model.n : fail(RB_ERR_NULL, "engine handle is NULL"); }

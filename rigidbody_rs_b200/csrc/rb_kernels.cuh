@@ -6,8 +6,16 @@
 // warp-level load/store is one fully used 256-byte run, and each array is streamed exactly once
 // (ld.global.cs / st.global.cs, no reuse, no smem staging needed).
 #pragma once
+// RB_DEVICE_ONLY (defined by the run-time compiler, rb_jit.cu) drops everything that is host code: NVRTC
+// compiles the kernels of this header for one uploaded chain and has neither the CUDA runtime API nor <stdint.h>.
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long uintptr_t;
+#endif
 #include "rb_dyn.cuh"
 #include "rb_tma.cuh"
 
@@ -30,6 +38,7 @@
 #define RB_STREAM 0        // 1 = route full tiles through the persistent TMA-fed kernels (measured slower)
 #endif
 
+#ifndef RB_DEVICE_ONLY
 struct RbOps {
     const char* name;
     int n;                 // joints this table serves (0 = any, run-time n)
@@ -58,6 +67,7 @@ const RbOps* rb_ops_generic_n();  // any chain length (rb_kernels_n.cu)
 const double* rb_fr3_table();     // the 7x24 table + 3 gravity doubles the FR3 kernels were compiled for
 const RbOps* rb_ops_chain32();    // compile-time 32-joint chain, long-chain layout (rb_kernels_c32.cu)
 const double* rb_chain32_table();
+#endif  // RB_DEVICE_ONLY
 
 #define RB_STATUS_NOT_SPD 1
 
@@ -340,6 +350,7 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __r
     if (!ok) atomicOr(status, RB_STATUS_NOT_SPD);
 }
 
+#ifndef RB_DEVICE_ONLY
 // ------------------------------------------------------------------ launchers for policy M
 template <class M>
 struct RbLaunch {
@@ -447,3 +458,4 @@ struct RbLaunch {
         return o;
     }
 };
+#endif  // RB_DEVICE_ONLY

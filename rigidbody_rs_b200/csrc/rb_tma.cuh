@@ -1,7 +1,9 @@
 // rb_tma.cuh -- the few PTX primitives the streaming kernels need: mbarrier + 1-D bulk async copies
 // (cp.async.bulk, executed by the TMA unit; SASS UBLKCP).  sm_90+ PTX, used here on sm_100a.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #ifndef RB_DI
 #define RB_DI __device__ __forceinline__

@@ -28,7 +28,7 @@ def _states(orc, B, seed=0x5EED0001, first=0):
 def _variants(rb, urdf):
     """Every kernel family able to serve the chain (selected via RIGIDBODY_B200_VARIANT)."""
     out = []
-    for v in ("auto", "generic-7", "generic-n"):
+    for v in ("auto", "jit-specialised", "generic-7", "generic-n"):
         os.environ["RIGIDBODY_B200_VARIANT"] = v
         try:
             out.append(rb.Multibody.from_urdf(urdf))
@@ -44,7 +44,7 @@ def test_kernel_families_selected(rb, mb_fr3, mb_chain32):
     assert mb_chain32.kernel_variant == "chain32-specialised"
     assert [m.kernel_variant for m in _variants(rb, CHAIN32)] == ["chain32-specialised", "generic-n"]
     names = [m.kernel_variant for m in _variants(rb, FR3)]
-    assert names == ["fr3-specialised", "generic-7", "generic-n"]
+    assert names == ["fr3-specialised", "jit-specialised", "generic-7", "generic-n"]
 
 
 def test_golden_vectors_fr3_all_families(rb):
@@ -243,6 +243,46 @@ def test_chain32_medium_batch(rb, mb_chain32, oracle_chain32):
     qt, dqt = mb_chain32.rollout(q[:, :8], dq[:, :8], np.repeat(tau[None, :, :8], 4, axis=0), 1e-3)
     oq, odq = o.rollout_batch(q[:, :8], dq[:, :8], np.repeat(tau[None, :, :8], 4, axis=0), 1e-3)
     assert state_err(qt, oq, 1).max() < 1e-9 and state_err(dqt, odq, 1).max() < 1e-9
+
+
+def test_jit_equals_ahead_of_time_build_bitwise(rb, oracle_fr3):
+    """The FR3 kernels compiled at load time by NVRTC are the kernels nvcc compiled ahead of time: same bits out."""
+    import torch
+    q, dq, ddq, tau = _states(oracle_fr3, 50_000)
+    dev = torch.device("cuda:0")
+    tq, tdq, tddq, ttau = (torch.from_numpy(x).to(dev) for x in (q, dq, ddq, tau))
+    fam = {m.kernel_variant: m for m in _variants(rb, FR3)}
+    a, j = fam["fr3-specialised"], fam["jit-specialised"]
+    assert "NVRTC" in j._note() or "cache" in j._note()
+    for fn, x3 in (("rnea", tddq), ("forward_dynamics", ttau)):
+        assert torch.equal(getattr(a, fn)(tq, tdq, x3), getattr(j, fn)(tq, tdq, x3)), fn
+    assert torch.equal(a.crba(tq[:, :4096].contiguous()), j.crba(tq[:, :4096].contiguous()))
+    assert torch.equal(a.jac(tq[:, :4096].contiguous()), j.jac(tq[:, :4096].contiguous()))
+    ra = a.rollout(tq[:, :512].contiguous(), tdq[:, :512].contiguous(), ttau[:, :512].contiguous().unsqueeze(0).repeat(4, 1, 1), 1e-3)
+    rj = j.rollout(tq[:, :512].contiguous(), tdq[:, :512].contiguous(), ttau[:, :512].contiguous().unsqueeze(0).repeat(4, 1, 1), 1e-3)
+    assert torch.equal(ra[0], rj[0]) and torch.equal(ra[1], rj[1])
+
+
+@pytest.mark.parametrize("n,seed", [(1, 5), (3, 6), (5, 7), (7, 8), (10, 9)])
+def test_jit_random_chains_match_matrix_oracle(rb, n, seed):
+    """Chains the library has never seen (general fixed rotations, 1..10 joints) get run-time specialised kernels;
+    parity against the numpy matrix-form oracle (the C oracle takes URDF-style rpy only)."""
+    from test_host import _random_chain
+    from oracle.rb_oracle_np import ChainNP
+    R, t, m, c, Ic = _random_chain(n, seed)
+    mb = rb.Multibody.from_descriptor(R, t, m, c, Ic)
+    assert mb.kernel_variant == "jit-specialised", mb._note()
+    ch = ChainNP.from_arrays(R, t, m, c, Ic)
+    rng = np.random.default_rng(seed)
+    B = 2000
+    q, dq, ddq, tau = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n)), rng.uniform(-20, 20, (B, n))
+    assert state_err(mb.rnea(q, dq, ddq, layout="aos"), ch.rnea(q, dq, ddq), 1).max() < TOL
+    assert state_err(mb.forward_dynamics(q, dq, tau, layout="aos"), ch.forward_dynamics(q, dq, tau), 1).max() < 1e-8
+    H = mb.crba(q[:64], layout="aos").reshape(64, n, n).transpose(0, 2, 1)
+    assert np.abs(H - ch.crba(q[:64])).max() < TOL
+    assert np.abs(mb.fwd_kin(q[:64], layout="aos") - ch.fwd_kin(q[:64])[1]).max() < TOL
+    J = mb.jac(q[:64], layout="aos").reshape(64, n, 6).transpose(0, 2, 1)
+    assert np.abs(J - ch.jac(q[:64])).max() < TOL
 
 
 def test_not_spd_is_reported(rb):

@@ -155,3 +155,38 @@ def test_bench_fp64_instruction_counts_match_the_built_library(built):
         assert len(line) == 1, out
         got = int(line[0].split("FP64 total")[1].split()[0])
         assert got == want, (kernel, got, want)
+
+
+def _random_chain(n, seed):
+    """A physically valid random serial chain with general (non-axis-aligned) fixed rotations."""
+    rng = np.random.default_rng(seed)
+    from scipy.spatial.transform import Rotation
+    R = Rotation.random(n, random_state=seed).as_matrix()
+    t = rng.uniform(-0.3, 0.3, (n, 3))
+    m = rng.uniform(0.5, 4.0, n)
+    c = rng.uniform(-0.1, 0.1, (n, 3))
+    A = rng.uniform(-1, 1, (n, 3, 3))
+    Ic = np.einsum("nij,nkj->nik", A, A) * 0.01 + np.eye(3) * 0.01
+    return R, t, m, c, Ic
+
+
+def test_jit_precompile_without_gpu(rb, tmp_path, monkeypatch):
+    """The run-time specialisation compiles with NVRTC alone (no GPU): FR3 and a random 5-joint chain, then cache hits."""
+    from rigidbody_rs_b200 import _lib
+    monkeypatch.setenv("RIGIDBODY_B200_CACHE", str(tmp_path / "cache"))
+    log = C.create_string_buffer(8192)
+    assert _lib.lib.multibody_jit_precompile(None, FR3.encode(), log, 8192) == 0, (_lib.lib.multibody_last_error(), log.value)
+    assert b"cache hit" not in log.value
+    assert _lib.lib.multibody_jit_precompile(None, FR3.encode(), log, 8192) == 0
+    assert b"cache hit" in log.value
+    R, t, m, c, Ic = _random_chain(5, 11)
+    d = _lib.RbChainDesc()
+    keep = [np.ascontiguousarray(x) for x in (R, t, m, c, Ic)]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    d.n_joints = 5
+    d.parent_rot, d.parent_trans, d.mass, d.com, d.inertia_com = (dp(x) for x in keep)
+    d.gravity[:] = [0.0, 0.0, 9.81]
+    assert _lib.lib.multibody_jit_precompile(C.byref(d), None, log, 8192) == 0, (_lib.lib.multibody_last_error(), log.value)
+    assert len(os.listdir(tmp_path / "cache")) == 2
+    # chains longer than the register-resident limit are refused, not miscompiled
+    assert _lib.lib.multibody_jit_precompile(None, CHAIN32.encode(), log, 8192) == _lib.RB_ERR_UNSUPPORTED
