@@ -183,6 +183,25 @@ int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, const doubl
                       double* q_traj, double* dq_traj, double* q_final, double* dq_final,
                       size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream);
 
+/* Fused rollout + running cost for sampling-based MPC (MPPI-style): the same integration as
+ * multibody_rollout, but instead of the trajectory it returns one scalar per trajectory,
+ *   cost = sum_t dt * sum_i [ w_q[i] (q_i(t+1) - q_ref[i])^2 + w_dq[i] dq_i(t+1)^2 + w_tau[i] tau_i(t)^2 ]
+ *          + sum_i [ w_q_final[i] (q_i(H) - q_ref[i])^2 + w_dq_final[i] dq_i(H)^2 ],
+ * so nothing but tau is read and n_traj doubles are written.  Weight arrays are host arrays of n_joints
+ * non-negative doubles (NULL = zeros).  cost has n_traj entries (host or device, as `mem` says); a trajectory that
+ * met a non-SPD mass matrix gets NaN.  q_final / dq_final (one state array each) may be NULL. */
+typedef struct RbQuadCost {
+    const double* q_ref;
+    const double* w_q;
+    const double* w_dq;
+    const double* w_tau;
+    const double* w_q_final;
+    const double* w_dq_final;
+} RbQuadCost;
+int multibody_rollout_cost(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
+                           const RbQuadCost* weights, double* cost, double* q_final, double* dq_final,
+                           size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
 /* ---- device-side helpers (bench / tests) --------------------------------------------------- */
 /* Fill a device SOA array [n][ld] with the counter-based sampler of SURVEY.md 8d:
  * value(joint i, state s) = fma(hi[i]-lo[i], u, lo[i]),  u = top 53 bits of

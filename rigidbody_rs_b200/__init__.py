@@ -284,6 +284,47 @@ class Multibody:
             res += [qf.arr, dqf.arr]
         return tuple(res)
 
+    def rollout_cost(self, q0, dq0, tau, dt, q_ref=None, w_q=None, w_dq=None, w_tau=None, w_q_final=None, w_dq_final=None,
+                     layout="soa", final=False):
+        """Fused rollout + quadratic running/terminal cost (one scalar per trajectory; include/rigidbody.h
+        multibody_rollout_cost).  Shapes as `rollout`; weights are length-n vectors (None = zeros)."""
+        a_q, a_dq, a_tau = _Arg(q0, "q0"), _Arg(dq0, "dq0"), _Arg(tau, "tau")
+        cuda = a_q.cuda
+        if a_dq.cuda != cuda or a_tau.cuda != cuda:
+            raise ValueError("all arrays of one call must live in the same place")
+        n = self.n
+        if layout == "soa":
+            B = a_q.shape[1]; H = a_tau.shape[0]
+            ok = a_q.shape == (n, B) and a_dq.shape == (n, B) and a_tau.shape == (H, n, B); lay = RB_LAYOUT_SOA
+        elif layout == "aos":
+            B = a_q.shape[0]; H = a_tau.shape[0]
+            ok = a_q.shape == (B, n) and a_dq.shape == (B, n) and a_tau.shape == (H, B, n); lay = RB_LAYOUT_AOS
+        else:
+            raise ValueError("layout must be 'soa' or 'aos'")
+        if not ok:
+            raise ValueError("rollout_cost: inconsistent shapes")
+        qc = _lib.RbQuadCost()
+        keep = []
+        for name, v in (("q_ref", q_ref), ("w_q", w_q), ("w_dq", w_dq), ("w_tau", w_tau), ("w_q_final", w_q_final), ("w_dq_final", w_dq_final)):
+            if v is not None:
+                a = np.ascontiguousarray(np.broadcast_to(v, (n,)), dtype=np.float64); keep.append(a)
+                setattr(qc, name, a.ctypes.data_as(C.POINTER(C.c_double)))
+
+        def new(shape):
+            if cuda:
+                import torch
+                return _Arg(torch.empty(shape, dtype=torch.float64, device=a_q.device), "out")
+            return _Arg(np.empty(shape, dtype=np.float64), "out")
+
+        cost = new((B,))
+        qf = new(a_q.shape) if final else None
+        dqf = new(a_q.shape) if final else None
+        ptr = lambda a: C.c_void_p(a.ptr) if a is not None else None
+        check(lib.multibody_rollout_cost(self._h, ptr(a_q), ptr(a_dq), ptr(a_tau), float(dt), int(H), C.byref(qc), ptr(cost),
+                                         ptr(qf), ptr(dqf), B, 0, lay, RB_MEM_DEVICE if cuda else RB_MEM_HOST,
+                                         self._stream(cuda, a_q)))
+        return (cost.arr, qf.arr, dqf.arr) if final else cost.arr
+
     # ---- device-side sampler (bench / tests)
     def fill(self, out, seed, field, lo, hi, first_index=0):
         """Fill a CUDA float64 tensor [n, B] with the counter-based sampler of SURVEY.md 8d."""

@@ -26,6 +26,10 @@ class RbChainDesc(C.Structure):
                 ("parent_trans", _dp), ("mass", _dp), ("com", _dp), ("inertia_com", _dp), ("gravity", C.c_double * 3)]
 
 
+class RbQuadCost(C.Structure):
+    _fields_ = [(k, _dp) for k in ("q_ref", "w_q", "w_dq", "w_tau", "w_q_final", "w_dq_final")]
+
+
 class RbJointLimits(C.Structure):
     _fields_ = [(k, C.c_double * RB_MAX_JOINTS) for k in ("lower", "upper", "velocity", "effort")]
 
@@ -61,6 +65,7 @@ PROTOTYPES = {
     "multibody_fwd_kin_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_jac_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_rollout": (_i, [_vp, _vp, _vp, _vp, C.c_double, _i, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
+    "multibody_rollout_cost": (_i, [_vp, _vp, _vp, _vp, C.c_double, _i, C.POINTER(RbQuadCost), _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_gpu_fill": (_i, [_vp, _vp, _u64, C.c_uint32, _dp, _dp, _sz, _sz, _sz, _vp]),
     "multibody_gpu_sync": (_i, [_vp]),
     "multibody_gpu_status": (_i, [_vp]),

@@ -69,6 +69,7 @@ struct RbGpu {
     double* d_model = nullptr;            // generic-n: model rows on the device
     DevBuf scratch;                       // generic-n: per-thread strided scratch
     DevBuf hpk;                           // generic-n: packed H of one chunk of states (forward dynamics)
+    DevBuf cost_w;                        // rollout cost weights (RB_CW_ROWS x RB_MAX_N doubles), engine-owned: ordered like scratch
     size_t scratch_threads = 0;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
@@ -99,6 +100,7 @@ namespace {
 struct ScratchOrder {
     RbGpu* g; cudaStream_t st; bool on;
     ScratchOrder(RbGpu* g_, const RbOps* t, cudaStream_t st_);
+    ScratchOrder(RbGpu* g_, bool shared, cudaStream_t st_);
     ~ScratchOrder();
 };
 
@@ -113,6 +115,9 @@ struct DeviceGuard {
 
 // Sets up the run-time-n family (model rows + scratch + H chunk on the device) as table `ops`/`param`.
 ScratchOrder::ScratchOrder(RbGpu* g_, const RbOps* t, cudaStream_t st_) : g(g_), st(st_), on(t->shared_scratch) {
+    if (on) { g->mu_scratch.lock(); cudaStreamWaitEvent(st, g->ev_scratch, 0); }
+}
+ScratchOrder::ScratchOrder(RbGpu* g_, bool shared, cudaStream_t st_) : g(g_), st(st_), on(shared) {
     if (on) { g->mu_scratch.lock(); cudaStreamWaitEvent(st, g->ev_scratch, 0); }
 }
 ScratchOrder::~ScratchOrder() {
@@ -459,6 +464,7 @@ extern "C" void multibody_gpu_free(RbGpu* g) {
     }
     g->scratch.release();
     g->hpk.release();
+    g->cost_w.release();
     rb_jit_unload(g->jit);
     if (g->d_model) cudaFree(g->d_model);
     if (g->d_status) cudaFree(g->d_status);
@@ -594,9 +600,10 @@ extern "C" int multibody_jac_batch(RbGpu* g, const double* q, double* J, size_t 
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
 }
 
-extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
-                                 double* q_traj, double* dq_traj, double* q_final, double* dq_final,
-                                 size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+namespace {
+int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
+                 double* q_traj, double* dq_traj, double* q_final, double* dq_final, const RbQuadCost* w, double* cost,
+                 size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     if (layout != RB_LAYOUT_SOA && layout != RB_LAYOUT_AOS) return fail(RB_ERR_ARG, "bad layout");
     if (mem != RB_MEM_HOST && mem != RB_MEM_DEVICE) return fail(RB_ERR_ARG, "bad mem");
@@ -606,13 +613,28 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     if (!q0 || !dq0 || !tau) return fail(RB_ERR_NULL, "input pointer is NULL");
     if (layout == RB_LAYOUT_SOA) { if (ld == 0) ld = n_traj; if (ld < n_traj) return fail(RB_ERR_ARG, "ld < n_traj"); }
     const int n = g->model.n;
+    if (cost && !w) return fail(RB_ERR_NULL, "cost weights are NULL");
     DeviceGuard dg(g->device);
     if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = mem == RB_MEM_DEVICE ? (cudaStream_t)stream : g->stream;
+    // cost weights -> the engine's device block (shared by all cost rollouts, hence ordered like scratch)
+    double cw[RB_CW_ROWS * RB_MAX_N];
+    if (cost) {
+        memset(cw, 0, sizeof cw);
+        const double* rows[RB_CW_ROWS] = {w->q_ref, w->w_q, w->w_dq, w->w_tau, w->w_q_final, w->w_dq_final};
+        for (int r = 0; r < RB_CW_ROWS; ++r)
+            if (rows[r]) for (int i = 0; i < n; ++i) {
+                if (!std::isfinite(rows[r][i]) || (r != RB_CW_QREF && rows[r][i] < 0.0)) return fail(RB_ERR_ARG, "cost weights must be finite and non-negative");
+                cw[r * RB_MAX_N + i] = rows[r][i];
+            }
+        int rcw = g->cost_w.ensure(sizeof cw); if (rcw) return rcw;
+    }
+    const bool shared = cost != nullptr || RB_TABLE(g, rollout)->shared_scratch;
     if (mem == RB_MEM_DEVICE && layout == RB_LAYOUT_SOA) {
-        ScratchOrder so(g, RB_TABLE(g, rollout), st);
+        ScratchOrder so(g, shared, st);
+        if (cost) RB_CUDA(cudaMemcpyAsync(g->cost_w.p, cw, sizeof cw, cudaMemcpyHostToDevice, st));
         cudaError_t e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_final, dq_final,
-                                        n_traj, ld, g->d_status, st);
+                                        n_traj, ld, g->d_status, cost ? g->cost_w.p : nullptr, cost, st);
         g->launches += 1;
         if (e != cudaSuccess) return fail_cuda(e, "rollout launch");
         return RB_OK;
@@ -623,7 +645,7 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     const bool aos = layout == RB_LAYOUT_AOS, host = mem == RB_MEM_HOST;
     // in[0]: q0 | dq0 | tau[H]      out[0]: q_traj[H] | dq_traj[H] | q_fin | dq_fin      tmp[0]: AoS landing zone
     int rc = g->in[0].ensure((2 + H) * one * sizeof(double)); if (rc) return rc;
-    rc = g->out[0].ensure((2 * H + 2) * one * sizeof(double)); if (rc) return rc;
+    rc = g->out[0].ensure(((2 * H + 2) * one + B) * sizeof(double)); if (rc) return rc;      // ... | cost[B]
     if (aos) { rc = g->tmp[0].ensure(std::max<size_t>(2 + H, 2 * H + 2) * one * sizeof(double)); if (rc) return rc; }
     double* d_in = g->in[0].p; double* d_out = g->out[0].p; double* d_tmp = g->tmp[0].p;
     auto bring_in = [&](const double* src, double* dst, size_t arrays) -> int {
@@ -652,12 +674,15 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     rc = bring_in(dq0, d_in + one, 1); if (rc) return rc;
     rc = bring_in(tau, d_in + 2 * one, H); if (rc) return rc;
     double* d_qt = d_out; double* d_dqt = d_out + H * one; double* d_qf = d_out + 2 * H * one; double* d_dqf = d_qf + one;
+    double* d_cost = d_dqf + one;
     cudaError_t e;
     {
-        ScratchOrder so(g, RB_TABLE(g, rollout), st);
+        ScratchOrder so(g, shared, st);
+        if (cost) RB_CUDA(cudaMemcpyAsync(g->cost_w.p, cw, sizeof cw, cudaMemcpyHostToDevice, st));
         e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), d_in, d_in + one, d_in + 2 * one, dt, horizon,
                                     q_traj ? d_qt : nullptr, dq_traj ? d_dqt : nullptr, q_final ? d_qf : nullptr,
-                                    dq_final ? d_dqf : nullptr, B, B, g->d_status, st);
+                                    dq_final ? d_dqf : nullptr, B, B, g->d_status, cost ? g->cost_w.p : nullptr,
+                                    cost ? d_cost : nullptr, st);
     }
     g->launches += 1;
     if (e != cudaSuccess) return fail_cuda(e, "rollout launch");
@@ -687,11 +712,24 @@ extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, 
     rc = bring_out(d_qf, q_final, 1); if (rc) return rc;
     if (aos && host) RB_CUDA(cudaStreamSynchronize(st));
     rc = bring_out(d_dqf, dq_final, 1); if (rc) return rc;
-    if (host) {
-        RB_CUDA(cudaStreamSynchronize(st));
-        return fetch_status(g);
-    }
-    return RB_OK;
+    if (cost) RB_CUDA(cudaMemcpyAsync(cost, d_cost, B * sizeof(double), host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    // everything above went through engine-owned staging: drain before another call may reuse it
+    RB_CUDA(cudaStreamSynchronize(st));
+    return host ? fetch_status(g) : RB_OK;
+}
+}  // namespace
+
+extern "C" int multibody_rollout(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
+                                 double* q_traj, double* dq_traj, double* q_final, double* dq_final,
+                                 size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    return rollout_impl(g, q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_final, dq_final, nullptr, nullptr, n_traj, ld, layout, mem, stream);
+}
+
+extern "C" int multibody_rollout_cost(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
+                                      const RbQuadCost* weights, double* cost, double* q_final, double* dq_final,
+                                      size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    if (!cost) return fail(RB_ERR_NULL, "cost output pointer is NULL");
+    return rollout_impl(g, q0, dq0, tau, dt, horizon, nullptr, nullptr, q_final, dq_final, weights, cost, n_traj, ld, layout, mem, stream);
 }
 
 // ===================================================================== helpers

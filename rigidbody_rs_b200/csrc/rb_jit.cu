@@ -250,11 +250,12 @@ cudaError_t j_crba(const void* param, const double* q, double* H, size_t B, size
 cudaError_t j_fk(const void* param, const double* q, double* x, size_t B, size_t ld, cudaStream_t st) { return j_q_only((const RbJitParam*)param, RB_JK_FK, q, x, B, ld, st); }
 cudaError_t j_jac(const void* param, const double* q, double* J, size_t B, size_t ld, cudaStream_t st) { return j_q_only((const RbJitParam*)param, RB_JK_JAC, q, J, B, ld, st); }
 cudaError_t j_rollout(const void* param, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
-                      double* q_traj, double* dq_traj, double* q_fin, double* dq_fin, size_t B, size_t ld, int* status, cudaStream_t st) {
+                      double* q_traj, double* dq_traj, double* q_fin, double* dq_fin, size_t B, size_t ld, int* status,
+                      const double* cost_w, double* cost, cudaStream_t st) {
     const RbJitParam* P = (const RbJitParam*)param;
     if (B == 0) return cudaSuccess;
     RbEmptyParam ep{0};
-    void* args[] = {&ep, &q0, &dq0, &tau, &dt, &horizon, &q_traj, &dq_traj, &q_fin, &dq_fin, &B, &ld, &status};
+    void* args[] = {&ep, &q0, &dq0, &tau, &dt, &horizon, &q_traj, &dq_traj, &q_fin, &dq_fin, &B, &ld, &status, &cost_w, &cost};
     return cudaLaunchKernel((const void*)P->k[RB_JK_ROLLOUT], dim3(jgrid(B, RB_RO_BLOCK)), dim3(RB_RO_BLOCK), args, 0, st);
 }
 }  // namespace

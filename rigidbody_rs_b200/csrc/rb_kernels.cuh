@@ -58,7 +58,7 @@ struct RbOps {
     cudaError_t (*jac)(const void* param, const double* q, double* J, size_t B, size_t ld, cudaStream_t st);
     cudaError_t (*rollout)(const void* param, const double* q0, const double* dq0, const double* tau, double dt,
                            int horizon, double* q_traj, double* dq_traj, double* q_fin, double* dq_fin,
-                           size_t B, size_t ld, int* status, cudaStream_t st);
+                           size_t B, size_t ld, int* status, const double* cost_w, double* cost, cudaStream_t st);
 };
 
 const RbOps* rb_ops_fr3();        // compile-time FR3 model (rb_kernels_fr3.cu)
@@ -308,6 +308,8 @@ rb_jac_kernel(const __grid_constant__ typename M::Param p, const double* __restr
 #ifndef RB_MINB_ROLLOUT
 #define RB_MINB_ROLLOUT 2   // measured on B200 (profiles/r1_kbench_rollout.jsonl): 255 regs, 2 blocks per SM is fastest
 #endif
+// Rows of the cost-weight block a rollout may carry: cost_w[row * RB_MAX_N + joint] (see RbQuadCost in rigidbody.h).
+enum : int { RB_CW_QREF = 0, RB_CW_Q, RB_CW_DQ, RB_CW_TAU, RB_CW_QF, RB_CW_DQF, RB_CW_ROWS };
 #ifndef RB_RO_BLOCK
 #define RB_RO_BLOCK 128     // threads per rollout block (smaller blocks balance the single wave across 148 SMs)
 #endif
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(RB_RO_BLOCK, RB_MINB_ROLLOUT * (RB_BLOCK / RB_
 rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q0, const double* __restrict__ dq0,
                   const double* __restrict__ tau, double dt, int horizon, double* __restrict__ q_traj,
                   double* __restrict__ dq_traj, double* __restrict__ q_fin, double* __restrict__ dq_fin,
-                  size_t B, size_t ld, int* __restrict__ status) {
+                  size_t B, size_t ld, int* __restrict__ status, const double* __restrict__ cost_w, double* __restrict__ cost) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_RO_BLOCK + threadIdx.x;
     if (s >= B) return;
@@ -324,6 +326,7 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __r
     rb_load<N>(q0, ld, s, q);
     rb_load<N>(dq0, ld, s, dq);
     bool ok = true;
+    double J = 0.0;                                    // running quadratic cost (sampling-based MPC), see RbQuadCost
     const size_t step = (size_t)N * ld;
     double u[N];
     rb_load<N>(tau, ld, s, u);
@@ -340,10 +343,30 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __r
         }
         if (q_traj) rb_store<N>(q_traj + (size_t)t * step, ld, s, q);
         if (dq_traj) rb_store<N>(dq_traj + (size_t)t * step, ld, s, dq);
+        if (cost) {                                    // stage cost of the state reached and the torque applied
+            double c = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
+                c = fma(__ldg(cost_w + RB_CW_Q * RB_MAX_N + i) * e, e, c);
+                c = fma(__ldg(cost_w + RB_CW_DQ * RB_MAX_N + i) * dq[i], dq[i], c);
+                c = fma(__ldg(cost_w + RB_CW_TAU * RB_MAX_N + i) * u[i], u[i], c);
+            }
+            J = fma(dt, c, J);
+        }
         if (t + 1 < horizon) {
 #pragma unroll
             for (int i = 0; i < N; ++i) u[i] = un[i];
         }
+    }
+    if (cost) {                                        // terminal cost
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
+            J = fma(__ldg(cost_w + RB_CW_QF * RB_MAX_N + i) * e, e, J);
+            J = fma(__ldg(cost_w + RB_CW_DQF * RB_MAX_N + i) * dq[i], dq[i], J);
+        }
+        __stcs(cost + s, ok ? J : __longlong_as_double(0x7ff8000000000000LL));
     }
     if (q_fin) rb_store<N>(q_fin, ld, s, q);
     if (dq_fin) rb_store<N>(dq_fin, ld, s, dq);
@@ -444,10 +467,10 @@ struct RbLaunch {
     }
     static cudaError_t rollout(const void* param, const double* q0, const double* dq0, const double* tau, double dt,
                                int horizon, double* q_traj, double* dq_traj, double* q_fin, double* dq_fin,
-                               size_t B, size_t ld, int* status, cudaStream_t st) {
+                               size_t B, size_t ld, int* status, const double* cost_w, double* cost, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
         rb_rollout_kernel<M><<<(unsigned)((B + RB_RO_BLOCK - 1) / RB_RO_BLOCK), RB_RO_BLOCK, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
-                                                          q_fin, dq_fin, B, ld, status);
+                                                          q_fin, dq_fin, B, ld, status, cost_w, cost);
         return cudaGetLastError();
     }
     static RbOps ops(const char* name) {

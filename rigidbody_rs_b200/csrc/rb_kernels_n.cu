@@ -242,7 +242,8 @@ rbn_fk_jac_kernel(RbNParam P, const double* __restrict__ q, double* __restrict__
 __global__ void __launch_bounds__(RB_BLOCK)
 rbn_rollout_kernel(RbNParam P, const double* __restrict__ q0, const double* __restrict__ dq0, const double* __restrict__ tau,
                    double dt, int horizon, double* __restrict__ q_traj, double* __restrict__ dq_traj,
-                   double* __restrict__ q_fin, double* __restrict__ dq_fin, size_t B, size_t ld, int* __restrict__ status) {
+                   double* __restrict__ q_fin, double* __restrict__ dq_fin, size_t B, size_t ld, int* __restrict__ status,
+                   const double* __restrict__ cost_w, double* __restrict__ cost) {
     const size_t tid = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
     const size_t nthr = (size_t)gridDim.x * RB_BLOCK;
     const int n = P.n;
@@ -258,6 +259,8 @@ rbn_rollout_kernel(RbNParam P, const double* __restrict__ q0, const double* __re
     bool all_ok = true;
     for (size_t s = tid; s < B; s += nthr) {
         for (int i = 0; i < n; ++i) { qs[i] = q0[(size_t)i * ld + s]; dqs[i] = dq0[(size_t)i * ld + s]; }
+        double J = 0.0;
+        bool ok_s = true;
         for (int t = 0; t < horizon; ++t) {
             for (int i = 0; i < n; ++i) {
                 double sn, cs;
@@ -267,14 +270,32 @@ rbn_rollout_kernel(RbNParam P, const double* __restrict__ q0, const double* __re
             rbn_rnea(jt, g, n, sc, dqs.base, nullptr, dqs.stride, x);
             for (int i = 0; i < n; ++i) x[i] = __ldcs(tau + (size_t)t * step + (size_t)i * ld + s) - x[i];
             rbn_crba(jt, n, sc, [&](int r, int c, double v) { Hs[r * n + c] = v; });
-            all_ok = rbn_ldlt_solve(n, Hs, x, dinv) && all_ok;
+            ok_s = rbn_ldlt_solve(n, Hs, x, dinv) && ok_s;
+            double c = 0.0;
             for (int i = 0; i < n; ++i) {
                 const double dqn = fma(dt, x[i], dqs[i]);
                 const double qn = fma(dt, dqn, qs[i]);
                 dqs[i] = dqn; qs[i] = qn;
                 if (q_traj) __stcs(q_traj + (size_t)t * step + (size_t)i * ld + s, qn);
                 if (dq_traj) __stcs(dq_traj + (size_t)t * step + (size_t)i * ld + s, dqn);
+                if (cost) {
+                    const double e = qn - cost_w[RB_CW_QREF * RB_MAX_N + i];
+                    const double u = __ldcs(tau + (size_t)t * step + (size_t)i * ld + s);
+                    c = fma(cost_w[RB_CW_Q * RB_MAX_N + i] * e, e, c);
+                    c = fma(cost_w[RB_CW_DQ * RB_MAX_N + i] * dqn, dqn, c);
+                    c = fma(cost_w[RB_CW_TAU * RB_MAX_N + i] * u, u, c);
+                }
             }
+            J = fma(dt, c, J);
+        }
+        all_ok = all_ok && ok_s;
+        if (cost) {
+            for (int i = 0; i < n; ++i) {
+                const double e = qs[i] - cost_w[RB_CW_QREF * RB_MAX_N + i];
+                J = fma(cost_w[RB_CW_QF * RB_MAX_N + i] * e, e, J);
+                J = fma(cost_w[RB_CW_DQF * RB_MAX_N + i] * dqs[i], dqs[i], J);
+            }
+            __stcs(cost + s, ok_s ? J : __longlong_as_double(0x7ff8000000000000LL));
         }
         for (int i = 0; i < n; ++i) {
             if (q_fin) q_fin[(size_t)i * ld + s] = qs[i];
@@ -458,10 +479,11 @@ cudaError_t n_jac(const void* param, const double* q, double* J, size_t B, size_
     return cudaGetLastError();
 }
 cudaError_t n_rollout(const void* param, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
-                      double* q_traj, double* dq_traj, double* q_fin, double* dq_fin, size_t B, size_t ld, int* status, cudaStream_t st) {
+                      double* q_traj, double* dq_traj, double* q_fin, double* dq_fin, size_t B, size_t ld, int* status,
+                      const double* cost_w, double* cost, cudaStream_t st) {
     const RbNParam* P = (const RbNParam*)param;
     if (B == 0) return cudaSuccess;
-    rbn_rollout_kernel<<<ngrid(P, B), RB_BLOCK, 0, st>>>(*P, q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_fin, dq_fin, B, ld, status);
+    rbn_rollout_kernel<<<ngrid(P, B), RB_BLOCK, 0, st>>>(*P, q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_fin, dq_fin, B, ld, status, cost_w, cost);
     return cudaGetLastError();
 }
 }  // namespace

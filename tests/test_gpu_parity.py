@@ -222,6 +222,35 @@ def test_rollout_matches_oracle(rb, oracle_fr3):
         np.testing.assert_array_equal(qa.transpose(0, 2, 1), qt)
 
 
+def test_rollout_cost_matches_trajectory_cost(rb, oracle_fr3):
+    """The fused rollout+cost kernel returns exactly the quadratic cost of the trajectory the oracle integrates."""
+    import torch
+    B, H, dt = 96, 32, 2e-3
+    q, dq, _, _ = _states(oracle_fr3, B, seed=0x5EED0003)
+    lim = oracle_fr3.model
+    tau = np.stack([oracle_fr3.fill(0x5EED0003, 4 + t % 32, -lim.effort, lim.effort, t * B, B) for t in range(H)])
+    oq, odq = oracle_fr3.rollout_batch(q, dq, tau, dt)
+    rng = np.random.default_rng(3)
+    q_ref = rng.uniform(-1, 1, 7); w_q, w_dq, w_tau = rng.uniform(0, 2, 7), rng.uniform(0, 1, 7), rng.uniform(0, 1e-3, 7)
+    w_qf, w_dqf = rng.uniform(0, 50, 7), rng.uniform(0, 5, 7)
+    run = ((w_q[None, :, None] * (oq - q_ref[None, :, None]) ** 2).sum(1) + (w_dq[None, :, None] * odq ** 2).sum(1)
+           + (w_tau[None, :, None] * tau ** 2).sum(1)).sum(0) * dt
+    want = run + (w_qf[:, None] * (oq[-1] - q_ref[:, None]) ** 2).sum(0) + (w_dqf[:, None] * odq[-1] ** 2).sum(0)
+    kw = dict(q_ref=q_ref, w_q=w_q, w_dq=w_dq, w_tau=w_tau, w_q_final=w_qf, w_dq_final=w_dqf)
+    for mb in _variants(rb, FR3):
+        c_host, qf, dqf = mb.rollout_cost(q, dq, tau, dt, final=True, **kw)
+        np.testing.assert_allclose(c_host, want, rtol=1e-10, err_msg=mb.kernel_variant)
+        assert state_err(qf, oq[-1], 0).max() < TOL
+        dev = torch.device("cuda:0")
+        c_dev = mb.rollout_cost(torch.from_numpy(q).to(dev), torch.from_numpy(dq).to(dev), torch.from_numpy(tau).to(dev), dt, **kw)
+        np.testing.assert_array_equal(c_dev.cpu().numpy(), c_host)
+        c_aos = mb.rollout_cost(np.ascontiguousarray(q.T), np.ascontiguousarray(dq.T), np.ascontiguousarray(tau.transpose(0, 2, 1)),
+                                dt, layout="aos", **kw)
+        np.testing.assert_array_equal(c_aos, c_host)
+    with pytest.raises(rb.RigidBodyError):
+        mb.rollout_cost(q, dq, tau, dt, w_q=-np.ones(7))
+
+
 def test_chain32_medium_batch(rb, mb_chain32, oracle_chain32):
     B = 4096
     o = oracle_chain32
