@@ -161,6 +161,17 @@ int multibody_rnea_batch(RbGpu* g, const double* q, const double* dq, const doub
 int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const double* dq, const double* tau, double* qdd,
                                      size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
 
+/* Optional fp32 mode of the two calls above (BASELINE.json: "an optional fp32 mode is held to a stated 1e-4
+ * tolerance"): the same kernels with float arithmetic and float arrays, for DEVICE-resident SoA batches only
+ * (ld as above; asynchronous on `stream`).  Tolerance against the fp64 reference on the same float inputs, per state
+ * max_i |x_i - ref_i| <= 1e-4 * max(1, ||ref||_inf) (measured over FR3 states within joint limits: inverse
+ * dynamics 3.3e-6, forward dynamics 1.2e-5; cond(H) <= ~1e3).
+ * Families without fp32 kernels (run-time-n, 32-joint) return RB_ERR_UNSUPPORTED. */
+int multibody_rnea_batch_f32(RbGpu* g, const float* q, const float* dq, const float* ddq, float* tau,
+                             size_t n_states, size_t ld, void* stream);
+int multibody_forward_dynamics_batch_f32(RbGpu* g, const float* q, const float* dq, const float* tau, float* qdd,
+                                         size_t n_states, size_t ld, void* stream);
+
 /* H = crba(q): multibody_crba (lib.rs:32-43).  Output convention of the reference: n*n entries per state,
  * entry k = r + n*c (column-major), diagonal + strict upper triangle filled, strict lower = 0.
  * SOA: H[k*ld + s];  AOS: H[s*n*n + k]. */

@@ -37,7 +37,8 @@ class _Arg:
         if self.torch:
             import torch
             if x.dtype != torch.float64:
-                raise TypeError(f"{name}: torch tensors must be float64 (Real = f64, rigidbody/src/lib.rs:15)")
+                raise TypeError(f"{name}: torch tensors must be float64 (Real = f64, rigidbody/src/lib.rs:15); "
+                                f"float32 is accepted by rnea / forward_dynamics only (fp32 mode)")
             if not x.is_contiguous():
                 raise ValueError(f"{name}: tensor must be contiguous")
             self.device = x.device
@@ -208,15 +209,41 @@ class Multibody:
                  self._stream(cuda, args[0])))
         return o.arr
 
+    def _call_f32(self, fn, a, b, c, out):
+        """fp32 mode: CUDA float32 tensors shaped [n, B] only (include/rigidbody.h multibody_*_batch_f32)."""
+        import torch
+        n = self.n
+        ts = (a, b, c)
+        if not all(_is_torch(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(a.shape) for t in ts) \
+                or a.dim() != 2 or a.shape[0] != n:
+            raise ValueError("fp32 mode takes contiguous CUDA float32 tensors shaped [n, B] (layout 'soa')")
+        if out is None:
+            out = torch.empty_like(a)
+        B = a.shape[1]
+        check(fn(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(out.data_ptr()),
+                 B, B, C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)))
+        return out
+
+    @staticmethod
+    def _is_f32(x):
+        if not _is_torch(x):
+            return False
+        import torch
+        return x.dtype == torch.float32
+
     # ---- the reference's operations, batched
     def rnea(self, q, dq, ddq, layout="soa", out=None):
         """tau = ID(q, dq, ddq)  (multibody.rs:111-153 after get_transforms :83-85; FFI lib.rs:15-30)."""
         n = self.n
+        if self._is_f32(q):
+            return self._call_f32(lib.multibody_rnea_batch_f32, q, dq, ddq, out)
         return self._call(lib.multibody_rnea_batch, (q, dq, ddq), ("q", "dq", "ddq"), (n, n, n), n, layout, out)
 
     def forward_dynamics(self, q, dq, tau, layout="soa", out=None):
         """qdd = chol_solve(sym(crba(q)), tau - rnea(q, dq, 0))  (not a reference function)."""
         n = self.n
+        if self._is_f32(q):
+            return self._call_f32(lib.multibody_forward_dynamics_batch_f32, q, dq, tau, out)
         return self._call(lib.multibody_forward_dynamics_batch, (q, dq, tau), ("q", "dq", "tau"), (n, n, n), n, layout, out)
 
     def crba(self, q, layout="soa", out=None):

@@ -564,6 +564,42 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }
 
+// ---- optional fp32 mode: device-resident SoA batches only ----
+namespace {
+int f32_common(RbGpu* g, const void* a, const void* b, const void* c, const void* out, size_t n_states, size_t& ld) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    if (n_states == 0) return RB_OK;
+    if (!a || !b || !c || !out) return fail(RB_ERR_NULL, "pointer is NULL");
+    if (ld == 0) ld = n_states;
+    if (ld < n_states) return fail(RB_ERR_ARG, "ld < n_states");
+    return RB_OK;
+}
+}  // namespace
+
+extern "C" int multibody_rnea_batch_f32(RbGpu* g, const float* q, const float* dq, const float* ddq, float* tau,
+                                        size_t n_states, size_t ld, void* stream) {
+    int rc = f32_common(g, q, dq, ddq, tau, n_states, ld);
+    if (rc != RB_OK || n_states == 0) return rc;
+    if (!g->ops->rnea_f32) return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no fp32 kernels");
+    DeviceGuard dg(g->device);
+    cudaError_t e = g->ops->rnea_f32(g->param.data(), q, dq, ddq, tau, n_states, ld, (cudaStream_t)stream);
+    g->launches += 1;
+    if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+    return RB_OK;
+}
+
+extern "C" int multibody_forward_dynamics_batch_f32(RbGpu* g, const float* q, const float* dq, const float* tau, float* qdd,
+                                                    size_t n_states, size_t ld, void* stream) {
+    int rc = f32_common(g, q, dq, tau, qdd, n_states, ld);
+    if (rc != RB_OK || n_states == 0) return rc;
+    if (!g->ops->fd_f32) return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no fp32 kernels");
+    DeviceGuard dg(g->device);
+    cudaError_t e = g->ops->fd_f32(g->param.data(), q, dq, tau, qdd, n_states, ld, g->d_status, (cudaStream_t)stream);
+    g->launches += 1;
+    if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+    return RB_OK;
+}
+
 extern "C" int multibody_crba_batch(RbGpu* g, const double* q, double* H, size_t n_states, size_t ld, RbLayout layout,
                                     RbMem mem, void* stream) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");

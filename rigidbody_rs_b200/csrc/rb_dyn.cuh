@@ -10,6 +10,8 @@
 #include "rb_model.h"
 
 #define RB_DI __device__ __forceinline__
+// Scalar type of the model policy in scope (every function below is templated on a policy M or on a scalar T).
+#define RB_R typename M::Real
 
 template <int V> struct RbIC { static constexpr int value = V; };
 
@@ -22,73 +24,77 @@ template <int I, class F> RB_DI void rb_for_down(F&& f) {
 }
 
 // ------------------------------------------------------------------ class-tagged scalar ops
-template <int C> RB_DI double k_mul(double k, double x) {
-    if constexpr (C == RB_ZERO) return 0.0;
+template <int C, class T> RB_DI T k_mul(T k, T x) {
+    if constexpr (C == RB_ZERO) return T(0);
     else if constexpr (C == RB_ONE) return x;
     else if constexpr (C == RB_NEG1) return -x;
     else return k * x;
 }
-template <int C> RB_DI double k_fma(double k, double x, double acc) {        // acc + k*x
+template <int C, class T> RB_DI T k_fma(T k, T x, T acc) {        // acc + k*x
     if constexpr (C == RB_ZERO) return acc;
     else if constexpr (C == RB_ONE) return acc + x;
     else if constexpr (C == RB_NEG1) return acc - x;
     else return fma(k, x, acc);
 }
-template <int C> RB_DI double k_fnma(double k, double x, double acc) {       // acc - k*x
+template <int C, class T> RB_DI T k_fnma(T k, T x, T acc) {       // acc - k*x
     if constexpr (C == RB_ZERO) return acc;
     else if constexpr (C == RB_ONE) return acc - x;
     else if constexpr (C == RB_NEG1) return acc + x;
     else return fma(-k, x, acc);
 }
-template <int C0, int C1, int C2>
-RB_DI double k_dot3(double k0, double k1, double k2, double x0, double x1, double x2) {
+template <int C0, int C1, int C2, class T>
+RB_DI T k_dot3(T k0, T k1, T k2, T x0, T x1, T x2) {
     if constexpr (C0 != RB_ZERO) return k_fma<C2>(k2, x2, k_fma<C1>(k1, x1, k_mul<C0>(k0, x0)));
     else if constexpr (C1 != RB_ZERO) return k_fma<C2>(k2, x2, k_mul<C1>(k1, x1));
     else return k_mul<C2>(k2, x2);
 }
-template <int C0, int C1, int C2>
-RB_DI double k_dot3_acc(double acc, double k0, double k1, double k2, double x0, double x1, double x2) {
+template <int C0, int C1, int C2, class T>
+RB_DI T k_dot3_acc(T acc, T k0, T k1, T k2, T x0, T x1, T x2) {
     return k_fma<C2>(k2, x2, k_fma<C1>(k1, x1, k_fma<C0>(k0, x0, acc)));
 }
 
 // ------------------------------------------------------------------ model policies
 // Run-time model: values from the kernel parameter (constant bank), nothing known at compile time.
-template <int N_>
+// Real is the scalar the kernels compute in (the parameter block always holds doubles).
+template <int N_, class Real_ = double>
 struct RtModel {
     static constexpr int N = N_;
     static constexpr bool kSpecialised = false;
+    using Real = Real_;
     using Param = RbModelK<N_>;
     template <int I, int F, int K> static constexpr int cls() { return RB_GEN; }
-    template <int I, int F, int K> static RB_DI double val(const Param& p) {
-        if constexpr (F == RB_F_R) return p.jt[I].R[K];
-        else if constexpr (F == RB_F_T) return p.jt[I].t[K];
-        else if constexpr (F == RB_F_M) return K == 0 ? p.jt[I].m : p.jt[I].mc;
-        else if constexpr (F == RB_F_H) return p.jt[I].h[K];
-        else return p.jt[I].I[K];
+    template <int I, int F, int K> static RB_DI Real val(const Param& p) {
+        if constexpr (F == RB_F_R) return (Real)p.jt[I].R[K];
+        else if constexpr (F == RB_F_T) return (Real)p.jt[I].t[K];
+        else if constexpr (F == RB_F_M) return (Real)(K == 0 ? p.jt[I].m : p.jt[I].mc);
+        else if constexpr (F == RB_F_H) return (Real)p.jt[I].h[K];
+        else return (Real)p.jt[I].I[K];
     }
     template <int K> static constexpr int gcls() { return RB_GEN; }
-    template <int K> static RB_DI double g(const Param& p) { return p.g[K]; }
+    template <int K> static RB_DI Real g(const Param& p) { return (Real)p.g[K]; }
 };
 
 // Compile-time model: Tab supplies `static constexpr int N; static constexpr double T[N][24]; G[3]`
-// with each row laid out exactly like RbJointK (R9 t3 m mc h3 I6 + pad).
+// with each row laid out exactly like RbJointK (R9 t3 m mc h3 I6 + pad).  Real as above: the table is double,
+// the constants are rounded to Real at compile time.
 struct RbEmptyParam { int unused; };
 constexpr int rb_classify(double v) { return v == 0.0 ? RB_ZERO : (v == 1.0 ? RB_ONE : (v == -1.0 ? RB_NEG1 : RB_GEN)); }
-template <class Tab>
+template <class Tab, class Real_ = double>
 struct CtModel {
     static constexpr int N = Tab::N;
     static constexpr bool kSpecialised = true;
+    using Real = Real_;
     using Param = RbEmptyParam;
     template <int F, int K> static constexpr int off() {
         return F == RB_F_R ? K : F == RB_F_T ? 9 + K : F == RB_F_M ? 12 + K : F == RB_F_H ? 14 + K : 17 + K;
     }
     template <int I, int F, int K> static constexpr int cls() { return rb_classify(Tab::T[I][off<F, K>()]); }
-    template <int I, int F, int K> static RB_DI double val(const Param&) {
-        constexpr double v = Tab::T[I][off<F, K>()];
+    template <int I, int F, int K> static RB_DI Real val(const Param&) {
+        constexpr Real v = (Real)Tab::T[I][off<F, K>()];
         return v;
     }
     template <int K> static constexpr int gcls() { return rb_classify(Tab::G[K]); }
-    template <int K> static RB_DI double g(const Param&) { constexpr double v = Tab::G[K]; return v; }
+    template <int K> static RB_DI Real g(const Param&) { constexpr Real v = (Real)Tab::G[K]; return v; }
 };
 
 #define KV(I, F, K) M::template val<I, F, K>(p)
@@ -98,18 +104,18 @@ struct CtModel {
 // Motion vector parent -> child across joint I (spatial.rs:110-116 applied with X_I = parent o Rz(q)):
 //   rot' = E rot, lin' = E (lin - t x rot), E = Rz(q)^T R_p^T.
 template <class M, int I>
-RB_DI void rb_motion(const typename M::Param& p, double s, double c, double (&lin)[3], double (&rot)[3]) {
-    const double t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
-    const double d0 = k_fma<KC(I, RB_F_T, 2)>(t2, rot[1], k_fnma<KC(I, RB_F_T, 1)>(t1, rot[2], lin[0]));
-    const double d1 = k_fma<KC(I, RB_F_T, 0)>(t0, rot[2], k_fnma<KC(I, RB_F_T, 2)>(t2, rot[0], lin[1]));
-    const double d2 = k_fma<KC(I, RB_F_T, 1)>(t1, rot[0], k_fnma<KC(I, RB_F_T, 0)>(t0, rot[1], lin[2]));
+RB_DI void rb_motion(const typename M::Param& p, RB_R s, RB_R c, RB_R (&lin)[3], RB_R (&rot)[3]) {
+    const RB_R t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
+    const RB_R d0 = k_fma<KC(I, RB_F_T, 2)>(t2, rot[1], k_fnma<KC(I, RB_F_T, 1)>(t1, rot[2], lin[0]));
+    const RB_R d1 = k_fma<KC(I, RB_F_T, 0)>(t0, rot[2], k_fnma<KC(I, RB_F_T, 2)>(t2, rot[0], lin[1]));
+    const RB_R d2 = k_fma<KC(I, RB_F_T, 1)>(t1, rot[0], k_fnma<KC(I, RB_F_T, 0)>(t0, rot[1], lin[2]));
     // y = R_p^T x : y_j = sum_k R[k][j] x_k
-    const double y0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), d0, d1, d2);
-    const double y1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), d0, d1, d2);
-    const double y2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), d0, d1, d2);
-    const double w0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), rot[0], rot[1], rot[2]);
-    const double w1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), rot[0], rot[1], rot[2]);
-    const double w2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), rot[0], rot[1], rot[2]);
+    const RB_R y0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), d0, d1, d2);
+    const RB_R y1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), d0, d1, d2);
+    const RB_R y2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), d0, d1, d2);
+    const RB_R w0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), rot[0], rot[1], rot[2]);
+    const RB_R w1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), rot[0], rot[1], rot[2]);
+    const RB_R w2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), rot[0], rot[1], rot[2]);
     // Rz(q)^T
     lin[0] = fma(c, y0, s * y1);  lin[1] = fma(c, y1, -(s * y0));  lin[2] = y2;
     rot[0] = fma(c, w0, s * w1);  rot[1] = fma(c, w1, -(s * w0));  rot[2] = w2;
@@ -118,17 +124,17 @@ RB_DI void rb_motion(const typename M::Param& p, double s, double c, double (&li
 // Force child -> parent across joint I (spatial.rs:242-248 applied to X_I^-1, as multibody.rs:147,165 do):
 //   lin' = R lin, rot' = R rot + t x (R lin), R = R_p Rz(q).   Result written to (ol, orr).
 template <class M, int I>
-RB_DI void rb_force(const typename M::Param& p, double s, double c, const double (&lin)[3], const double (&rot)[3],
-                    double (&ol)[3], double (&orr)[3]) {
-    const double y0 = fma(c, lin[0], -(s * lin[1])), y1 = fma(s, lin[0], c * lin[1]), y2 = lin[2];
-    const double w0 = fma(c, rot[0], -(s * rot[1])), w1 = fma(s, rot[0], c * rot[1]), w2 = rot[2];
-    const double L0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), y0, y1, y2);
-    const double L1 = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), y0, y1, y2);
-    const double L2 = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), y0, y1, y2);
-    const double t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
-    double r0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), w0, w1, w2);
-    double r1 = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), w0, w1, w2);
-    double r2 = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), w0, w1, w2);
+RB_DI void rb_force(const typename M::Param& p, RB_R s, RB_R c, const RB_R (&lin)[3], const RB_R (&rot)[3],
+                    RB_R (&ol)[3], RB_R (&orr)[3]) {
+    const RB_R y0 = fma(c, lin[0], -(s * lin[1])), y1 = fma(s, lin[0], c * lin[1]), y2 = lin[2];
+    const RB_R w0 = fma(c, rot[0], -(s * rot[1])), w1 = fma(s, rot[0], c * rot[1]), w2 = rot[2];
+    const RB_R L0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), y0, y1, y2);
+    const RB_R L1 = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), y0, y1, y2);
+    const RB_R L2 = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), y0, y1, y2);
+    const RB_R t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
+    RB_R r0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), w0, w1, w2);
+    RB_R r1 = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), w0, w1, w2);
+    RB_R r2 = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), w0, w1, w2);
     r0 = k_fnma<KC(I, RB_F_T, 2)>(t2, L1, k_fma<KC(I, RB_F_T, 1)>(t1, L2, r0));
     r1 = k_fnma<KC(I, RB_F_T, 0)>(t0, L2, k_fma<KC(I, RB_F_T, 2)>(t2, L0, r1));
     r2 = k_fnma<KC(I, RB_F_T, 1)>(t1, L0, k_fma<KC(I, RB_F_T, 0)>(t0, L1, r2));
@@ -138,25 +144,27 @@ RB_DI void rb_force(const typename M::Param& p, double s, double c, const double
 
 // f = I_I * a  (inertia.rs:107-117):  lin = m a.lin - h x a.rot ; rot = I_o a.rot + h x a.lin
 template <class M, int I>
-RB_DI void rb_inertia_mul(const typename M::Param& p, const double (&al)[3], const double (&ar)[3],
-                          double (&fl)[3], double (&fr)[3]) {
-    const double m = KV(I, RB_F_M, 0);
-    const double h0 = KV(I, RB_F_H, 0), h1 = KV(I, RB_F_H, 1), h2 = KV(I, RB_F_H, 2);
+RB_DI void rb_inertia_mul(const typename M::Param& p, const RB_R (&al)[3], const RB_R (&ar)[3],
+                          RB_R (&fl)[3], RB_R (&fr)[3]) {
+    const RB_R m = KV(I, RB_F_M, 0);
+    const RB_R h0 = KV(I, RB_F_H, 0), h1 = KV(I, RB_F_H, 1), h2 = KV(I, RB_F_H, 2);
     fl[0] = fma(h2, ar[1], fma(-h1, ar[2], m * al[0]));
     fl[1] = fma(h0, ar[2], fma(-h2, ar[0], m * al[1]));
     fl[2] = fma(h1, ar[0], fma(-h0, ar[1], m * al[2]));
-    const double Ixx = KV(I, RB_F_I, 0), Ixy = KV(I, RB_F_I, 1), Ixz = KV(I, RB_F_I, 2);
-    const double Iyy = KV(I, RB_F_I, 3), Iyz = KV(I, RB_F_I, 4), Izz = KV(I, RB_F_I, 5);
+    const RB_R Ixx = KV(I, RB_F_I, 0), Ixy = KV(I, RB_F_I, 1), Ixz = KV(I, RB_F_I, 2);
+    const RB_R Iyy = KV(I, RB_F_I, 3), Iyz = KV(I, RB_F_I, 4), Izz = KV(I, RB_F_I, 5);
     fr[0] = fma(-h2, al[1], fma(h1, al[2], fma(Ixz, ar[2], fma(Ixy, ar[1], Ixx * ar[0]))));
     fr[1] = fma(-h0, al[2], fma(h2, al[0], fma(Iyz, ar[2], fma(Iyy, ar[1], Ixy * ar[0]))));
     fr[2] = fma(-h1, al[0], fma(h0, al[1], fma(Izz, ar[2], fma(Iyz, ar[1], Ixz * ar[0]))));
 }
 
 // sin/cos of every joint angle (joint.rs:48-50 builds the same rotation as a quaternion).
-template <int N>
-RB_DI void rb_sincos_all(const double (&q)[N], double (&s)[N], double (&c)[N]) {
+RB_DI void rb_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+RB_DI void rb_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+template <int N, class T>
+RB_DI void rb_sincos_all(const T (&q)[N], T (&s)[N], T (&c)[N]) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) sincos(q[i], &s[i], &c[i]);
+    for (int i = 0; i < N; ++i) rb_sincos(q[i], &s[i], &c[i]);
 }
 
 // ------------------------------------------------------------------ RNEA  (multibody.rs:111-153)
@@ -170,39 +178,39 @@ RB_DI void rb_sincos_all(const double (&q)[N], double (&s)[N], double (&c)[N]) {
 // so the linear velocity never has to be carried (about 20 fewer FP64 instructions per joint).  The outward
 // sweep (:122-141) and the inward sweep (:143-150) are otherwise unchanged; gravity is the base's a' (:116-120).
 template <class M, int I>
-RB_DI void rb_rotate_in(const typename M::Param& p, double s, double c, const double (&x)[3], double (&o)[3]) {
+RB_DI void rb_rotate_in(const typename M::Param& p, RB_R s, RB_R c, const RB_R (&x)[3], RB_R (&o)[3]) {
     // o = Rz(q)^T R_p^T x
-    const double y0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), x[0], x[1], x[2]);
-    const double y1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), x[0], x[1], x[2]);
-    const double y2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), x[0], x[1], x[2]);
+    const RB_R y0 = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), x[0], x[1], x[2]);
+    const RB_R y1 = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), x[0], x[1], x[2]);
+    const RB_R y2 = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), x[0], x[1], x[2]);
     o[0] = fma(c, y0, s * y1);  o[1] = fma(c, y1, -(s * y0));  o[2] = y2;
 }
 
 template <class M, bool HAS_DDQ>
-RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
-                   const double (&dq)[M::N], const double (&ddq)[M::N], double (&tau)[M::N]) {
+RB_DI void rb_rnea(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
+                   const RB_R (&dq)[M::N], const RB_R (&ddq)[M::N], RB_R (&tau)[M::N]) {
     constexpr int N = M::N;
-    double fl[N][3], fr[N][3];
-    double w[3], al[3], ac[3];            // omega, alpha, a' of the current link, in its own frame
+    RB_R fl[N][3], fr[N][3];
+    RB_R w[3], al[3], ac[3];            // omega, alpha, a' of the current link, in its own frame
     rb_for_up<0, N>([&](auto ic) {
         constexpr int I = decltype(ic)::value;
-        const double dqi = dq[I];
+        const RB_R dqi = dq[I];
         if constexpr (I == 0) {
             // base: w = alpha = 0, a' = g (:116-120)
             constexpr int G0 = M::template gcls<0>(), G1 = M::template gcls<1>(), G2 = M::template gcls<2>();
-            const double g0 = M::template g<0>(p), g1 = M::template g<1>(p), g2 = M::template g<2>(p);
+            const RB_R g0 = M::template g<0>(p), g1 = M::template g<1>(p), g2 = M::template g<2>(p);
             // y = R_p^T g with both factors model constants
             constexpr bool y0z = (KC(0, RB_F_R, 0) == RB_ZERO || G0 == RB_ZERO) && (KC(0, RB_F_R, 3) == RB_ZERO || G1 == RB_ZERO) && (KC(0, RB_F_R, 6) == RB_ZERO || G2 == RB_ZERO);
             constexpr bool y1z = (KC(0, RB_F_R, 1) == RB_ZERO || G0 == RB_ZERO) && (KC(0, RB_F_R, 4) == RB_ZERO || G1 == RB_ZERO) && (KC(0, RB_F_R, 7) == RB_ZERO || G2 == RB_ZERO);
-            const double y0 = k_dot3<KC(0, RB_F_R, 0), KC(0, RB_F_R, 3), KC(0, RB_F_R, 6)>(KV(0, RB_F_R, 0), KV(0, RB_F_R, 3), KV(0, RB_F_R, 6), g0, g1, g2);
-            const double y1 = k_dot3<KC(0, RB_F_R, 1), KC(0, RB_F_R, 4), KC(0, RB_F_R, 7)>(KV(0, RB_F_R, 1), KV(0, RB_F_R, 4), KV(0, RB_F_R, 7), g0, g1, g2);
-            const double y2 = k_dot3<KC(0, RB_F_R, 2), KC(0, RB_F_R, 5), KC(0, RB_F_R, 8)>(KV(0, RB_F_R, 2), KV(0, RB_F_R, 5), KV(0, RB_F_R, 8), g0, g1, g2);
+            const RB_R y0 = k_dot3<KC(0, RB_F_R, 0), KC(0, RB_F_R, 3), KC(0, RB_F_R, 6)>(KV(0, RB_F_R, 0), KV(0, RB_F_R, 3), KV(0, RB_F_R, 6), g0, g1, g2);
+            const RB_R y1 = k_dot3<KC(0, RB_F_R, 1), KC(0, RB_F_R, 4), KC(0, RB_F_R, 7)>(KV(0, RB_F_R, 1), KV(0, RB_F_R, 4), KV(0, RB_F_R, 7), g0, g1, g2);
+            const RB_R y2 = k_dot3<KC(0, RB_F_R, 2), KC(0, RB_F_R, 5), KC(0, RB_F_R, 8)>(KV(0, RB_F_R, 2), KV(0, RB_F_R, 5), KV(0, RB_F_R, 8), g0, g1, g2);
             w[0] = 0.0; w[1] = 0.0; w[2] = dqi;                                       // :130
-            al[0] = 0.0; al[1] = 0.0; al[2] = HAS_DDQ ? ddq[I] : 0.0;                  // :133
-            double nz;                                                                 // the only entry of f_0 that is ever read (:144)
+            al[0] = 0.0; al[1] = 0.0; al[2] = HAS_DDQ ? ddq[I] : RB_R(0);                 // :133
+            RB_R nz;                                                                 // the only entry of f_0 that is ever read (:144)
             if constexpr (y0z && y1z) {
                 ac[0] = 0.0; ac[1] = 0.0; ac[2] = y2;
-                nz = HAS_DDQ ? KV(0, RB_F_I, 5) * ddq[I] : 0.0;
+                nz = HAS_DDQ ? KV(0, RB_F_I, 5) * ddq[I] : RB_R(0);
             } else {
                 ac[0] = fma(c[0], y0, s[0] * y1);  ac[1] = fma(c[0], y1, -(s[0] * y0));  ac[2] = y2;
                 nz = fma(KV(0, RB_F_H, 0), ac[1], -(KV(0, RB_F_H, 1) * ac[0]));
@@ -212,16 +220,16 @@ RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const do
             fr[0][0] = 0.0; fr[0][1] = 0.0; fr[0][2] = nz;
         } else {
             // a'_i = E (a' + alpha x t + w x (w x t)) with the parent's w, alpha, a'
-            const double t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
+            const RB_R t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
             constexpr int T0 = KC(I, RB_F_T, 0), T1 = KC(I, RB_F_T, 1), T2 = KC(I, RB_F_T, 2);
-            double b[3];
+            RB_R b[3];
             if constexpr (T0 == RB_ZERO && T1 == RB_ZERO && T2 == RB_ZERO) {
                 b[0] = ac[0]; b[1] = ac[1]; b[2] = ac[2];
             } else {
                 // u = w x t
-                const double u0 = k_fnma<T1>(t1, w[2], k_mul<T2>(t2, w[1]));
-                const double u1 = k_fnma<T2>(t2, w[0], k_mul<T0>(t0, w[2]));
-                const double u2 = k_fnma<T0>(t0, w[1], k_mul<T1>(t1, w[0]));
+                const RB_R u0 = k_fnma<T1>(t1, w[2], k_mul<T2>(t2, w[1]));
+                const RB_R u1 = k_fnma<T2>(t2, w[0], k_mul<T0>(t0, w[2]));
+                const RB_R u2 = k_fnma<T0>(t0, w[1], k_mul<T1>(t1, w[0]));
                 b[0] = k_fma<T2>(t2, al[1], k_fnma<T1>(t1, al[2], ac[0]));            // + alpha x t
                 b[1] = k_fma<T0>(t0, al[2], k_fnma<T2>(t2, al[0], ac[1]));
                 b[2] = k_fma<T1>(t1, al[0], k_fnma<T0>(t0, al[1], ac[2]));
@@ -229,7 +237,7 @@ RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const do
                 b[1] = fma(w[2], u0, fma(-w[0], u2, b[1]));
                 b[2] = fma(w[0], u1, fma(-w[1], u0, b[2]));
             }
-            double wn[3], aln[3];
+            RB_R wn[3], aln[3];
             rb_rotate_in<M, I>(p, s[I], c[I], b, ac);
             rb_rotate_in<M, I>(p, s[I], c[I], w, wn);                                  // :129
             rb_rotate_in<M, I>(p, s[I], c[I], al, aln);                                // :132
@@ -239,21 +247,21 @@ RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const do
             al[2] = HAS_DDQ ? aln[2] + ddq[I] : aln[2];
             w[0] = wn[0]; w[1] = wn[1]; w[2] = wn[2] + dqi;
             // wrench of link i about its origin (:140)
-            const double m = KV(I, RB_F_M, 0);
-            const double h0 = KV(I, RB_F_H, 0), h1 = KV(I, RB_F_H, 1), h2 = KV(I, RB_F_H, 2);
-            const double Ixx = KV(I, RB_F_I, 0), Ixy = KV(I, RB_F_I, 1), Ixz = KV(I, RB_F_I, 2);
-            const double Iyy = KV(I, RB_F_I, 3), Iyz = KV(I, RB_F_I, 4), Izz = KV(I, RB_F_I, 5);
-            const double e0 = fma(w[1], h2, -(w[2] * h1));                             // e = w x h
-            const double e1 = fma(w[2], h0, -(w[0] * h2));
-            const double e2 = fma(w[0], h1, -(w[1] * h0));
+            const RB_R m = KV(I, RB_F_M, 0);
+            const RB_R h0 = KV(I, RB_F_H, 0), h1 = KV(I, RB_F_H, 1), h2 = KV(I, RB_F_H, 2);
+            const RB_R Ixx = KV(I, RB_F_I, 0), Ixy = KV(I, RB_F_I, 1), Ixz = KV(I, RB_F_I, 2);
+            const RB_R Iyy = KV(I, RB_F_I, 3), Iyz = KV(I, RB_F_I, 4), Izz = KV(I, RB_F_I, 5);
+            const RB_R e0 = fma(w[1], h2, -(w[2] * h1));                             // e = w x h
+            const RB_R e1 = fma(w[2], h0, -(w[0] * h2));
+            const RB_R e2 = fma(w[0], h1, -(w[1] * h0));
             // F = m a' + alpha x h + w x e
             fl[I][0] = fma(w[1], e2, fma(-w[2], e1, fma(al[1], h2, fma(-al[2], h1, m * ac[0]))));
             fl[I][1] = fma(w[2], e0, fma(-w[0], e2, fma(al[2], h0, fma(-al[0], h2, m * ac[1]))));
             fl[I][2] = fma(w[0], e1, fma(-w[1], e0, fma(al[0], h1, fma(-al[1], h0, m * ac[2]))));
             // L = I_o w ;  n = I_o alpha + w x L + h x a'
-            const double L0 = fma(Ixz, w[2], fma(Ixy, w[1], Ixx * w[0]));
-            const double L1 = fma(Iyz, w[2], fma(Iyy, w[1], Ixy * w[0]));
-            const double L2 = fma(Izz, w[2], fma(Iyz, w[1], Ixz * w[0]));
+            const RB_R L0 = fma(Ixz, w[2], fma(Ixy, w[1], Ixx * w[0]));
+            const RB_R L1 = fma(Iyz, w[2], fma(Iyy, w[1], Ixy * w[0]));
+            const RB_R L2 = fma(Izz, w[2], fma(Iyz, w[1], Ixz * w[0]));
             fr[I][0] = fma(h1, ac[2], fma(-h2, ac[1], fma(w[1], L2, fma(-w[2], L1, fma(Ixz, al[2], fma(Ixy, al[1], Ixx * al[0]))))));
             fr[I][1] = fma(h2, ac[0], fma(-h0, ac[2], fma(w[2], L0, fma(-w[0], L2, fma(Iyz, al[2], fma(Iyy, al[1], Ixy * al[0]))))));
             fr[I][2] = fma(h0, ac[1], fma(-h1, ac[0], fma(w[0], L1, fma(-w[1], L0, fma(Izz, al[2], fma(Iyz, al[1], Ixz * al[0]))))));
@@ -263,7 +271,7 @@ RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const do
         constexpr int I = decltype(ic)::value;
         tau[I] = fr[I][2];                                                           // :144
         if constexpr (I > 0) {
-            double tl[3], tr[3];
+            RB_R tl[3], tr[3];
             rb_force<M, I>(p, s[I], c[I], fl[I], fr[I], tl, tr);                     // :147
             fl[I - 1][0] += tl[0]; fl[I - 1][1] += tl[1]; fl[I - 1][2] += tl[2];     // :148
             fr[I - 1][0] += tr[0]; fr[I - 1][1] += tr[1]; fr[I - 1][2] += tr[2];
@@ -279,69 +287,69 @@ RB_DI void rb_rnea(const typename M::Param& p, const double (&s)[M::N], const do
 //   h' = R h + m t,   I_o' = R I_o R^T - (t u^T + u t^T) + 2 (t.u) Id,   then add link i-1's own (h, I_o).
 // `put(RbIC<J>, RbIC<I>, value)` receives every entry H(J, I), J <= I, once.
 template <class M, class Put>
-RB_DI void rb_crba_put(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N], Put&& put) {
+RB_DI void rb_crba_put(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], Put&& put) {
     constexpr int N = M::N;
-    double h[3] = {KV(N - 1, RB_F_H, 0), KV(N - 1, RB_F_H, 1), KV(N - 1, RB_F_H, 2)};            // :157
-    double Ixx = KV(N - 1, RB_F_I, 0), Ixy = KV(N - 1, RB_F_I, 1), Ixz = KV(N - 1, RB_F_I, 2);
-    double Iyy = KV(N - 1, RB_F_I, 3), Iyz = KV(N - 1, RB_F_I, 4), Izz = KV(N - 1, RB_F_I, 5);
+    RB_R h[3] = {KV(N - 1, RB_F_H, 0), KV(N - 1, RB_F_H, 1), KV(N - 1, RB_F_H, 2)};            // :157
+    RB_R Ixx = KV(N - 1, RB_F_I, 0), Ixy = KV(N - 1, RB_F_I, 1), Ixz = KV(N - 1, RB_F_I, 2);
+    RB_R Iyy = KV(N - 1, RB_F_I, 3), Iyz = KV(N - 1, RB_F_I, 4), Izz = KV(N - 1, RB_F_I, 5);
     rb_for_down<N - 1>([&](auto ic) {
         constexpr int I = decltype(ic)::value;
         put(RbIC<I>{}, RbIC<I>{}, Izz);                                              // :161
-        double Fl[3] = {-h[1], h[0], 0.0};                                           // :162  F = I^c * S_z
-        double Fr[3] = {Ixz, Iyz, Izz};
+        RB_R Fl[3] = {-h[1], h[0], 0.0};                                           // :162  F = I^c * S_z
+        RB_R Fr[3] = {Ixz, Iyz, Izz};
         rb_for_down<I - 1>([&](auto jc) {
             constexpr int J = decltype(jc)::value;
-            double ol[3], orr[3];
+            RB_R ol[3], orr[3];
             rb_force<M, J + 1>(p, s[J + 1], c[J + 1], Fl, Fr, ol, orr);              // :165
             Fl[0] = ol[0]; Fl[1] = ol[1]; Fl[2] = ol[2];
             Fr[0] = orr[0]; Fr[1] = orr[1]; Fr[2] = orr[2];
             put(RbIC<J>{}, RbIC<I>{}, Fr[2]);                                        // :166
         });
         if constexpr (I > 0) {                                                       // :169-171
-            const double si = s[I], ci = c[I];
+            const RB_R si = s[I], ci = c[I];
             // Rz(q): h, I_o
-            const double g0 = fma(ci, h[0], -(si * h[1])), g1 = fma(si, h[0], ci * h[1]), g2 = h[2];
-            const double cs = ci * si, s2 = cs + cs, c2 = fma(ci, ci, -(si * si));
-            const double hm = 0.5 * (Ixx - Iyy), hp = 0.5 * (Ixx + Iyy);
-            const double u_ = fma(hm, c2, -(Ixy * s2));
-            const double a = hp + u_, e = hp - u_, b = fma(hm, s2, Ixy * c2);
-            const double d = fma(ci, Ixz, -(si * Iyz)), f = fma(si, Ixz, ci * Iyz), g = Izz;
+            const RB_R g0 = fma(ci, h[0], -(si * h[1])), g1 = fma(si, h[0], ci * h[1]), g2 = h[2];
+            const RB_R cs = ci * si, s2 = cs + cs, c2 = fma(ci, ci, -(si * si));
+            const RB_R hm = RB_R(0.5) * (Ixx - Iyy), hp = RB_R(0.5) * (Ixx + Iyy);
+            const RB_R u_ = fma(hm, c2, -(Ixy * s2));
+            const RB_R a = hp + u_, e = hp - u_, b = fma(hm, s2, Ixy * c2);
+            const RB_R d = fma(ci, Ixz, -(si * Iyz)), f = fma(si, Ixz, ci * Iyz), g = Izz;
             // R_p: h'' = R_p g ; I'' = R_p A R_p^T with A = [[a,b,d],[b,e,f],[d,f,g]]
 #define RR(r, k) KV(I, RB_F_R, 3 * (r) + (k))
 #define RC(r, k) KC(I, RB_F_R, 3 * (r) + (k))
-            const double q0 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), g0, g1, g2);
-            const double q1 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), g0, g1, g2);
-            const double q2 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), g0, g1, g2);
+            const RB_R q0 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), g0, g1, g2);
+            const RB_R q1 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), g0, g1, g2);
+            const RB_R q2 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), g0, g1, g2);
             // P = R_p A (rows of R_p against columns of symmetric A)
-            const double P00 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), a, b, d);
-            const double P01 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), b, e, f);
-            const double P02 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), d, f, g);
-            const double P10 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), a, b, d);
-            const double P11 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), b, e, f);
-            const double P12 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), d, f, g);
-            const double P20 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), a, b, d);
-            const double P21 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), b, e, f);
-            const double P22 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), d, f, g);
+            const RB_R P00 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), a, b, d);
+            const RB_R P01 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), b, e, f);
+            const RB_R P02 = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), d, f, g);
+            const RB_R P10 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), a, b, d);
+            const RB_R P11 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), b, e, f);
+            const RB_R P12 = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), d, f, g);
+            const RB_R P20 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), a, b, d);
+            const RB_R P21 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), b, e, f);
+            const RB_R P22 = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), d, f, g);
             // I'' = P R_p^T, six unique entries: I''[r][c] = sum_k P[r][k] R_p[c][k]
-            double Jxx = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), P00, P01, P02);
-            double Jxy = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), P00, P01, P02);
-            double Jxz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P00, P01, P02);
-            double Jyy = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), P10, P11, P12);
-            double Jyz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P10, P11, P12);
-            double Jzz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P20, P21, P22);
+            RB_R Jxx = k_dot3<RC(0, 0), RC(0, 1), RC(0, 2)>(RR(0, 0), RR(0, 1), RR(0, 2), P00, P01, P02);
+            RB_R Jxy = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), P00, P01, P02);
+            RB_R Jxz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P00, P01, P02);
+            RB_R Jyy = k_dot3<RC(1, 0), RC(1, 1), RC(1, 2)>(RR(1, 0), RR(1, 1), RR(1, 2), P10, P11, P12);
+            RB_R Jyz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P10, P11, P12);
+            RB_R Jzz = k_dot3<RC(2, 0), RC(2, 1), RC(2, 2)>(RR(2, 0), RR(2, 1), RR(2, 2), P20, P21, P22);
 #undef RR
 #undef RC
             // translation by t with composite mass mc_I:  u = h'' + (mc/2) t
-            const double mc = KV(I, RB_F_M, 1);
-            const double t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
+            const RB_R mc = KV(I, RB_F_M, 1);
+            const RB_R t0 = KV(I, RB_F_T, 0), t1 = KV(I, RB_F_T, 1), t2 = KV(I, RB_F_T, 2);
             constexpr int T0 = KC(I, RB_F_T, 0), T1 = KC(I, RB_F_T, 1), T2 = KC(I, RB_F_T, 2);
-            const double hmc = 0.5 * mc;
-            const double u0 = k_fma<T0>(t0, hmc, q0), u1 = k_fma<T1>(t1, hmc, q1), u2 = k_fma<T2>(t2, hmc, q2);
-            const double tu0 = k_mul<T0>(t0, u0), tu1 = k_mul<T1>(t1, u1), tu2 = k_mul<T2>(t2, u2);
+            const RB_R hmc = RB_R(0.5) * mc;
+            const RB_R u0 = k_fma<T0>(t0, hmc, q0), u1 = k_fma<T1>(t1, hmc, q1), u2 = k_fma<T2>(t2, hmc, q2);
+            const RB_R tu0 = k_mul<T0>(t0, u0), tu1 = k_mul<T1>(t1, u1), tu2 = k_mul<T2>(t2, u2);
             // diag: + 2 (t.u - t_k u_k);  off-diag: - (t_r u_c + t_c u_r);  then add link I-1's own inertia
-            Ixx = fma(2.0, tu1 + tu2, Jxx) + KV(I - 1, RB_F_I, 0);
-            Iyy = fma(2.0, tu0 + tu2, Jyy) + KV(I - 1, RB_F_I, 3);
-            Izz = fma(2.0, tu0 + tu1, Jzz) + KV(I - 1, RB_F_I, 5);
+            Ixx = fma(RB_R(2), tu1 + tu2, Jxx) + KV(I - 1, RB_F_I, 0);
+            Iyy = fma(RB_R(2), tu0 + tu2, Jyy) + KV(I - 1, RB_F_I, 3);
+            Izz = fma(RB_R(2), tu0 + tu1, Jzz) + KV(I - 1, RB_F_I, 5);
             Ixy = k_fnma<T1>(t1, u0, k_fnma<T0>(t0, u1, Jxy)) + KV(I - 1, RB_F_I, 1);
             Ixz = k_fnma<T2>(t2, u0, k_fnma<T0>(t0, u2, Jxz)) + KV(I - 1, RB_F_I, 2);
             Iyz = k_fnma<T2>(t2, u1, k_fnma<T1>(t1, u2, Jyz)) + KV(I - 1, RB_F_I, 4);
@@ -353,9 +361,9 @@ RB_DI void rb_crba_put(const typename M::Param& p, const double (&s)[M::N], cons
 }
 
 template <class M>
-RB_DI void rb_crba(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
-                   double (&H)[M::N][M::N]) {
-    rb_crba_put<M>(p, s, c, [&](auto jc, auto ic, double v) { H[decltype(jc)::value][decltype(ic)::value] = v; });
+RB_DI void rb_crba(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
+                   RB_R (&H)[M::N][M::N]) {
+    rb_crba_put<M>(p, s, c, [&](auto jc, auto ic, RB_R v) { H[decltype(jc)::value][decltype(ic)::value] = v; });
 }
 
 // 1/d for a pivot d of an SPD matrix (normal, positive): hardware seed (rcp.approx.ftz.f64, ~20 good bits,
@@ -369,22 +377,23 @@ RB_DI double rb_rcp_pos(double d) {
     e = fma(-d, x, 1.0);
     return fma(x, e, x);
 }
+RB_DI float rb_rcp_pos(float d) { return __frcp_rn(d); }
 
 // ------------------------------------------------------------------ solve  H x = b, H SPD given by its upper triangle
 // In-place right-looking LDL^T (the square-root-free Cholesky), then the two triangular solves.
 // Returns false if a pivot is not positive (H not SPD).
-template <int N>
-RB_DI bool rb_ldlt_solve(double (&A)[N][N], double (&x)[N]) {
-    double dinv[N];
+template <int N, class T>
+RB_DI bool rb_ldlt_solve(T (&A)[N][N], T (&x)[N]) {
+    T dinv[N];
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        const double d = A[j][j];
-        ok = ok && (d > 0.0);
+        const T d = A[j][j];
+        ok = ok && (d > T(0));
         dinv[j] = rb_rcp_pos(d);
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
-            const double l = A[j][i] * dinv[j];
+            const T l = A[j][i] * dinv[j];
 #pragma unroll
             for (int k = i; k < N; ++k) A[i][k] = fma(-l, A[j][k], A[i][k]);
             A[j][i] = l;                     // U[j][i] = L[i][j]
@@ -408,16 +417,16 @@ RB_DI bool rb_ldlt_solve(double (&A)[N][N], double (&x)[N]) {
 // ------------------------------------------------------------------ forward dynamics
 // qdd = solve(sym(crba(q)), tau - rnea(q, dq, 0)); sin/cos computed once and shared by both halves.
 template <class M>
-RB_DI bool rb_forward_dynamics(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N],
-                               const double (&dq)[M::N], const double (&tau)[M::N], double (&qdd)[M::N]) {
+RB_DI bool rb_forward_dynamics(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
+                               const RB_R (&dq)[M::N], const RB_R (&tau)[M::N], RB_R (&qdd)[M::N]) {
     constexpr int N = M::N;
     {
-        double bias[N];
+        RB_R bias[N];
         rb_rnea<M, false>(p, s, c, dq, dq /*unused*/, bias);
 #pragma unroll
         for (int i = 0; i < N; ++i) qdd[i] = tau[i] - bias[i];
     }
-    double H[N][N];
+    RB_R H[N][N];
     rb_crba<M>(p, s, c, H);
     return rb_ldlt_solve<N>(H, qdd);
 }
@@ -425,12 +434,12 @@ RB_DI bool rb_forward_dynamics(const typename M::Param& p, const double (&s)[M::
 // ------------------------------------------------------------------ forward kinematics / Jacobian
 // Tip pose in the base frame, composed tip -> base as multibody.rs:87-93 does: p <- R_i p + t_i.
 template <class M>
-RB_DI void rb_fwd_kin(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N], double (&pos)[3]) {
+RB_DI void rb_fwd_kin(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], RB_R (&pos)[3]) {
     constexpr int N = M::N;
     pos[0] = 0.0; pos[1] = 0.0; pos[2] = 0.0;
     rb_for_down<N - 1>([&](auto ic) {
         constexpr int I = decltype(ic)::value;
-        const double y0 = fma(c[I], pos[0], -(s[I] * pos[1])), y1 = fma(s[I], pos[0], c[I] * pos[1]), y2 = pos[2];
+        const RB_R y0 = fma(c[I], pos[0], -(s[I] * pos[1])), y1 = fma(s[I], pos[0], c[I] * pos[1]), y2 = pos[2];
         pos[0] = k_dot3_acc<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_T, 0), KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), y0, y1, y2);
         pos[1] = k_dot3_acc<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_T, 1), KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), y0, y1, y2);
         pos[2] = k_dot3_acc<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_T, 2), KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), y0, y1, y2);
@@ -441,10 +450,10 @@ RB_DI void rb_fwd_kin(const typename M::Param& p, const double (&s)[M::N], const
 // motion transform of the accumulated pose (A, r) of the tip in frame i:  rot = A^T z, lin = A^T (-(r x z)).
 // J is [N][6]: J[i][0..2] lin, J[i][3..5] rot.
 template <class M>
-RB_DI void rb_jac(const typename M::Param& p, const double (&s)[M::N], const double (&c)[M::N], double (&J)[M::N][6]) {
+RB_DI void rb_jac(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], RB_R (&J)[M::N][6]) {
     constexpr int N = M::N;
-    double A[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
-    double r[3] = {0.0, 0.0, 0.0};
+    RB_R A[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
+    RB_R r[3] = {0.0, 0.0, 0.0};
     rb_for_down<N - 1>([&](auto ic) {
         constexpr int I = decltype(ic)::value;
         // -(r x z) = (-r1, r0, 0)
@@ -455,7 +464,7 @@ RB_DI void rb_jac(const typename M::Param& p, const double (&s)[M::N], const dou
         }
         if constexpr (I > 0) {
             // (A, r) <- X_I o (A, r):  A <- R_p Rz A,  r <- R_p Rz r + t
-            double B[3][3], y[3];
+            RB_R B[3][3], y[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 B[0][k] = fma(c[I], A[0][k], -(s[I] * A[1][k]));

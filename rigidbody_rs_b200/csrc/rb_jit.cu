@@ -79,7 +79,8 @@ const char* const kKernelExprs[RB_JIT_KERNELS] = {
     "rb_rnea_kernel<CtModel<TabJit>, false>", "rb_rnea_kernel<CtModel<TabJit>, true>",
     "rb_fd_kernel<CtModel<TabJit>, false>",   "rb_fd_kernel<CtModel<TabJit>, true>",
     "rb_crba_kernel<CtModel<TabJit>>",        "rb_fwd_kin_kernel<CtModel<TabJit>>",
-    "rb_jac_kernel<CtModel<TabJit>>",         "rb_rollout_kernel<CtModel<TabJit>>"};
+    "rb_jac_kernel<CtModel<TabJit>>",         "rb_rollout_kernel<CtModel<TabJit>>",
+    "rb_rnea_kernel<CtModel<TabJit, float>, false>", "rb_fd_kernel<CtModel<TabJit, float>, false>"};
 const char* const kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DRB_DEVICE_ONLY=1"};
 
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -258,10 +259,24 @@ cudaError_t j_rollout(const void* param, const double* q0, const double* dq0, co
     void* args[] = {&ep, &q0, &dq0, &tau, &dt, &horizon, &q_traj, &dq_traj, &q_fin, &dq_fin, &B, &ld, &status, &cost_w, &cost};
     return cudaLaunchKernel((const void*)P->k[RB_JK_ROLLOUT], dim3(jgrid(B, RB_RO_BLOCK)), dim3(RB_RO_BLOCK), args, 0, st);
 }
+cudaError_t j_rnea_f32(const void* param, const float* q, const float* dq, const float* ddq, float* tau, size_t B, size_t ld, cudaStream_t st) {
+    const RbJitParam* P = (const RbJitParam*)param;
+    if (B == 0) return cudaSuccess;
+    RbEmptyParam ep{0};
+    void* args[] = {&ep, &q, &dq, &ddq, &tau, &B, &ld};
+    return cudaLaunchKernel((const void*)P->k[RB_JK_RNEA_F32], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
+}
+cudaError_t j_fd_f32(const void* param, const float* q, const float* dq, const float* tau, float* qdd, size_t B, size_t ld, int* status, cudaStream_t st) {
+    const RbJitParam* P = (const RbJitParam*)param;
+    if (B == 0) return cudaSuccess;
+    RbEmptyParam ep{0};
+    void* args[] = {&ep, &q, &dq, &tau, &qdd, &B, &ld, &status};
+    return cudaLaunchKernel((const void*)P->k[RB_JK_FD_F32], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
+}
 }  // namespace
 
 const RbOps* rb_ops_jit() {
     static const RbOps ops = {"jit-specialised", 0, sizeof(RbJitParam), false, &j_rnea, &j_fd, &j_rnea_aos, &j_fd_aos,
-                              &j_crba, &j_fk, &j_jac, &j_rollout};
+                              &j_crba, &j_fk, &j_jac, &j_rollout, &j_rnea_f32, &j_fd_f32};
     return &ops;
 }

@@ -11,6 +11,7 @@
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #else
 typedef unsigned int uint32_t;
 typedef unsigned long long uint64_t;
@@ -59,6 +60,12 @@ struct RbOps {
     cudaError_t (*rollout)(const void* param, const double* q0, const double* dq0, const double* tau, double dt,
                            int horizon, double* q_traj, double* dq_traj, double* q_fin, double* dq_fin,
                            size_t B, size_t ld, int* status, const double* cost_w, double* cost, cudaStream_t st);
+    // optional fp32 mode (BASELINE.json: "an optional fp32 mode is held to a stated 1e-4 tolerance"): the same kernels
+    // instantiated with Real = float, device-resident SoA batches only (null = family has no fp32 kernels)
+    cudaError_t (*rnea_f32)(const void* param, const float* q, const float* dq, const float* ddq, float* tau,
+                            size_t B, size_t ld, cudaStream_t st);
+    cudaError_t (*fd_f32)(const void* param, const float* q, const float* dq, const float* tau, float* qdd,
+                          size_t B, size_t ld, int* status, cudaStream_t st);
 };
 
 const RbOps* rb_ops_fr3();        // compile-time FR3 model (rb_kernels_fr3.cu)
@@ -82,27 +89,32 @@ struct RbNParam {
     size_t hpk_states;       // states per chunk
 };
 
-template <int N>
-RB_DI void rb_load(const double* __restrict__ x, size_t ld, size_t s, double (&v)[N]) {
+// Quiet NaN of the scalar type (marks states whose mass matrix was not positive definite).
+template <class T> RB_DI T rb_nan();
+template <> RB_DI double rb_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+template <> RB_DI float rb_nan<float>() { return __int_as_float(0x7fc00000); }
+
+template <int N, class T>
+RB_DI void rb_load(const T* __restrict__ x, size_t ld, size_t s, T (&v)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = __ldcs(x + (size_t)i * ld + s);
 }
-template <int N>
-RB_DI void rb_store(double* __restrict__ x, size_t ld, size_t s, const double (&v)[N]) {
+template <int N, class T>
+RB_DI void rb_store(T* __restrict__ x, size_t ld, size_t s, const T (&v)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) __stcs(x + (size_t)i * ld + s, v[i]);
 }
 
-// AoS batches ([B][N], the reference's double[7] repeated): a block stages its RB_BLOCK states through shared
+// AoS batches ([B][N], the reference's RB_R[7] repeated): a block stages its RB_BLOCK states through shared
 // memory so the global accesses stay contiguous runs; thread t then reads its N values at stride N (odd N: no
 // bank conflicts).  No extra pass over HBM, unlike a separate transpose.
-template <int N>
-RB_DI void rb_aos_load3(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ x2,
-                        size_t B, double* buf, double (&a)[N], double (&b)[N], double (&c)[N]) {
+template <int N, class T>
+RB_DI void rb_aos_load3(const T* __restrict__ x0, const T* __restrict__ x1, const T* __restrict__ x2,
+                        size_t B, T* buf, T (&a)[N], T (&b)[N], T (&c)[N]) {
     const size_t base = (size_t)blockIdx.x * RB_BLOCK * N;
     const size_t rest = B * N - base;
     const int cnt = rest < (size_t)RB_BLOCK * N ? (int)rest : RB_BLOCK * N;
-    double* b0 = buf; double* b1 = buf + RB_BLOCK * N; double* b2 = buf + 2 * RB_BLOCK * N;
+    T* b0 = buf; T* b1 = buf + RB_BLOCK * N; T* b2 = buf + 2 * RB_BLOCK * N;
     for (int k = threadIdx.x; k < cnt; k += RB_BLOCK) {
         b0[k] = __ldcs(x0 + base + k); b1[k] = __ldcs(x1 + base + k); b2[k] = __ldcs(x2 + base + k);
     }
@@ -113,12 +125,12 @@ RB_DI void rb_aos_load3(const double* __restrict__ x0, const double* __restrict_
         for (int i = 0; i < N; ++i) { a[i] = b0[o + i]; b[i] = b1[o + i]; c[i] = b2[o + i]; }
     } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) { a[i] = 0.0; b[i] = 0.0; c[i] = 0.0; }
+        for (int i = 0; i < N; ++i) { a[i] = T(0); b[i] = T(0); c[i] = T(0); }
     }
     __syncthreads();
 }
-template <int N>
-RB_DI void rb_aos_store(double* __restrict__ out, size_t B, double* buf, const double (&v)[N]) {
+template <int N, class T>
+RB_DI void rb_aos_store(T* __restrict__ out, size_t B, T* buf, const T (&v)[N]) {
     const size_t base = (size_t)blockIdx.x * RB_BLOCK * N;
     const size_t rest = B * N - base;
     const int cnt = rest < (size_t)RB_BLOCK * N ? (int)rest : RB_BLOCK * N;
@@ -131,13 +143,14 @@ RB_DI void rb_aos_store(double* __restrict__ out, size_t B, double* buf, const d
 
 template <class M, bool AOS = false>
 __global__ void __launch_bounds__(RB_BLOCK, M::kSpecialised ? RB_MINB_RNEA : RB_MINB_RNEA_RT)
-rb_rnea_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
-               const double* __restrict__ ddq, double* __restrict__ tau, size_t B, size_t ld) {
+rb_rnea_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
+               const RB_R* __restrict__ ddq, RB_R* __restrict__ tau, size_t B, size_t ld) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    double a[N], b[N], c[N], sn[N], cs[N], t[N];
+    RB_R a[N], b[N], c[N], sn[N], cs[N], t[N];
     if constexpr (AOS) {
-        extern __shared__ double rb_aos_buf[];
+        extern __shared__ double rb_aos_raw[];
+        RB_R* rb_aos_buf = reinterpret_cast<RB_R*>(rb_aos_raw);
         rb_aos_load3<N>(q, dq, ddq, B, rb_aos_buf, a, b, c);
         rb_sincos_all<N>(a, sn, cs);
         rb_rnea<M, true>(p, sn, cs, b, c, t);
@@ -155,13 +168,14 @@ rb_rnea_kernel(const __grid_constant__ typename M::Param p, const double* __rest
 
 template <class M, bool AOS = false>
 __global__ void __launch_bounds__(RB_BLOCK, M::kSpecialised ? RB_MINB_FD : RB_MINB_FD_RT)
-rb_fd_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
-             const double* __restrict__ tau, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
+rb_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
+             const RB_R* __restrict__ tau, RB_R* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    double a[N], b[N], c[N], sn[N], cs[N], x[N];
+    RB_R a[N], b[N], c[N], sn[N], cs[N], x[N];
     if constexpr (AOS) {
-        extern __shared__ double rb_aos_buf[];
+        extern __shared__ double rb_aos_raw[];
+        RB_R* rb_aos_buf = reinterpret_cast<RB_R*>(rb_aos_raw);
         rb_aos_load3<N>(q, dq, tau, B, rb_aos_buf, a, b, c);
     } else {
         if (s >= B) return;
@@ -174,10 +188,11 @@ rb_fd_kernel(const __grid_constant__ typename M::Param p, const double* __restri
     if (!ok) {
         if (s < B) atomicOr(status, RB_STATUS_NOT_SPD);     // padding threads of an AoS tail block do not count
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = __longlong_as_double(0x7ff8000000000000LL);
+        for (int i = 0; i < N; ++i) x[i] = rb_nan<RB_R>();
     }
     if constexpr (AOS) {
-        extern __shared__ double rb_aos_buf[];
+        extern __shared__ double rb_aos_raw[];
+        RB_R* rb_aos_buf = reinterpret_cast<RB_R*>(rb_aos_raw);
         rb_aos_store<N>(qdd, B, rb_aos_buf, x);
     } else {
         rb_store<N>(qdd, ld, s, x);
@@ -194,8 +209,8 @@ rb_fd_kernel(const __grid_constant__ typename M::Param p, const double* __restri
 #define RB_STAGES 2
 template <class M, int MINB, bool IS_FD>
 __global__ void __launch_bounds__(RB_BLOCK, MINB)
-rb_stream_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ in0, const double* __restrict__ in1,
-                 const double* __restrict__ in2, double* __restrict__ out, unsigned num_tiles, size_t ld, int* __restrict__ status) {
+rb_stream_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ in0, const RB_R* __restrict__ in1,
+                 const RB_R* __restrict__ in2, RB_R* __restrict__ out, unsigned num_tiles, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N, ROWS = 3 * N;
     extern __shared__ __align__(128) double rb_stage[];      // [RB_STAGES][ROWS][RB_BLOCK]
     __shared__ __align__(8) uint64_t bar[RB_STAGES];
@@ -208,12 +223,12 @@ rb_stream_kernel(const __grid_constant__ typename M::Param p, const double* __re
     __syncthreads();
     auto issue = [&](unsigned tile, int st) {
         const size_t s0 = (size_t)tile * RB_BLOCK;
-        double* dst = rb_stage + (size_t)st * ROWS * RB_BLOCK;
-        rb_mbar_expect_tx(&bar[st], ROWS * RB_BLOCK * (uint32_t)sizeof(double));
+        RB_R* dst = rb_stage + (size_t)st * ROWS * RB_BLOCK;
+        rb_mbar_expect_tx(&bar[st], ROWS * RB_BLOCK * (uint32_t)sizeof(RB_R));
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            const double* src = (r < N ? in0 : (r < 2 * N ? in1 : in2)) + (size_t)(r % N) * ld + s0;
-            rb_bulk_g2s(dst + r * RB_BLOCK, src, RB_BLOCK * (uint32_t)sizeof(double), &bar[st]);
+            const RB_R* src = (r < N ? in0 : (r < 2 * N ? in1 : in2)) + (size_t)(r % N) * ld + s0;
+            rb_bulk_g2s(dst + r * RB_BLOCK, src, RB_BLOCK * (uint32_t)sizeof(RB_R), &bar[st]);
         }
     };
     if (tid == 0) {
@@ -228,8 +243,8 @@ rb_stream_kernel(const __grid_constant__ typename M::Param p, const double* __re
     for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int st = it % RB_STAGES;
         rb_mbar_wait(&bar[st], (it / RB_STAGES) & 1);
-        const double* src = rb_stage + (size_t)st * ROWS * RB_BLOCK + tid;
-        double a[N], b[N], c[N], sn[N], cs[N], x[N];
+        const RB_R* src = rb_stage + (size_t)st * ROWS * RB_BLOCK + tid;
+        RB_R a[N], b[N], c[N], sn[N], cs[N], x[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             a[i] = src[i * RB_BLOCK]; b[i] = src[(N + i) * RB_BLOCK]; c[i] = src[(2 * N + i) * RB_BLOCK];
@@ -244,7 +259,7 @@ rb_stream_kernel(const __grid_constant__ typename M::Param p, const double* __re
             if (!rb_forward_dynamics<M>(p, sn, cs, b, c, x)) {
                 ok = false;
 #pragma unroll
-                for (int i = 0; i < N; ++i) x[i] = __longlong_as_double(0x7ff8000000000000LL);
+                for (int i = 0; i < N; ++i) x[i] = rb_nan<RB_R>();
             }
         } else {
             rb_rnea<M, true>(p, sn, cs, b, c, x);
@@ -257,29 +272,29 @@ rb_stream_kernel(const __grid_constant__ typename M::Param p, const double* __re
 // H out: reference convention, n*n entries per state, entry k = r + n*c, upper filled, strict lower 0.
 template <class M>
 __global__ void __launch_bounds__(RB_BLOCK)
-rb_crba_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, double* __restrict__ Hout,
+rb_crba_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, RB_R* __restrict__ Hout,
                size_t B, size_t ld) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
     if (s >= B) return;
-    double a[N], sn[N], cs[N], H[N][N];
+    RB_R a[N], sn[N], cs[N], H[N][N];
     rb_load<N>(q, ld, s, a);
     rb_sincos_all<N>(a, sn, cs);
     rb_crba<M>(p, sn, cs, H);
 #pragma unroll
     for (int c = 0; c < N; ++c)
 #pragma unroll
-        for (int r = 0; r < N; ++r) __stcs(Hout + (size_t)(r + N * c) * ld + s, r <= c ? H[r][c] : 0.0);
+        for (int r = 0; r < N; ++r) __stcs(Hout + (size_t)(r + N * c) * ld + s, r <= c ? H[r][c] : RB_R(0));
 }
 
 template <class M>
 __global__ void __launch_bounds__(RB_BLOCK)
-rb_fwd_kin_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, double* __restrict__ xyz,
+rb_fwd_kin_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, RB_R* __restrict__ xyz,
                   size_t B, size_t ld) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
     if (s >= B) return;
-    double a[N], sn[N], cs[N], pos[3];
+    RB_R a[N], sn[N], cs[N], pos[3];
     rb_load<N>(q, ld, s, a);
     rb_sincos_all<N>(a, sn, cs);
     rb_fwd_kin<M>(p, sn, cs, pos);
@@ -288,12 +303,12 @@ rb_fwd_kin_kernel(const __grid_constant__ typename M::Param p, const double* __r
 
 template <class M>
 __global__ void __launch_bounds__(RB_BLOCK)
-rb_jac_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, double* __restrict__ Jout,
+rb_jac_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, RB_R* __restrict__ Jout,
               size_t B, size_t ld) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
     if (s >= B) return;
-    double a[N], sn[N], cs[N], J[N][6];
+    RB_R a[N], sn[N], cs[N], J[N][6];
     rb_load<N>(q, ld, s, a);
     rb_sincos_all<N>(a, sn, cs);
     rb_jac<M>(p, sn, cs, J);
@@ -315,23 +330,23 @@ enum : int { RB_CW_QREF = 0, RB_CW_Q, RB_CW_DQ, RB_CW_TAU, RB_CW_QF, RB_CW_DQF, 
 #endif
 template <class M>
 __global__ void __launch_bounds__(RB_RO_BLOCK, RB_MINB_ROLLOUT * (RB_BLOCK / RB_RO_BLOCK))
-rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q0, const double* __restrict__ dq0,
-                  const double* __restrict__ tau, double dt, int horizon, double* __restrict__ q_traj,
-                  double* __restrict__ dq_traj, double* __restrict__ q_fin, double* __restrict__ dq_fin,
-                  size_t B, size_t ld, int* __restrict__ status, const double* __restrict__ cost_w, double* __restrict__ cost) {
+rb_rollout_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q0, const RB_R* __restrict__ dq0,
+                  const RB_R* __restrict__ tau, RB_R dt, int horizon, RB_R* __restrict__ q_traj,
+                  RB_R* __restrict__ dq_traj, RB_R* __restrict__ q_fin, RB_R* __restrict__ dq_fin,
+                  size_t B, size_t ld, int* __restrict__ status, const RB_R* __restrict__ cost_w, RB_R* __restrict__ cost) {
     constexpr int N = M::N;
     const size_t s = (size_t)blockIdx.x * RB_RO_BLOCK + threadIdx.x;
     if (s >= B) return;
-    double q[N], dq[N];
+    RB_R q[N], dq[N];
     rb_load<N>(q0, ld, s, q);
     rb_load<N>(dq0, ld, s, dq);
     bool ok = true;
-    double J = 0.0;                                    // running quadratic cost (sampling-based MPC), see RbQuadCost
+    RB_R J = RB_R(0);                                // running quadratic cost (sampling-based MPC), see RbQuadCost
     const size_t step = (size_t)N * ld;
-    double u[N];
+    RB_R u[N];
     rb_load<N>(tau, ld, s, u);
     for (int t = 0; t < horizon; ++t) {
-        double sn[N], cs[N], qdd[N], un[N];
+        RB_R sn[N], cs[N], qdd[N], un[N];
         // prefetch the next step's torques so the load latency hides behind this step's arithmetic
         if (t + 1 < horizon) rb_load<N>(tau + (size_t)(t + 1) * step, ld, s, un);
         rb_sincos_all<N>(q, sn, cs);
@@ -344,10 +359,10 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __r
         if (q_traj) rb_store<N>(q_traj + (size_t)t * step, ld, s, q);
         if (dq_traj) rb_store<N>(dq_traj + (size_t)t * step, ld, s, dq);
         if (cost) {                                    // stage cost of the state reached and the torque applied
-            double c = 0.0;
+            RB_R c = RB_R(0);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const double e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
+                const RB_R e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
                 c = fma(__ldg(cost_w + RB_CW_Q * RB_MAX_N + i) * e, e, c);
                 c = fma(__ldg(cost_w + RB_CW_DQ * RB_MAX_N + i) * dq[i], dq[i], c);
                 c = fma(__ldg(cost_w + RB_CW_TAU * RB_MAX_N + i) * u[i], u[i], c);
@@ -362,11 +377,11 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const double* __r
     if (cost) {                                        // terminal cost
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
+            const RB_R e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
             J = fma(__ldg(cost_w + RB_CW_QF * RB_MAX_N + i) * e, e, J);
             J = fma(__ldg(cost_w + RB_CW_DQF * RB_MAX_N + i) * dq[i], dq[i], J);
         }
-        __stcs(cost + s, ok ? J : __longlong_as_double(0x7ff8000000000000LL));
+        __stcs(cost + s, ok ? J : rb_nan<RB_R>());
     }
     if (q_fin) rb_store<N>(q_fin, ld, s, q);
     if (dq_fin) rb_store<N>(dq_fin, ld, s, dq);
@@ -473,11 +488,29 @@ struct RbLaunch {
                                                           q_fin, dq_fin, B, ld, status, cost_w, cost);
         return cudaGetLastError();
     }
+    // M32 = the same policy with Real = float (fp32 mode)
+    template <class M32>
+    static cudaError_t rnea_f32(const void* param, const float* q, const float* dq, const float* ddq, float* tau,
+                                size_t B, size_t ld, cudaStream_t st) {
+        if (B == 0) return cudaSuccess;
+        rb_rnea_kernel<M32, false><<<grid(B), RB_BLOCK, 0, st>>>(*(const typename M32::Param*)param, q, dq, ddq, tau, B, ld);
+        return cudaGetLastError();
+    }
+    template <class M32>
+    static cudaError_t fd_f32(const void* param, const float* q, const float* dq, const float* tau, float* qdd,
+                              size_t B, size_t ld, int* status, cudaStream_t st) {
+        if (B == 0) return cudaSuccess;
+        rb_fd_kernel<M32, false><<<grid(B), RB_BLOCK, 0, st>>>(*(const typename M32::Param*)param, q, dq, tau, qdd, B, ld, status);
+        return cudaGetLastError();
+    }
+    template <class M32 = void>
     static RbOps ops(const char* name) {
         RbOps o;
         o.name = name; o.n = M::N; o.param_bytes = sizeof(P); o.shared_scratch = false;
         o.rnea = &rnea; o.fd = &fd; o.rnea_aos = &rnea_aos; o.fd_aos = &fd_aos;
         o.crba = &crba; o.fwd_kin = &fwd_kin; o.jac = &jac; o.rollout = &rollout;
+        o.rnea_f32 = nullptr; o.fd_f32 = nullptr;
+        if constexpr (!std::is_void<M32>::value) { o.rnea_f32 = &rnea_f32<M32>; o.fd_f32 = &fd_f32<M32>; }
         return o;
     }
 };

@@ -6,7 +6,7 @@
 #include "gen/model_fr3.h"
 
 const RbOps* rb_ops_fr3() {
-    static const RbOps ops = RbLaunch<CtModel<TabFr3>>::ops("fr3-specialised");
+    static const RbOps ops = RbLaunch<CtModel<TabFr3>>::ops<CtModel<TabFr3, float>>("fr3-specialised");
     return &ops;
 }
 

@@ -120,6 +120,7 @@ struct RbLaunchLong {
         RbOps o;
         o.name = name; o.n = M::N; o.param_bytes = sizeof(LP); o.shared_scratch = true;      // the H chunk buffer
         o.rnea = &rnea; o.fd = &fd; o.rnea_aos = nullptr; o.fd_aos = nullptr; o.crba = &crba; o.fwd_kin = nullptr; o.jac = nullptr; o.rollout = nullptr;
+        o.rnea_f32 = nullptr; o.fd_f32 = nullptr;
         return o;
     }
 };

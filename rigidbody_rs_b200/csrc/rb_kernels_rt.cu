@@ -3,6 +3,6 @@
 #include "rb_kernels.cuh"
 
 const RbOps* rb_ops_rt7() {
-    static const RbOps ops = RbLaunch<RtModel<7>>::ops("generic-7");
+    static const RbOps ops = RbLaunch<RtModel<7>>::ops<RtModel<7, float>>("generic-7");
     return &ops;
 }

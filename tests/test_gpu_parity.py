@@ -314,6 +314,32 @@ def test_jit_random_chains_match_matrix_oracle(rb, n, seed):
     assert np.abs(J - ch.jac(q[:64])).max() < TOL
 
 
+def test_fp32_mode_tolerances(rb, oracle_fr3):
+    """Optional fp32 mode (include/rigidbody.h): float kernels against the fp64 oracle on the same (float-rounded)
+    inputs.  Stated tolerance (BASELINE.json north_star), per state max_i|x_i - ref_i| <= 1e-4 * max(1, ||ref||_inf)."""
+    import torch
+    B = 200_000
+    q, dq, ddq, tau = _states(oracle_fr3, B)
+    f = [np.ascontiguousarray(x, dtype=np.float32) for x in (q, dq, ddq, tau)]
+    want_t = oracle_fr3.rnea_batch(*(x.astype(np.float64) for x in f[:3]))
+    want_a = oracle_fr3.forward_dynamics_batch(f[0].astype(np.float64), f[1].astype(np.float64), f[3].astype(np.float64))
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(x).to(dev) for x in f]
+    for mb in _variants(rb, FR3):
+        if mb.kernel_variant == "generic-n":
+            with pytest.raises(rb.RigidBodyError):
+                mb.rnea(t[0], t[1], t[2])
+            continue
+        got_t = mb.rnea(t[0], t[1], t[2])
+        got_a = mb.forward_dynamics(t[0], t[1], t[3])
+        assert got_t.dtype == torch.float32
+        e_t = state_err(got_t.cpu().numpy().astype(np.float64), want_t, 0)
+        e_a = state_err(got_a.cpu().numpy().astype(np.float64), want_a, 0)
+        assert e_t.max() < 1e-4, (mb.kernel_variant, e_t.max())
+        assert e_a.max() < 1e-4, (mb.kernel_variant, e_a.max())
+        print(mb.kernel_variant, "fp32 errors: rnea", e_t.max(), "fd", e_a.max(), "fd 99.9th pct", np.quantile(e_a, 0.999))
+
+
 def test_not_spd_is_reported(rb):
     """A physically impossible chain (negative rotational inertia) makes H indefinite: host calls return
     RB_ERR_NOT_SPD and NaN rows instead of garbage."""

@@ -13,6 +13,7 @@ ap.add_argument("--tag", default="")
 ap.add_argument("--urdf", default="assets/fr3.urdf")
 ap.add_argument("--ops", default="rnea,fd")
 ap.add_argument("--layout", default="soa", choices=["soa", "aos"])
+ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
 a = ap.parse_args()
 mb = rb.Multibody.from_urdf(a.urdf)
 n, B = mb.n, a.states
@@ -21,7 +22,7 @@ dev = torch.device("cuda:0")
 q = torch.empty((n, B), dtype=torch.float64, device=dev)
 dq, x3, out = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
 mb.fill(q, 1, 0, lim["lower"], lim["upper"]); mb.fill(dq, 1, 1, -lim["velocity"], lim["velocity"]); mb.fill(x3, 1, 2, -10.0, 10.0)
-res = {"tag": a.tag, "variant": mb.kernel_variant, "states": B, "layout": a.layout}
+res = {"tag": a.tag, "variant": mb.kernel_variant, "states": B, "layout": a.layout, "dtype": a.dtype}
 H = 64
 for op in a.ops.split(","):
     units = B
@@ -39,7 +40,10 @@ for op in a.ops.split(","):
         fn = lambda: mb.crba(qc, out=Hout)
         units = Bc
     else:
-        if a.layout == "aos":
+        if a.dtype == "f32":
+            q32, dq32, x32, o32 = (t.float() for t in (q, dq, x3, out))
+            fn = {"rnea": lambda: mb.rnea(q32, dq32, x32, out=o32), "fd": lambda: mb.forward_dynamics(q32, dq32, x32, out=o32)}[op]
+        elif a.layout == "aos":
             qa, dqa, x3a, outa = (t.t().contiguous() for t in (q, dq, x3, out))
             fn = {"rnea": lambda: mb.rnea(qa, dqa, x3a, layout="aos", out=outa),
                   "fd": lambda: mb.forward_dynamics(qa, dqa, x3a, layout="aos", out=outa)}[op]
