@@ -49,7 +49,8 @@ void multibody_free_result(double* p);
 /* New: number of movable joints kept by from_urdf (7 for the FR3; the reference panics otherwise, multibody.rs:76). */
 int multibody_n_joints(const Multibody* mb);
 /* New: the flattened model as loaded on the host (no GPU needed): parent_rot [9n], parent_trans [3n], mass [n],
- * h = m*com [3n], inertia_origin [6n] (xx xy xz yy yz zz).  Any output may be NULL. */
+ * h = m*com [3n], inertia_origin [6n] (xx xy xz yy yz zz), in the engine's joint frames (equal to the URDF's when
+ * every axis is +z, re-based so that the axis is z otherwise).  Any output may be NULL. */
 int multibody_get_model(const Multibody* mb, double* parent_rot, double* parent_trans, double* mass,
                         double* h, double* inertia_origin);
 
@@ -87,8 +88,12 @@ typedef struct RbChainDesc {
     int32_t n_joints;             /* 1..RB_MAX_JOINTS */
     const int32_t* parent;        /* [n] parent link index, -1 = base.  NULL = serial chain (i-1).  Only serial
                                      chains are accepted: the reference is serial-only (multibody.rs:148,165). */
-    const double* axis;           /* [3n] unit joint axes (joint.rs:27).  Must be (0,0,1): rnea/crba hard-code z
-                                     (multibody.rs:29,130).  NULL = all z. */
+    const double* axis;           /* [3n] joint axes in the joint frames (joint.rs:27), any non-zero vector (normalised
+                                     on load, joint.rs:56).  NULL = all +z.  The reference's rnea/crba hard-code z
+                                     (multibody.rs:29,130) and agree with its own kinematics only for +z; here a
+                                     non-z axis is used consistently: the loader re-bases the joint frame so that
+                                     the axis becomes z, and the kernels stay z-only.  tau, qdd, H, fwd_kin and jac
+                                     are those of the chain as described. */
     const double* parent_rot;     /* [9n] row-major rotation of joint frame i in link i-1 (joint.rs:29 .rotation) */
     const double* parent_trans;   /* [3n] translation of joint frame i in link i-1 (joint.rs:29 .translation) */
     const double* mass;           /* [n]  inertia.rs:13 */

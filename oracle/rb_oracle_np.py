@@ -60,12 +60,17 @@ class ChainNP:
             C = _skew(c[i])
             Io.append(Ic + self.m[i] * C @ C.T)                                   # inertia.rs:31-32
         self.Io = np.stack(Io)
+        self.axis = np.tile(np.array([0.0, 0.0, 1.0]), (n, 1))      # the dynamics' axis (multibody.rs:29,130)
 
     @classmethod
-    def from_arrays(cls, Rp, tp, mass, com, inertia_com):
-        """Chain given directly by its flattened descriptor (what RbChainDesc carries)."""
+    def from_arrays(cls, Rp, tp, mass, com, inertia_com, axis=None):
+        """Chain given directly by its flattened descriptor (what RbChainDesc carries).  `axis` [n,3]: joint axes in
+        the joint frames, used CONSISTENTLY by kinematics and dynamics (the reference uses them in the kinematics
+        only, joint.rs:48-50 vs multibody.rs:130; for +z the two agree)."""
         self = cls.__new__(cls)
         self.n = len(mass)
+        ax = np.tile(np.array([0.0, 0.0, 1.0]), (self.n, 1)) if axis is None else np.array(axis, dtype=np.float64)
+        self.axis = ax / np.linalg.norm(ax, axis=1, keepdims=True)
         self.Rp = np.array(Rp, dtype=np.float64); self.tp = np.array(tp, dtype=np.float64)
         self.m = np.array(mass, dtype=np.float64)
         c = np.array(com, dtype=np.float64)
@@ -75,11 +80,12 @@ class ChainNP:
 
     # -- helpers, all batched over leading axis B
     def _R(self, i, q):
-        """R_i(q) = R_p Rz(q): [B,3,3]"""
-        c, s = np.cos(q), np.sin(q)
-        Rz = np.zeros(q.shape + (3, 3))
-        Rz[..., 0, 0] = c; Rz[..., 0, 1] = -s; Rz[..., 1, 0] = s; Rz[..., 1, 1] = c; Rz[..., 2, 2] = 1.0
-        return self.Rp[i] @ Rz
+        """R_i(q) = R_p Rot(axis_i, q): [B,3,3]  (Rodrigues; Rz(q) for the +z axis)"""
+        c, s = np.cos(q)[..., None, None], np.sin(q)[..., None, None]
+        a = self.axis[i]
+        K = _skew(a)
+        Rq = np.eye(3) + s * K + (1.0 - c) * (K @ K)
+        return self.Rp[i] @ Rq
 
     def _Imul(self, i, lin, rot):
         f_lin = self.m[i] * lin - np.cross(self.h[i], rot)
@@ -100,21 +106,21 @@ class ChainNP:
             t = self.tp[i]
             v_lin = np.einsum("bij,bj->bi", Rt, v_lin - np.cross(t, v_rot))
             v_rot = np.einsum("bij,bj->bi", Rt, v_rot)
-            v_rot[:, 2] += dq[:, i]
+            ax = self.axis[i]
+            v_rot = v_rot + ax * dq[:, i:i + 1]
             a_lin = np.einsum("bij,bj->bi", Rt, a_lin - np.cross(t, a_rot))
             a_rot = np.einsum("bij,bj->bi", Rt, a_rot)
-            a_rot[:, 2] += ddq[:, i]
-            a_lin[:, 0] += v_lin[:, 1] * dq[:, i]
-            a_lin[:, 1] += -v_lin[:, 0] * dq[:, i]
-            a_rot[:, 0] += v_rot[:, 1] * dq[:, i]
-            a_rot[:, 1] += -v_rot[:, 0] * dq[:, i]
+            a_rot = a_rot + ax * ddq[:, i:i + 1]
+            # v x (S dq), S = (axis; 0):  lin += v_lin x axis dq,  rot += v_rot x axis dq
+            a_lin = a_lin + np.cross(v_lin, ax) * dq[:, i:i + 1]
+            a_rot = a_rot + np.cross(v_rot, ax) * dq[:, i:i + 1]
             Ia_l, Ia_r = self._Imul(i, a_lin, a_rot)
             Iv_l, Iv_r = self._Imul(i, v_lin, v_rot)
             f_lin.append(Ia_l + np.cross(v_rot, Iv_l))
             f_rot.append(Ia_r + np.cross(v_rot, Iv_r) + np.cross(v_lin, Iv_l))
         tau = np.zeros((B, n))
         for i in range(n - 1, -1, -1):
-            tau[:, i] = f_rot[i][:, 2]
+            tau[:, i] = f_rot[i] @ self.axis[i]
             if i > 0:
                 Rl = np.einsum("bij,bj->bi", R[i], f_lin[i])
                 f_lin[i - 1] = f_lin[i - 1] + Rl
@@ -129,14 +135,15 @@ class ChainNP:
         H = np.zeros((B, n, n))
         m = np.full(B, self.m[n - 1]); h = np.tile(self.h[n - 1], (B, 1)); Io = np.tile(self.Io[n - 1], (B, 1, 1))
         for i in range(n - 1, -1, -1):
-            H[:, i, i] = Io[:, 2, 2]
-            F_lin = -np.cross(h, np.array([0.0, 0.0, 1.0]))     # I * S_z
-            F_rot = Io[:, :, 2].copy()
+            ax = self.axis[i]
+            F_lin = -np.cross(h, ax)                            # I * S,  S = (axis; 0)
+            F_rot = Io @ ax
+            H[:, i, i] = F_rot @ ax
             for j in range(i - 1, -1, -1):
                 Rl = np.einsum("bij,bj->bi", R[j + 1], F_lin)
                 F_rot = np.einsum("bij,bj->bi", R[j + 1], F_rot) + np.cross(self.tp[j + 1], Rl)
                 F_lin = Rl
-                H[:, j, i] = F_rot[:, 2]
+                H[:, j, i] = F_rot @ self.axis[j]
             if i > 0:
                 # composite inertia into the parent frame, 10-parameter form:
                 # h' = R h + m t ;  I_o' = R I_o R^T - [t]x[Rh]x - [Rh]x[t]x - m [t]x[t]x
@@ -184,11 +191,11 @@ class ChainNP:
         B, n = q.shape
         J = np.zeros((B, 6, n))
         Racc = np.tile(np.eye(3), (B, 1, 1)); p = np.zeros((B, 3))   # pose of tip in frame i
-        z = np.array([0.0, 0.0, 1.0])
         for i in range(n - 1, -1, -1):
             Rt = np.swapaxes(Racc, 1, 2)
+            z = self.axis[i]
             J[:, 0:3, i] = np.einsum("bij,bj->bi", Rt, -np.cross(p, z))
-            J[:, 3:6, i] = Rt[:, :, 2]
+            J[:, 3:6, i] = Rt @ z
             Ri = self._R(i, q[:, i])
             p = np.einsum("bij,bj->bi", Ri, p) + self.tp[i]
             Racc = Ri @ Racc

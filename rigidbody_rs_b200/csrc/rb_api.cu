@@ -148,8 +148,8 @@ int pick_ops(RbGpu* g) {
     const std::string want = force ? force : "auto";
     const int n = g->model.n;
     std::vector<double> flat = rb_model_flat(g->model);
-    const bool is_fr3 = n == 7 && memcmp(flat.data(), rb_fr3_table(), sizeof(double) * (7 * 24 + 3)) == 0;
-    const bool is_c32 = n == 32 && memcmp(flat.data(), rb_chain32_table(), sizeof(double) * (32 * 24 + 3)) == 0;
+    const bool is_fr3 = n == 7 && memcmp(flat.data(), rb_fr3_table(), sizeof(double) * RB_MODEL_DOUBLES(7)) == 0;
+    const bool is_c32 = n == 32 && memcmp(flat.data(), rb_chain32_table(), sizeof(double) * RB_MODEL_DOUBLES(32)) == 0;
     if ((want == "auto" || want == "fr3-specialised") && is_fr3) {
         g->ops = rb_ops_fr3();
         g->param.assign(g->ops->param_bytes, 0);

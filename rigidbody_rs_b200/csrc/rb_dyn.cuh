@@ -72,6 +72,7 @@ struct RtModel {
     }
     template <int K> static constexpr int gcls() { return RB_GEN; }
     template <int K> static RB_DI Real g(const Param& p) { return (Real)p.g[K]; }
+    template <int K> static RB_DI Real tip(const Param& p) { return (Real)p.tip[K]; }
 };
 
 // Compile-time model: Tab supplies `static constexpr int N; static constexpr double T[N][24]; G[3]`
@@ -95,6 +96,7 @@ struct CtModel {
     }
     template <int K> static constexpr int gcls() { return rb_classify(Tab::G[K]); }
     template <int K> static RB_DI Real g(const Param&) { constexpr Real v = (Real)Tab::G[K]; return v; }
+    template <int K> static RB_DI Real tip(const Param&) { constexpr Real v = (Real)Tab::TIP[K]; return v; }
 };
 
 #define KV(I, F, K) M::template val<I, F, K>(p)
@@ -452,7 +454,10 @@ RB_DI void rb_fwd_kin(const typename M::Param& p, const RB_R (&s)[M::N], const R
 template <class M>
 RB_DI void rb_jac(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], RB_R (&J)[M::N][6]) {
     constexpr int N = M::N;
-    RB_R A[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
+    // orientation of the reference's tip frame in the model's last frame (identity unless the last axis was re-based)
+    RB_R A[3][3] = {{M::template tip<0>(p), M::template tip<1>(p), M::template tip<2>(p)},
+                    {M::template tip<3>(p), M::template tip<4>(p), M::template tip<5>(p)},
+                    {M::template tip<6>(p), M::template tip<7>(p), M::template tip<8>(p)}};
     RB_R r[3] = {0.0, 0.0, 0.0};
     rb_for_down<N - 1>([&](auto ic) {
         constexpr int I = decltype(ic)::value;

@@ -153,6 +153,85 @@ void origin_inertia(double mass, const double c[3], const double Ic[9], double I
     I6[5] = Ic[8] + mass * (cc - cz * cz);
 }
 
+// One movable joint as the sources give it: axis and link inertia in the joint's own (child) frame.
+struct RawJoint {
+    double axis[3]; double R[9]; double t[3]; double mass; double com[3]; double Ic[9];
+};
+
+void mat3_mul(const double A[9], const double B[9], double C[9]) {
+    double T[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) T[3 * r + c] = A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+    memcpy(C, T, sizeof T);
+}
+void mat3_t(const double A[9], double T[9]) {
+    const double B[9] = {A[0], A[3], A[6], A[1], A[4], A[7], A[2], A[5], A[8]};
+    memcpy(T, B, sizeof B);
+}
+void mat3_vec(const double A[9], const double v[3], double o[3]) {
+    const double x = A[0] * v[0] + A[1] * v[1] + A[2] * v[2], y = A[3] * v[0] + A[4] * v[1] + A[5] * v[2],
+                 z = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+
+// The kernels rotate every joint about its frame's z axis, as the reference's rnea / crba do (multibody.rs:29,130).
+// A joint whose axis a is not +z (the reference would silently mis-handle it: joint_transform uses the axis,
+// joint.rs:48-50, the dynamics do not) is re-based: its frame is rotated by Q with Q z = a, so Rot(a, q) = Q Rz(q) Q^T
+// and everything attached to that frame (link inertia, the next joint's placement) is re-expressed in the rotated
+// frame.  tau, qdd, H and the tip position are invariant; the tip-frame Jacobian needs the last Q back (model.tip).
+int build_model(const std::vector<RawJoint>& raw, RbHostModel& out, std::string& err) {
+    double Qprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    bool prev_identity = true;
+    for (size_t i = 0; i < raw.size(); ++i) {
+        const RawJoint& j = raw[i];
+        const double an = std::sqrt(j.axis[0] * j.axis[0] + j.axis[1] * j.axis[1] + j.axis[2] * j.axis[2]);
+        if (!(an > 0.0) || !std::isfinite(an)) { err = "joint axis must be a non-zero finite vector"; return RB_ERR_ARG; }
+        const double a[3] = {j.axis[0] / an, j.axis[1] / an, j.axis[2] / an};       // UnitVector3::new_normalize (joint.rs:56)
+        double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        const bool identity = std::fabs(a[0]) < 1e-12 && std::fabs(a[1]) < 1e-12 && a[2] > 0.0;
+        if (!identity) {
+            if (a[2] < -1.0 + 1e-12) {
+                const double F[9] = {1, 0, 0, 0, -1, 0, 0, 0, -1};                   // z -> -z: half turn about x
+                memcpy(Q, F, sizeof F);
+            } else {
+                // minimal rotation taking z to a:  Q = I + [v]x + [v]x^2 / (1 + c),  v = z x a,  c = z . a
+                const double vx = -a[1], vy = a[0], c = a[2], k = 1.0 / (1.0 + c);
+                const double F[9] = {1.0 - k * vy * vy, k * vx * vy,       vy,
+                                     k * vx * vy,       1.0 - k * vx * vx, -vx,
+                                     -vy,               vx,                1.0 - k * (vx * vx + vy * vy)};
+                memcpy(Q, F, sizeof F);
+            }
+        }
+        RbJointK r{};
+        double R[9], t[3], com[3], Ic[9];
+        memcpy(R, j.R, sizeof R); memcpy(t, j.t, sizeof t); memcpy(com, j.com, sizeof com); memcpy(Ic, j.Ic, sizeof Ic);
+        if (!prev_identity) {                       // placement re-expressed in the re-based parent frame
+            double Qt[9]; mat3_t(Qprev, Qt);
+            mat3_mul(Qt, R, R);
+            mat3_vec(Qt, t, t);
+        }
+        if (!identity) {                            // child frame re-based: link inertia follows
+            double Qt[9]; mat3_t(Q, Qt);
+            mat3_mul(R, Q, R);
+            mat3_vec(Qt, com, com);
+            mat3_mul(Qt, Ic, Ic); mat3_mul(Ic, Q, Ic);
+        }
+        for (int e = 0; e < 9; ++e) r.R[e] = snap(R[e]);
+        for (int e = 0; e < 3; ++e) r.t[e] = t[e];
+        r.m = j.mass;
+        for (int e = 0; e < 3; ++e) r.h[e] = j.mass * com[e];
+        origin_inertia(j.mass, com, Ic, r.I);                                        // joint.rs:66
+        out.jt.push_back(r);
+        memcpy(Qprev, Q, sizeof Q);
+        prev_identity = identity;
+    }
+    mat3_t(Qprev, out.tip);                          // the original last frame seen from the re-based one
+    for (int e = 0; e < 9; ++e) out.tip[e] = snap(out.tip[e]);
+    out.n = (int)raw.size();
+    finish_model(out);
+    return RB_OK;
+}
+
 }  // namespace
 
 int rb_model_from_urdf(const char* path, RbHostModel& out, std::string& err) {
@@ -208,19 +287,15 @@ int rb_model_from_urdf(const char* path, RbHostModel& out, std::string& err) {
     }
 
     out = RbHostModel();
+    std::vector<RawJoint> raw;
     const size_t pairs = std::min(links.size(), joints.size());          // zip (multibody.rs:70)
     for (size_t k = 0; k < pairs; ++k) {
         const J& j = joints[k];
         const L& l = links[k];
         if (j.type.find("fixed") != std::string::npos) continue;          // multibody.rs:71
-        if (out.n >= RB_MAX_JOINTS) { err = "more than RB_MAX_JOINTS movable joints"; return RB_ERR_UNSUPPORTED; }
-        const double an = std::sqrt(j.axis[0] * j.axis[0] + j.axis[1] * j.axis[1] + j.axis[2] * j.axis[2]);
-        // rnea/crba hard-code the z motion subspace (multibody.rs:29,130); parity exists only for z axes.
-        if (!(an > 0.0) || std::fabs(j.axis[0] / an) > 1e-12 || std::fabs(j.axis[1] / an) > 1e-12 || j.axis[2] / an < 0.0) {
-            err = "joint '" + j.name + "': only +z revolute axes are supported (the reference hard-codes z)";
-            return RB_ERR_UNSUPPORTED;
-        }
-        RbJointK r{};
+        if (raw.size() >= RB_MAX_JOINTS) { err = "more than RB_MAX_JOINTS movable joints"; return RB_ERR_UNSUPPORTED; }
+        RawJoint r{};
+        memcpy(r.axis, j.axis, sizeof r.axis);
         // Rotation3::from_euler_angles(roll, pitch, yaw) = Rz(yaw) Ry(pitch) Rx(roll)   (joint.rs:59-63)
         const double sr = std::sin(j.rpy[0]), cr = std::cos(j.rpy[0]);
         const double sp = std::sin(j.rpy[1]), cp = std::cos(j.rpy[1]);
@@ -228,21 +303,20 @@ int rb_model_from_urdf(const char* path, RbHostModel& out, std::string& err) {
         const double R[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
                              sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
                              -sp,     cp * sr,                cp * cr};
-        for (int e = 0; e < 9; ++e) r.R[e] = snap(R[e]);
-        for (int e = 0; e < 3; ++e) r.t[e] = j.xyz[e];
-        r.m = l.mass;
-        for (int e = 0; e < 3; ++e) r.h[e] = l.mass * l.com[e];
+        memcpy(r.R, R, sizeof R);
+        memcpy(r.t, j.xyz, sizeof r.t);
+        r.mass = l.mass;
+        memcpy(r.com, l.com, sizeof r.com);
         const double Ic[9] = {l.six[0], l.six[1], l.six[2], l.six[1], l.six[3], l.six[4], l.six[2], l.six[4], l.six[5]};
-        origin_inertia(l.mass, l.com, Ic, r.I);                            // joint.rs:66
-        out.jt.push_back(r);
-        out.lim.lower[out.n] = j.lim[0]; out.lim.upper[out.n] = j.lim[1];
-        out.lim.velocity[out.n] = j.lim[2]; out.lim.effort[out.n] = j.lim[3];
+        memcpy(r.Ic, Ic, sizeof Ic);
+        raw.push_back(r);
+        const int i = (int)raw.size() - 1;
+        out.lim.lower[i] = j.lim[0]; out.lim.upper[i] = j.lim[1];
+        out.lim.velocity[i] = j.lim[2]; out.lim.effort[i] = j.lim[3];
         out.names.push_back(j.name);
-        ++out.n;
     }
-    if (out.n == 0) { err = "URDF holds no movable joint"; return RB_ERR_URDF; }
-    finish_model(out);
-    return RB_OK;
+    if (raw.empty()) { err = "URDF holds no movable joint"; return RB_ERR_URDF; }
+    return build_model(raw, out, err);
 }
 
 int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err) {
@@ -253,20 +327,15 @@ int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err)
         err = "descriptor array is NULL"; return RB_ERR_NULL;
     }
     out = RbHostModel();
-    out.n = d->n_joints;
-    for (int i = 0; i < out.n; ++i) {
+    std::vector<RawJoint> raw;
+    for (int i = 0; i < d->n_joints; ++i) {
         if (d->parent && d->parent[i] != i - 1) {
             err = "only serial chains are supported (parent[i] must be i-1; the reference is serial-only)";
             return RB_ERR_UNSUPPORTED;
         }
-        if (d->axis) {
-            const double* a = d->axis + 3 * i;
-            if (std::fabs(a[0]) > 1e-12 || std::fabs(a[1]) > 1e-12 || std::fabs(a[2] - 1.0) > 1e-12) {
-                err = "only +z joint axes are supported (the reference hard-codes z)";
-                return RB_ERR_UNSUPPORTED;
-            }
-        }
-        RbJointK r{};
+        RawJoint r{};
+        r.axis[0] = 0.0; r.axis[1] = 0.0; r.axis[2] = 1.0;
+        if (d->axis) memcpy(r.axis, d->axis + 3 * i, sizeof r.axis);
         const double* R = d->parent_rot + 9 * i;
         // must be a rotation: R R^T = Id within 1e-9
         for (int a = 0; a < 3; ++a)
@@ -275,13 +344,13 @@ int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err)
                 for (int k = 0; k < 3; ++k) dot += R[3 * a + k] * R[3 * b + k];
                 if (!(std::fabs(dot - (a == b ? 1.0 : 0.0)) < 1e-9)) { err = "parent_rot is not a rotation matrix"; return RB_ERR_ARG; }
             }
-        for (int e = 0; e < 9; ++e) r.R[e] = snap(R[e]);
-        for (int e = 0; e < 3; ++e) r.t[e] = d->parent_trans[3 * i + e];
-        r.m = d->mass[i];
-        if (!(r.m > 0.0) || !std::isfinite(r.m)) { err = "link mass must be positive and finite"; return RB_ERR_ARG; }
-        for (int e = 0; e < 3; ++e) r.h[e] = r.m * d->com[3 * i + e];
-        origin_inertia(r.m, d->com + 3 * i, d->inertia_com + 9 * i, r.I);
-        out.jt.push_back(r);
+        memcpy(r.R, R, sizeof r.R);
+        memcpy(r.t, d->parent_trans + 3 * i, sizeof r.t);
+        r.mass = d->mass[i];
+        if (!(r.mass > 0.0) || !std::isfinite(r.mass)) { err = "link mass must be positive and finite"; return RB_ERR_ARG; }
+        memcpy(r.com, d->com + 3 * i, sizeof r.com);
+        memcpy(r.Ic, d->inertia_com + 9 * i, sizeof r.Ic);
+        raw.push_back(r);
         out.lim.lower[i] = -3.141592653589793; out.lim.upper[i] = 3.141592653589793;
         out.lim.velocity[i] = 2.0; out.lim.effort[i] = 50.0;
         out.names.push_back("joint" + std::to_string(i + 1));
@@ -290,15 +359,15 @@ int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err)
         if (!std::isfinite(d->gravity[k])) { err = "gravity must be finite"; return RB_ERR_ARG; }
         out.g[k] = d->gravity[k];
     }
-    finish_model(out);
-    return RB_OK;
+    return build_model(raw, out, err);
 }
 
 std::vector<double> rb_model_flat(const RbHostModel& m) {
-    std::vector<double> v((size_t)m.n * 24 + 3);
+    std::vector<double> v((size_t)RB_MODEL_DOUBLES(m.n));
     static_assert(sizeof(RbJointK) == 24 * sizeof(double), "RbJointK must be 24 doubles");
     memcpy(v.data(), m.jt.data(), (size_t)m.n * sizeof(RbJointK));
     for (int k = 0; k < 3; ++k) v[(size_t)m.n * 24 + k] = m.g[k];
+    for (int k = 0; k < 9; ++k) v[(size_t)m.n * 24 + 3 + k] = m.tip[k];
     return v;
 }
 
@@ -319,6 +388,8 @@ std::string rb_model_emit_header(const RbHostModel& m, const char* tab_name) {
     }
     o += "    };\n";
     snprintf(buf, sizeof buf, "    static constexpr double G[3] = {%a, %a, %a};\n", m.g[0], m.g[1], m.g[2]); o += buf;
+    o += "    static constexpr double TIP[9] = {";
+    for (int k = 0; k < 9; ++k) { snprintf(buf, sizeof buf, "%a%s", m.tip[k], k == 8 ? "};\n" : ", "); o += buf; }
     o += "};\n";
     return o;
 }

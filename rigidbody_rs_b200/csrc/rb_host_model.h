@@ -14,6 +14,7 @@ struct RbHostModel {
     int n = 0;
     std::vector<RbJointK> jt;
     double g[3] = {0.0, 0.0, 9.81};          // multibody.rs:118
+    double tip[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     RbJointLimits lim{};
     std::vector<std::string> names;
 };
@@ -26,5 +27,5 @@ int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err)
 // the compile-time table CtModel<> specialises the kernels on.
 std::string rb_model_emit_header(const RbHostModel& m, const char* tab_name);
 
-// Flattens the model into the layout of RbModelK<n> (n rows of 24 doubles then g[3]).
+// Flattens the model into the layout of RbModelK<n> (n rows of 24 doubles, then g[3] and tip[9]).
 std::vector<double> rb_model_flat(const RbHostModel& m);

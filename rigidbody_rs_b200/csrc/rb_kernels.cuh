@@ -80,7 +80,7 @@ const double* rb_chain32_table();
 
 // Parameter block of the run-time-n family (rb_kernels_n.cu); rb_api.cu fills it when a chain is uploaded.
 struct RbNParam {
-    const double* model;     // device: n rows of 24 doubles + g[3]
+    const double* model;     // device: n rows of 24 doubles + g[3] + tip[9]
     int n;
     double* scratch;         // per-thread strided scratch: `slots` doubles per thread, element k at scratch[k*threads + tid]
     size_t threads;          // threads the scratch was sized for (persistent grid * block)

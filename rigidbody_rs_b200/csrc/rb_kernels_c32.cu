@@ -10,12 +10,13 @@ const RbOps* rb_ops_chain32() {
 }
 
 const double* rb_chain32_table() {
-    static double flat[32 * 24 + 3];
+    static double flat[RB_MODEL_DOUBLES(32)];
     static bool init = false;
     if (!init) {
         for (int i = 0; i < 32; ++i)
             for (int k = 0; k < 24; ++k) flat[i * 24 + k] = TabChain32::T[i][k];
         for (int k = 0; k < 3; ++k) flat[32 * 24 + k] = TabChain32::G[k];
+        for (int k = 0; k < 9; ++k) flat[32 * 24 + 3 + k] = TabChain32::TIP[k];
         init = true;
     }
     return flat;

@@ -201,7 +201,8 @@ rbn_fk_jac_kernel(RbNParam P, const double* __restrict__ q, double* __restrict__
     const int n = P.n;
     const RbJointK* jt = reinterpret_cast<const RbJointK*>(P.model);
     for (size_t s = tid; s < B; s += nthr) {
-        double A[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}};
+        const double* tip = P.model + (size_t)n * 24 + 3;
+        double A[3][3] = {{tip[0], tip[1], tip[2]}, {tip[3], tip[4], tip[5]}, {tip[6], tip[7], tip[8]}};
         double r[3] = {0.0, 0.0, 0.0};
         for (int i = n - 1; i >= 0; --i) {
             const RbJointK& j = jt[i];

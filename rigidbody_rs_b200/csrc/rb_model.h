@@ -23,7 +23,12 @@ template <int N>
 struct RbModelK {
     RbJointK jt[N];
     double g[3];   // base linear acceleration (reference: 0,0,+9.81; multibody.rs:118)
+    double tip[9]; // row-major orientation of the reference's last link frame in the model's last frame: identity
+                   // unless the last joint axis had to be re-based onto z (rb_host_model.cpp); read by jac only
 };
+
+#define RB_MODEL_TAIL 12                                   // doubles after the joint rows: g[3] + tip[9]
+#define RB_MODEL_DOUBLES(n) ((n) * 24 + RB_MODEL_TAIL)
 
 // Entry-class tags used by compile-time-specialised models to drop multiplications by 0 and +-1.
 enum : int { RB_GEN = 0, RB_ZERO = 1, RB_ONE = 2, RB_NEG1 = 3 };

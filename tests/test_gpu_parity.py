@@ -314,6 +314,39 @@ def test_jit_random_chains_match_matrix_oracle(rb, n, seed):
     assert np.abs(J - ch.jac(q[:64])).max() < TOL
 
 
+@pytest.mark.parametrize("n", [7, 4])
+def test_general_joint_axes_all_families(rb, n):
+    """Joint axes other than +z (x, y, -z, unnormalised, oblique): the loader re-bases the frames, every kernel family
+    stays z-only.  Checked against the twin's direct S = (axis; 0) formulation, tip-frame Jacobian included."""
+    from test_host import _random_chain, AXES
+    from oracle.rb_oracle_np import ChainNP
+    R, t, m, c, Ic = _random_chain(n, 40 + n)
+    ax = AXES[:n]
+    ch = ChainNP.from_arrays(R, t, m, c, Ic, axis=ax)
+    rng = np.random.default_rng(n)
+    B = 1500
+    q, dq, ddq, tau = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n)), rng.uniform(-20, 20, (B, n))
+    want = ch.rnea(q, dq, ddq), ch.forward_dynamics(q, dq, tau), ch.crba(q[:64]), ch.fwd_kin(q[:64])[1], ch.jac(q[:64])
+    seen = []
+    for v in ("auto", "generic-7", "generic-n"):
+        os.environ["RIGIDBODY_B200_VARIANT"] = v
+        try:
+            mb = rb.Multibody.from_descriptor(R, t, m, c, Ic, axis=ax)
+        except rb.RigidBodyError:
+            continue
+        finally:
+            os.environ.pop("RIGIDBODY_B200_VARIANT", None)
+        seen.append(mb.kernel_variant)
+        assert state_err(mb.rnea(q, dq, ddq, layout="aos"), want[0], 1).max() < TOL, mb.kernel_variant
+        assert state_err(mb.forward_dynamics(q, dq, tau, layout="aos"), want[1], 1).max() < 1e-8, mb.kernel_variant
+        H = mb.crba(q[:64], layout="aos").reshape(64, n, n).transpose(0, 2, 1)
+        assert np.abs(H - want[2]).max() < TOL, mb.kernel_variant
+        assert np.abs(mb.fwd_kin(q[:64], layout="aos") - want[3]).max() < TOL, mb.kernel_variant
+        J = mb.jac(q[:64], layout="aos").reshape(64, n, 6).transpose(0, 2, 1)
+        assert np.abs(J - want[4]).max() < TOL, mb.kernel_variant
+    assert seen == (["jit-specialised", "generic-7", "generic-n"] if n == 7 else ["jit-specialised", "generic-n"])
+
+
 def test_fp32_mode_tolerances(rb, oracle_fr3):
     """Optional fp32 mode (include/rigidbody.h): float kernels against the fp64 oracle on the same (float-rounded)
     inputs.  Stated tolerance (BASELINE.json north_star), per state max_i|x_i - ref_i| <= 1e-4 * max(1, ||ref||_inf)."""

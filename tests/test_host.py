@@ -85,8 +85,13 @@ def test_urdf_errors_are_statuses_not_crashes(rb, tmp_path):
     yaxis.write_text("<robot name='r'><link name='a'><inertial><origin xyz='0 0 0'/><mass value='1'/>"
                      "<inertia ixx='1' ixy='0' ixz='0' iyy='1' iyz='0' izz='1'/></inertial></link>"
                      "<joint name='j' type='revolute'><origin xyz='0 0 0' rpy='0 0 0'/><axis xyz='0 1 0'/></joint></robot>")
-    assert not lib.multibody_new_from_urdf(str(yaxis).encode())
-    assert b"only +z" in lib.multibody_last_error()
+    mb = lib.multibody_new_from_urdf(str(yaxis).encode())          # non-z axes load (re-based to z on the host)
+    assert mb and lib.multibody_n_joints(mb) == 1
+    lib.multibody_free(mb)
+    zero = tmp_path / "zero.urdf"
+    zero.write_text(yaxis.read_text().replace("0 1 0", "0 0 0"))
+    assert not lib.multibody_new_from_urdf(str(zero).encode())
+    assert b"non-zero" in lib.multibody_last_error()
     lib.multibody_free(None)            # null-safe like the reference (lib.rs:73-78)
     lib.multibody_free_result(None)
 
@@ -168,6 +173,77 @@ def _random_chain(n, seed):
     A = rng.uniform(-1, 1, (n, 3, 3))
     Ic = np.einsum("nij,nkj->nik", A, A) * 0.01 + np.eye(3) * 0.01
     return R, t, m, c, Ic
+
+
+AXES = [[1, 0, 0], [0, 1, 0], [0, 0, -1], [0, 0, 2], [1, 1, 0], [0.3, -0.5, 0.8], [-0.2, 0.1, -0.97]]
+
+
+def _axis_urdf(path, R_rpy, t, m, c, Ic, axes):
+    """Writes a serial-chain URDF with the given joint axes (k-th joint pairs with k-th link, multibody.rs:70)."""
+    f = lambda v: " ".join(repr(float(x)) for x in v)
+    out = ["<robot name='axes'>"]
+    for i in range(len(m)):
+        out.append(f"<link name='l{i}'><inertial><origin xyz='{f(c[i])}' rpy='0 0 0'/><mass value='{float(m[i])!r}'/>"
+                   f"<inertia ixx='{float(Ic[i][0][0])!r}' ixy='{float(Ic[i][0][1])!r}' ixz='{float(Ic[i][0][2])!r}' iyy='{float(Ic[i][1][1])!r}' "
+                   f"iyz='{float(Ic[i][1][2])!r}' izz='{float(Ic[i][2][2])!r}'/></inertial></link>")
+    for i in range(len(m)):
+        out.append(f"<joint name='j{i}' type='revolute'><origin xyz='{f(t[i])}' rpy='{f(R_rpy[i])}'/>"
+                   f"<axis xyz='{f(axes[i])}'/><limit lower='-2' upper='2' velocity='2' effort='50'/></joint>")
+    out.append("</robot>")
+    path.write_text("\n".join(out))
+    return str(path)
+
+
+def test_twin_with_general_axes_is_self_consistent():
+    """The numpy twin's S = (axis; 0) generalisation, checked against physics it does not assume: gravity torque =
+    dU/dq (central differences), H = d tau / d ddq, H SPD, and for +z axes it is the old z-only code path."""
+    R, t, m, c, Ic = _random_chain(7, 5)
+    ch = ChainNP.from_arrays(R, t, m, c, Ic, axis=AXES)
+    rng = np.random.default_rng(0)
+    q, dq, ddq = rng.uniform(-2, 2, (3, 6, 7))
+    g = ch.rnea(q, 0 * q, 0 * q)
+    eps = 1e-6
+    for j in range(7):
+        e = np.zeros(7); e[j] = eps
+        dU = (ch.potential_energy(q + e) - ch.potential_energy(q - e)) / (2 * eps)
+        np.testing.assert_allclose(g[:, j], dU, rtol=0, atol=2e-8)
+    H = ch.crba(q, symmetric=True)
+    assert np.all(np.linalg.eigvalsh(H) > 0)
+    np.testing.assert_allclose(ch.rnea(q, dq, ddq) - ch.rnea(q, dq, 0 * q), np.einsum("bij,bj->bi", H, ddq), rtol=0, atol=1e-12)
+    # Coriolis terms: power balance  d/dt (1/2 dq^T H dq) = dq . (tau - g)  along ddq = 0  =>  dq^T Hdot dq / 2 = dq . c
+    cor = ch.rnea(q, dq, 0 * q) - g
+    h = 1e-6
+    Hd = (ch.crba(q + h * dq, symmetric=True) - ch.crba(q - h * dq, symmetric=True)) / (2 * h)
+    np.testing.assert_allclose(np.einsum("bi,bi->b", dq, cor), 0.5 * np.einsum("bi,bij,bj->b", dq, Hd, dq), rtol=0, atol=5e-8)
+
+
+def test_axis_rebasing_on_the_host(rb, tmp_path):
+    """csrc/rb_host_model.cpp turns non-z axes into z by re-basing the joint frames.  The re-based rows, run through
+    the twin's z-only formulation, must give the tau / H / tip position of the chain with its axes as written."""
+    from rigidbody_rs_b200 import _lib
+    from scipy.spatial.transform import Rotation
+    n = 7
+    R, t, m, c, Ic = _random_chain(n, 21)
+    rpy = Rotation.from_matrix(R).as_euler("xyz")                  # Rz(y) Ry(p) Rx(r), joint.rs:59-63
+    path = _axis_urdf(tmp_path / "axes.urdf", rpy, t, m, c, Ic, AXES)
+    n2, Rk, tk, mk, hk, Ik = _host_model(_lib.lib, path)
+    assert n2 == n
+    canon = ChainNP.__new__(ChainNP)
+    canon.n, canon.Rp, canon.tp, canon.m, canon.h = n, Rk, tk, mk, hk
+    canon.Io = np.stack([[[a[0], a[1], a[2]], [a[1], a[3], a[4]], [a[2], a[4], a[5]]] for a in Ik])
+    canon.axis = np.tile(np.array([0.0, 0.0, 1.0]), (n, 1))
+    direct = ChainNP.from_arrays(Rotation.from_euler("xyz", rpy).as_matrix(), t, m, c, Ic, axis=AXES)
+    rng = np.random.default_rng(2)
+    q, dq, ddq = rng.uniform(-2.5, 2.5, (3, 16, n))
+    np.testing.assert_allclose(canon.rnea(q, dq, ddq), direct.rnea(q, dq, ddq), rtol=0, atol=2e-12)
+    np.testing.assert_allclose(canon.crba(q), direct.crba(q), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(canon.fwd_kin(q)[1], direct.fwd_kin(q)[1], rtol=0, atol=1e-13)
+    # +z joints keep their frame exactly when the previous joint did too (joint 3: axis (0,0,2) after (0,0,-1) does not)
+    zz = ChainNP.from_arrays(R, t, m, c, Ic)
+    path = _axis_urdf(tmp_path / "z.urdf", rpy, t, m, c, Ic, [[0, 0, 1]] * n)
+    _, Rz_, tz_, *_ = _host_model(_lib.lib, path)
+    np.testing.assert_allclose(Rz_, zz.Rp, rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(tz_, t)
 
 
 def test_jit_precompile_without_gpu(rb, tmp_path, monkeypatch):
