@@ -13,6 +13,11 @@
 #include "rb_kernels.cuh"
 #include "rb_util.cuh"
 
+// 1 = forward dynamics through rb_fd_prepare_kernel + the tile solver; 0 (default) = leave it to the run-time-n
+// family's warp-per-state kernel (rb_kernels_warp.cu), which keeps H on the SM.
+#ifndef RB_LONG_FD
+#define RB_LONG_FD 0
+#endif
 #ifndef RB_MINB_LONG
 #define RB_MINB_LONG 2
 #endif
@@ -119,7 +124,7 @@ struct RbLaunchLong {
     static RbOps ops(const char* name) {
         RbOps o;
         o.name = name; o.n = M::N; o.param_bytes = sizeof(LP); o.shared_scratch = true;      // the H chunk buffer
-        o.rnea = &rnea; o.fd = &fd; o.rnea_aos = nullptr; o.fd_aos = nullptr; o.crba = &crba; o.fwd_kin = nullptr; o.jac = nullptr; o.rollout = nullptr;
+        o.rnea = &rnea; o.fd = RB_LONG_FD ? &fd : nullptr; o.rnea_aos = nullptr; o.fd_aos = nullptr; o.crba = &crba; o.fwd_kin = nullptr; o.jac = nullptr; o.rollout = nullptr;
         o.rnea_f32 = nullptr; o.fd_f32 = nullptr;
         return o;
     }

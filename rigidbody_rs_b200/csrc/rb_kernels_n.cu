@@ -451,6 +451,10 @@ cudaError_t rb_launch_ldlt_tiles(int n, const double* hpk, size_t hpk_states, do
 namespace {
 cudaError_t n_fd(const void* param, const double* q, const double* dq, const double* tau, double* qdd, size_t B, size_t ld, int* status, cudaStream_t st) {
     const RbNParam* P = (const RbNParam*)param;
+#if RB_WARP_FD
+    if (P->n <= 32)                                                  // warp-per-state, nothing leaves the SM (rb_kernels_warp.cu)
+        return rb_launch_warp_fd(P->model, P->n, q, dq, tau, qdd, B, ld, status, st);
+#endif
     for (size_t off = 0; off < B; off += P->hpk_states) {
         const size_t cnt = (B - off < P->hpk_states) ? (B - off) : P->hpk_states;
         rbn_fd_prepare_kernel<<<ngrid(P, cnt), RB_BLOCK, 0, st>>>(*P, q + off, dq + off, tau + off, qdd + off, cnt, ld);

@@ -16,3 +16,10 @@ cudaError_t rb_launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t
 // Batched LDL^T solve in shared-memory tiles (rb_kernels_n.cu): H packed upper [n(n+1)/2][hpk_states], rhs/x in qdd.
 cudaError_t rb_launch_ldlt_tiles(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld,
                                  int* status, cudaStream_t st);
+// Forward dynamics of a chain of n <= 32 joints, one warp per state / one lane per joint (rb_kernels_warp.cu);
+// `model` = device rows in the rb_model.h layout (n x 24 doubles, then g[3]).
+cudaError_t rb_launch_warp_fd(const double* model, int n, const double* q, const double* dq, const double* tau,
+                              double* qdd, size_t B, size_t ld, int* status, cudaStream_t st);
+#ifndef RB_WARP_FD
+#define RB_WARP_FD 1
+#endif
