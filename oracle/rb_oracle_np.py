@@ -61,14 +61,18 @@ class ChainNP:
             Io.append(Ic + self.m[i] * C @ C.T)                                   # inertia.rs:31-32
         self.Io = np.stack(Io)
         self.axis = np.tile(np.array([0.0, 0.0, 1.0]), (n, 1))      # the dynamics' axis (multibody.rs:29,130)
+        self.parent = np.arange(n) - 1                               # serial chain (multibody.rs:148,165)
 
     @classmethod
-    def from_arrays(cls, Rp, tp, mass, com, inertia_com, axis=None):
+    def from_arrays(cls, Rp, tp, mass, com, inertia_com, axis=None, parent=None):
         """Chain given directly by its flattened descriptor (what RbChainDesc carries).  `axis` [n,3]: joint axes in
         the joint frames, used CONSISTENTLY by kinematics and dynamics (the reference uses them in the kinematics
-        only, joint.rs:48-50 vs multibody.rs:130; for +z the two agree)."""
+        only, joint.rs:48-50 vs multibody.rs:130; for +z the two agree).  `parent` [n]: parent link of each joint,
+        -1 = base, parent[i] < i (kinematic tree; the reference is the serial case parent[i] = i-1).  The tip of
+        fwd_kin / jac is the last link."""
         self = cls.__new__(cls)
         self.n = len(mass)
+        self.parent = np.arange(self.n) - 1 if parent is None else np.array(parent, dtype=int)
         ax = np.tile(np.array([0.0, 0.0, 1.0]), (self.n, 1)) if axis is None else np.array(axis, dtype=np.float64)
         self.axis = ax / np.linalg.norm(ax, axis=1, keepdims=True)
         self.Rp = np.array(Rp, dtype=np.float64); self.tp = np.array(tp, dtype=np.float64)
@@ -97,11 +101,11 @@ class ChainNP:
         q, dq, ddq = (np.atleast_2d(np.asarray(x, dtype=np.float64)) for x in (q, dq, ddq))
         B, n = q.shape
         R = [self._R(i, q[:, i]) for i in range(n)]
-        v_lin = np.zeros((B, 3)); v_rot = np.zeros((B, 3))
-        a_lin = np.zeros((B, 3)); a_lin[:, 2] = GRAVITY
-        a_rot = np.zeros((B, 3))
+        base = (np.zeros((B, 3)), np.zeros((B, 3)), np.tile(np.array([0.0, 0.0, GRAVITY]), (B, 1)), np.zeros((B, 3)))
+        state = []
         f_lin, f_rot = [], []
         for i in range(n):
+            v_lin, v_rot, a_lin, a_rot = state[self.parent[i]] if self.parent[i] >= 0 else base
             Rt = np.swapaxes(R[i], 1, 2)
             t = self.tp[i]
             v_lin = np.einsum("bij,bj->bi", Rt, v_lin - np.cross(t, v_rot))
@@ -114,6 +118,7 @@ class ChainNP:
             # v x (S dq), S = (axis; 0):  lin += v_lin x axis dq,  rot += v_rot x axis dq
             a_lin = a_lin + np.cross(v_lin, ax) * dq[:, i:i + 1]
             a_rot = a_rot + np.cross(v_rot, ax) * dq[:, i:i + 1]
+            state.append((v_lin, v_rot, a_lin, a_rot))
             Ia_l, Ia_r = self._Imul(i, a_lin, a_rot)
             Iv_l, Iv_r = self._Imul(i, v_lin, v_rot)
             f_lin.append(Ia_l + np.cross(v_rot, Iv_l))
@@ -121,10 +126,11 @@ class ChainNP:
         tau = np.zeros((B, n))
         for i in range(n - 1, -1, -1):
             tau[:, i] = f_rot[i] @ self.axis[i]
-            if i > 0:
+            p = self.parent[i]
+            if p >= 0:
                 Rl = np.einsum("bij,bj->bi", R[i], f_lin[i])
-                f_lin[i - 1] = f_lin[i - 1] + Rl
-                f_rot[i - 1] = f_rot[i - 1] + np.einsum("bij,bj->bi", R[i], f_rot[i]) + np.cross(self.tp[i], Rl)
+                f_lin[p] = f_lin[p] + Rl
+                f_rot[p] = f_rot[p] + np.einsum("bij,bj->bi", R[i], f_rot[i]) + np.cross(self.tp[i], Rl)
         return tau
 
     def crba(self, q, symmetric=False):
@@ -133,30 +139,35 @@ class ChainNP:
         B, n = q.shape
         R = [self._R(i, q[:, i]) for i in range(n)]
         H = np.zeros((B, n, n))
-        m = np.full(B, self.m[n - 1]); h = np.tile(self.h[n - 1], (B, 1)); Io = np.tile(self.Io[n - 1], (B, 1, 1))
+        m = [np.full(B, self.m[i]) for i in range(n)]
+        h = [np.tile(self.h[i], (B, 1)) for i in range(n)]
+        Io = [np.tile(self.Io[i], (B, 1, 1)) for i in range(n)]
         for i in range(n - 1, -1, -1):
             ax = self.axis[i]
-            F_lin = -np.cross(h, ax)                            # I * S,  S = (axis; 0)
-            F_rot = Io @ ax
+            F_lin = -np.cross(h[i], ax)                         # I * S,  S = (axis; 0)
+            F_rot = Io[i] @ ax
             H[:, i, i] = F_rot @ ax
-            for j in range(i - 1, -1, -1):
-                Rl = np.einsum("bij,bj->bi", R[j + 1], F_lin)
-                F_rot = np.einsum("bij,bj->bi", R[j + 1], F_rot) + np.cross(self.tp[j + 1], Rl)
+            j = i
+            while self.parent[j] >= 0:                          # up the supporting branch only (zeros elsewhere)
+                Rl = np.einsum("bij,bj->bi", R[j], F_lin)
+                F_rot = np.einsum("bij,bj->bi", R[j], F_rot) + np.cross(self.tp[j], Rl)
                 F_lin = Rl
+                j = self.parent[j]
                 H[:, j, i] = F_rot @ self.axis[j]
-            if i > 0:
+            p = self.parent[i]
+            if p >= 0:
                 # composite inertia into the parent frame, 10-parameter form:
                 # h' = R h + m t ;  I_o' = R I_o R^T - [t]x[Rh]x - [Rh]x[t]x - m [t]x[t]x
                 t = self.tp[i]
-                Rh = np.einsum("bij,bj->bi", R[i], h)
-                RIR = R[i] @ Io @ np.swapaxes(R[i], 1, 2)
+                Rh = np.einsum("bij,bj->bi", R[i], h[i])
+                RIR = R[i] @ Io[i] @ np.swapaxes(R[i], 1, 2)
                 T = _skew(t)
                 S = np.zeros((B, 3, 3))
                 S[:, 0, 1] = -Rh[:, 2]; S[:, 0, 2] = Rh[:, 1]; S[:, 1, 0] = Rh[:, 2]
                 S[:, 1, 2] = -Rh[:, 0]; S[:, 2, 0] = -Rh[:, 1]; S[:, 2, 1] = Rh[:, 0]
-                Io = RIR - T @ S - S @ T - m[:, None, None] * (T @ T) + self.Io[i - 1]
-                h = Rh + m[:, None] * t + self.h[i - 1]
-                m = m + self.m[i - 1]
+                Io[p] = Io[p] + RIR - T @ S - S @ T - m[i][:, None, None] * (T @ T)
+                h[p] = h[p] + Rh + m[i][:, None] * t
+                m[p] = m[p] + m[i]
         if symmetric:
             iu = np.triu_indices(n, 1)
             H[:, iu[1], iu[0]] = H[:, iu[0], iu[1]]
@@ -179,10 +190,12 @@ class ChainNP:
         q = np.atleast_2d(np.asarray(q, dtype=np.float64))
         B, n = q.shape
         Racc = np.tile(np.eye(3), (B, 1, 1)); p = np.zeros((B, 3))
-        for i in range(n - 1, -1, -1):
+        i = n - 1
+        while i >= 0:                                           # tip = last link; walk its supporting branch
             Ri = self._R(i, q[:, i])
             p = np.einsum("bij,bj->bi", Ri, p) + self.tp[i]
             Racc = Ri @ Racc
+            i = self.parent[i]
         return Racc, p
 
     def jac(self, q):
@@ -191,7 +204,8 @@ class ChainNP:
         B, n = q.shape
         J = np.zeros((B, 6, n))
         Racc = np.tile(np.eye(3), (B, 1, 1)); p = np.zeros((B, 3))   # pose of tip in frame i
-        for i in range(n - 1, -1, -1):
+        i = n - 1
+        while i >= 0:                                           # joints off the tip's branch keep zero columns
             Rt = np.swapaxes(Racc, 1, 2)
             z = self.axis[i]
             J[:, 0:3, i] = np.einsum("bij,bj->bi", Rt, -np.cross(p, z))
@@ -199,6 +213,7 @@ class ChainNP:
             Ri = self._R(i, q[:, i])
             p = np.einsum("bij,bj->bi", Ri, p) + self.tp[i]
             Racc = Ri @ Racc
+            i = self.parent[i]
         return J
 
     def potential_energy(self, q):
@@ -206,11 +221,13 @@ class ChainNP:
         q = np.atleast_2d(np.asarray(q, dtype=np.float64))
         B, n = q.shape
         U = np.zeros(B)
-        Racc = np.tile(np.eye(3), (B, 1, 1)); p = np.zeros((B, 3))
+        pose = []
         for i in range(n):
+            Racc, p = pose[self.parent[i]] if self.parent[i] >= 0 else (np.tile(np.eye(3), (B, 1, 1)), np.zeros((B, 3)))
             Ri = self._R(i, q[:, i])
             p = p + np.einsum("bij,j->bi", Racc, self.tp[i])
             Racc = Racc @ Ri
+            pose.append((Racc, p))
             com_w = p + np.einsum("bij,j->bi", Racc, self.h[i] / self.m[i])
             U += self.m[i] * GRAVITY * com_w[:, 2]
         return U

@@ -134,6 +134,15 @@ int setup_generic_n(RbGpu* g, const std::vector<double>& flat, const RbOps** ops
     const size_t slots = (size_t)12 * n + (size_t)n * n;
     int rc = g->scratch.ensure(slots * g->scratch_threads * sizeof(double));
     if (rc != RB_OK) return rc;
+    if (n > 32) {
+        // forward dynamics of chains beyond a warp's width: H (packed upper triangle) of one chunk of states lives in
+        // HBM between the kernel that builds it and the tile kernel that factorises it in shared memory (<= 1 GiB)
+        const size_t np = (size_t)n * (n + 1) / 2;
+        const size_t chunk = ((size_t)1024 << 20) / (np * sizeof(double));
+        g->hpk_states = std::max<size_t>(1024, chunk / 1024 * 1024);
+        rc = g->hpk.ensure(np * g->hpk_states * sizeof(double));
+        if (rc != RB_OK) return rc;
+    }
     RbNParam P{g->d_model, n, g->scratch.p, g->scratch_threads, slots, g->hpk.p, g->hpk_states};
     param->assign(sizeof(P), 0);
     if ((*ops)->param_bytes != sizeof(P)) return fail(RB_ERR_ARG, "internal: RbNParam size mismatch");
@@ -185,19 +194,9 @@ int pick_ops(RbGpu* g) {
     if (want == "generic-7") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=generic-7 needs a 7-joint chain");
     if (want != "auto" && want != "generic-n" && want != "chain32-specialised" && want != "jit-specialised")
         return fail(RB_ERR_ARG, "unknown RIGIDBODY_B200_VARIANT '" + want + "'");
-    // forward dynamics of long chains: H (packed upper triangle) of one chunk of states lives in HBM between the
-    // kernel that builds it and the tile kernel that factorises it in shared memory (<= 1 GiB per chunk)
-    const size_t np = (size_t)n * (n + 1) / 2;
-    size_t chunk = ((size_t)1024 << 20) / (np * sizeof(double));
-    g->hpk_states = std::max<size_t>(1024, chunk / 1024 * 1024);
-    int rc = g->hpk.ensure(np * g->hpk_states * sizeof(double));
-    if (rc != RB_OK) return rc;
     if ((want == "auto" || want == "chain32-specialised") && is_c32) {
         g->ops = rb_ops_chain32();
-        struct { RbEmptyParam model; double* hpk; size_t hpk_states; } LP{{0}, g->hpk.p, g->hpk_states};
-        if (g->ops->param_bytes != sizeof(LP)) return fail(RB_ERR_ARG, "internal: RbLongParam size mismatch");
-        g->param.assign(sizeof(LP), 0);
-        memcpy(g->param.data(), &LP, sizeof(LP));
+        g->param.assign(g->ops->param_bytes, 0);
         return setup_generic_n(g, flat, &g->ops2, &g->param2);
     }
     if (want == "chain32-specialised") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=chain32-specialised but the chain is not the compiled-in 32-joint model");

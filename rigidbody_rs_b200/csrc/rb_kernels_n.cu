@@ -76,9 +76,6 @@ rbn_fd_prepare_kernel(RbNParam P, const double* __restrict__ q, const double* __
 #ifndef RB_TILE_WARPS
 #define RB_TILE_WARPS 8
 #endif
-#ifndef RB_WARP_SOLVER
-#define RB_WARP_SOLVER 1      // n == 32: warp-per-state register-resident solver instead of the shared-memory tiles
-#endif
 template <int TS>
 __global__ void __launch_bounds__(32 * RB_TILE_WARPS)
 rbn_ldlt_tile_kernel(int n, const double* __restrict__ hpk, size_t hpk_states, double* __restrict__ qdd, size_t B, size_t ld,
@@ -318,87 +315,6 @@ cudaError_t n_rnea(const void* param, const double* q, const double* dq, const d
     rbn_rnea_kernel<<<ngrid(P, B), RB_BLOCK, 0, st>>>(*P, q, dq, ddq, tau, B, ld);
     return cudaGetLastError();
 }
-// ---- register-resident solver for chains of exactly N <= 32 joints ----------------------------------------------
-// A block stages one tile of 32 states in shared memory with cp.async (coalesced: the prepare kernels write H
-// state-minor), then each WARP takes states of the tile with lane r = row r: the lane pulls its full symmetric
-// row out of shared memory (row stride 33 doubles: lanes hit different banks) into registers and the elimination
-// runs on registers alone.  Right-looking: at step k the pivot row travels from lane k to every lane by shuffles,
-// lane r > k scales it with its own S(r, k) / d_k and updates its row; the rhs rides along as column N; the back
-// substitution broadcasts one solved entry per column.  ~N^2/2 FMAs + ~N^2 shuffles per state, no barriers
-// inside a state.  (Reading the rows straight from global memory instead ran at 0.097 G states/s: 32 cache lines
-// per load instruction.)
-#ifndef RB_WS_WARPS
-#define RB_WS_WARPS 16
-#endif
-template <int N>
-__global__ void __launch_bounds__(32 * RB_WS_WARPS, 1)
-rbn_ldlt_warp_kernel(const double* __restrict__ hpk, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
-    constexpr int NP = N * (N + 1) / 2, LDT = 33;
-    constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ double rb_tile[];
-    double* T = rb_tile;                                     // [NP][LDT]  packed upper triangle, state-minor
-    double* R = rb_tile + (size_t)NP * LDT;                  // [N][LDT]   rhs in, solution out
-    const int r = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int rr = r < N ? r : N - 1;                        // lanes beyond N (N < 32) mirror the last row, never store
-    const size_t tiles = (B + 31) / 32;
-    bool all_ok = true;
-    for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const size_t s = tile * 32 + r;
-        if (s < B) {
-            const double* src = hpk + tile * (size_t)NP * 32 + r;
-            for (int k = w; k < NP; k += RB_WS_WARPS) {
-                const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(T + k * LDT + r);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d32), "l"(src + (size_t)k * 32) : "memory");
-            }
-            for (int i = w; i < N; i += RB_WS_WARPS) {
-                const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(R + i * LDT + r);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d32), "l"(qdd + (size_t)i * ld + s) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        const int in_tile = (int)((B - tile * 32 < 32) ? (B - tile * 32) : 32);
-        for (int st = w; st < in_tile; st += RB_WS_WARPS) {
-            double a[N], b;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const int jj = rr < i ? rr : i, ii = rr < i ? i : rr;
-                a[i] = T[(jj * N - jj * (jj - 1) / 2 + (ii - jj)) * LDT + st];
-            }
-            b = R[rr * LDT + st];
-            bool ok = true;
-            double mydinv = 0.0;
-#pragma unroll
-            for (int k = 0; k < N; ++k) {
-                const double d = __shfl_sync(FULL, a[k], k);
-                ok = ok && (d > 0.0);
-                const double dinv = rb_rcp_pos(d);
-                if (r == k) mydinv = dinv;
-                const double l = r > k ? a[k] * dinv : 0.0;
-#pragma unroll
-                for (int i = k + 1; i < N; ++i) a[i] = fma(-l, __shfl_sync(FULL, a[i], k), a[i]);
-                b = fma(-l, __shfl_sync(FULL, b, k), b);
-            }
-            // lane k now holds row k of D U in a[k..N-1] and (D U x)_k in b
-            double x = 0.0;
-#pragma unroll
-            for (int i = N - 1; i >= 0; --i) {
-                const double xi = __shfl_sync(FULL, b * mydinv, i);
-                if (r == i) x = xi;
-                b = fma(r < i ? -a[i] : 0.0, xi, b);
-            }
-            all_ok = all_ok && ok;
-            if (r < N) R[r * LDT + st] = ok ? x : __longlong_as_double(0x7ff8000000000000LL);
-        }
-        __syncthreads();
-        if (s < B)
-            for (int i = w; i < N; i += RB_WS_WARPS) __stcs(qdd + (size_t)i * ld + s, R[i * LDT + r]);
-        __syncthreads();
-    }
-    if (!all_ok && r == 0) atomicOr(status, RB_STATUS_NOT_SPD);
-}
-
 template <int TS>
 cudaError_t launch_tile(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld, int* status,
                         size_t smem, int dev, int sms, cudaStream_t st) {
@@ -421,23 +337,6 @@ cudaError_t launch_tile(int n, const double* hpk, size_t hpk_states, double* qdd
 cudaError_t rb_launch_ldlt_tiles(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld,
                                  int* status, cudaStream_t st) {
     if (cnt == 0) return cudaSuccess;
-#if RB_WARP_SOLVER
-    if (n == 32) {                                                   // register-resident warp-per-state solver
-        int dev0 = 0, sms0 = 148;
-        cudaGetDevice(&dev0);
-        cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
-        constexpr size_t smem = (size_t)(32 * 33 / 2 + 32) * 33 * sizeof(double);
-        static bool configured[64] = {false};
-        if (dev0 >= 0 && dev0 < 64 && !configured[dev0]) {
-            cudaError_t e = cudaFuncSetAttribute(rbn_ldlt_warp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured[dev0] = true;
-        }
-        const size_t tiles = (cnt + 31) / 32, cap = (size_t)sms0;
-        rbn_ldlt_warp_kernel<32><<<(unsigned)(tiles < cap ? tiles : cap), 32 * RB_WS_WARPS, smem, st>>>(hpk, qdd, cnt, ld, status);
-        return cudaGetLastError();
-    }
-#endif
     const size_t rows = (size_t)n * (n + 1) / 2 + 4 * (size_t)n;      // S (with the rhs column) + M0 + M1 + DI
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -314,6 +314,33 @@ def test_jit_random_chains_match_matrix_oracle(rb, n, seed):
     assert np.abs(J - ch.jac(q[:64])).max() < TOL
 
 
+@pytest.mark.parametrize("n,seed", [(13, 1), (24, 2), (32, 3), (33, 4), (64, 5)])
+def test_long_random_chains(rb, n, seed):
+    """Chains beyond the register-resident limit: run-time-n kernels; forward dynamics by the warp-per-state kernel
+    up to 32 joints (idle lanes padded) and by the shared-memory tile solver beyond."""
+    from test_host import _random_chain
+    from oracle.rb_oracle_np import ChainNP
+    R, t, m, c, Ic = _random_chain(n, seed)
+    t = t * (8.0 / n)                                    # keep the reach (and cond(H)) comparable across lengths
+    mb = rb.Multibody.from_descriptor(R, t, m, c, Ic)
+    assert mb.kernel_variant == "generic-n"
+    ch = ChainNP.from_arrays(R, t, m, c, Ic)
+    rng = np.random.default_rng(seed)
+    B = 333
+    q, dq, ddq = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n))
+    tau = ch.rnea(q, dq, ddq)
+    assert state_err(mb.rnea(q, dq, ddq, layout="aos"), tau, 1).max() < TOL
+    assert state_err(mb.forward_dynamics(q, dq, tau, layout="aos"), ddq, 1).max() < 1e-7      # round trip, cond(H) ~ 1e5
+    qs, dqs = np.ascontiguousarray(q.T), np.ascontiguousarray(dq.T)
+    got = mb.forward_dynamics(qs, dqs, np.ascontiguousarray(tau.T))                            # SoA, ragged tail of a group
+    assert state_err(got, ddq.T, 0).max() < 1e-7
+    H = mb.crba(q[:32], layout="aos").reshape(32, n, n).transpose(0, 2, 1)
+    assert np.abs(H - ch.crba(q[:32])).max() < TOL * np.abs(H).max()
+    assert np.abs(mb.fwd_kin(q[:32], layout="aos") - ch.fwd_kin(q[:32])[1]).max() < TOL
+    J = mb.jac(q[:32], layout="aos").reshape(32, n, 6).transpose(0, 2, 1)
+    assert np.abs(J - ch.jac(q[:32])).max() < TOL
+
+
 @pytest.mark.parametrize("n", [7, 4])
 def test_general_joint_axes_all_families(rb, n):
     """Joint axes other than +z (x, y, -z, unnormalised, oblique): the loader re-bases the frames, every kernel family

@@ -232,6 +232,7 @@ def test_axis_rebasing_on_the_host(rb, tmp_path):
     canon.n, canon.Rp, canon.tp, canon.m, canon.h = n, Rk, tk, mk, hk
     canon.Io = np.stack([[[a[0], a[1], a[2]], [a[1], a[3], a[4]], [a[2], a[4], a[5]]] for a in Ik])
     canon.axis = np.tile(np.array([0.0, 0.0, 1.0]), (n, 1))
+    canon.parent = np.arange(n) - 1
     direct = ChainNP.from_arrays(Rotation.from_euler("xyz", rpy).as_matrix(), t, m, c, Ic, axis=AXES)
     rng = np.random.default_rng(2)
     q, dq, ddq = rng.uniform(-2.5, 2.5, (3, 16, n))
