@@ -86,8 +86,11 @@ typedef enum RbMem {
  */
 typedef struct RbChainDesc {
     int32_t n_joints;             /* 1..RB_MAX_JOINTS */
-    const int32_t* parent;        /* [n] parent link index, -1 = base.  NULL = serial chain (i-1).  Only serial
-                                     chains are accepted: the reference is serial-only (multibody.rs:148,165). */
+    const int32_t* parent;        /* [n] parent link index, -1 = base, parent[i] < i (topological order).  NULL = serial
+                                     chain (i-1), the reference's only case (multibody.rs:148,165) and the one the
+                                     specialised kernel families serve; a branching tree runs on the run-time-n family.
+                                     The tip of fwd_kin / jac is the last link; H(j, i) = 0 and the Jacobian column
+                                     of j is 0 where joint j does not support link i / the tip. */
     const double* axis;           /* [3n] joint axes in the joint frames (joint.rs:27), any non-zero vector (normalised
                                      on load, joint.rs:56).  NULL = all +z.  The reference's rnea/crba hard-code z
                                      (multibody.rs:29,130) and agree with its own kinematics only for +z; here a

@@ -131,10 +131,11 @@ int setup_generic_n(RbGpu* g, const std::vector<double>& flat, const RbOps** ops
     RB_CUDA(cudaMemcpy(g->d_model, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
     // persistent grid: 8 blocks of RB_BLOCK threads per SM; scratch sized for the largest user (rollout)
     g->scratch_threads = (size_t)g->sm_count * 8 * RB_BLOCK;
-    const size_t slots = (size_t)12 * n + (size_t)n * n;
+    const bool tree = !g->model.serial;
+    const size_t slots = (size_t)(tree ? 24 : 12) * n + (size_t)n * n;
     int rc = g->scratch.ensure(slots * g->scratch_threads * sizeof(double));
     if (rc != RB_OK) return rc;
-    if (n > 32) {
+    if (n > 32 || tree) {
         // forward dynamics of chains beyond a warp's width: H (packed upper triangle) of one chunk of states lives in
         // HBM between the kernel that builds it and the tile kernel that factorises it in shared memory (<= 1 GiB)
         const size_t np = (size_t)n * (n + 1) / 2;
@@ -143,7 +144,7 @@ int setup_generic_n(RbGpu* g, const std::vector<double>& flat, const RbOps** ops
         rc = g->hpk.ensure(np * g->hpk_states * sizeof(double));
         if (rc != RB_OK) return rc;
     }
-    RbNParam P{g->d_model, n, g->scratch.p, g->scratch_threads, slots, g->hpk.p, g->hpk_states};
+    RbNParam P{g->d_model, n, g->scratch.p, g->scratch_threads, slots, g->hpk.p, g->hpk_states, tree ? 1 : 0};
     param->assign(sizeof(P), 0);
     if ((*ops)->param_bytes != sizeof(P)) return fail(RB_ERR_ARG, "internal: RbNParam size mismatch");
     memcpy(param->data(), &P, sizeof(P));
@@ -157,6 +158,13 @@ int pick_ops(RbGpu* g) {
     const std::string want = force ? force : "auto";
     const int n = g->model.n;
     std::vector<double> flat = rb_model_flat(g->model);
+    if (!g->model.serial) {
+        // kinematic trees (parent[i] != i-1): the run-time-n family only; every other family unrolls a serial chain
+        if (want != "auto" && want != "generic-n")
+            return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=" + want + " serves serial chains only; trees run on generic-n");
+        g->family_note = "kinematic tree: run-time-n kernels (rbn_tree_* recursions)";
+        return setup_generic_n(g, flat, &g->ops, &g->param);
+    }
     const bool is_fr3 = n == 7 && memcmp(flat.data(), rb_fr3_table(), sizeof(double) * RB_MODEL_DOUBLES(7)) == 0;
     const bool is_c32 = n == 32 && memcmp(flat.data(), rb_chain32_table(), sizeof(double) * RB_MODEL_DOUBLES(32)) == 0;
     if ((want == "auto" || want == "fr3-specialised") && is_fr3) {

@@ -1,4 +1,5 @@
-// rb_dyn_n.cuh -- run-time-n variant of rb_dyn.cuh: any serial chain of 1..RB_MAX_N joints.
+// rb_dyn_n.cuh -- run-time-n variant of rb_dyn.cuh: any serial chain of 1..RB_MAX_N joints, and (rbn_tree_*)
+// kinematic trees given by parent indices.
 //
 // Same algebra, same citations, but the joint loop is a real loop and per-link state (f_i, H) lives in a
 // per-thread scratch slice of global memory laid out [slot][thread] so every access is coalesced.
@@ -154,6 +155,134 @@ RB_DI void rbn_crba(const RbJointK* __restrict__ jt, int n, const RbScratch& sc,
             h[0] = fma(J.t[0], J.mc, q0) + Pn.h[0];
             h[1] = fma(J.t[1], J.mc, q1) + Pn.h[1];
             h[2] = fma(J.t[2], J.mc, q2) + Pn.h[2];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ kinematic trees (parent[i] < i, -1 = base)
+// The reference is serial-only (f[i-1], multibody.rs:148; ic[i-1], :170).  With a parent index per joint the same
+// recursions run over a tree: motion comes from the parent link instead of link i-1, wrenches and composite
+// inertias are accumulated into the parent, and H(j, i) is non-zero only when j supports i.
+// Extra scratch: va[12 i + k] = (v.lin, v.rot, a.lin, a.rot) of link i, kept for its children.
+RB_DI void rbn_tree_rnea(const RbJointK* __restrict__ jt, const double* g, int n, const RbScratch& sc, const RbScratch& va,
+                         const double* dq, const double* ddq, size_t ld, const RbScratch& tau) {
+    for (int i = 0; i < n; ++i) {
+        const RbJointK& j = jt[i];
+        const int p = (int)j.parent;
+        double vl[3] = {0.0, 0.0, 0.0}, vr[3] = {0.0, 0.0, 0.0};
+        double al[3] = {g[0], g[1], g[2]}, ar[3] = {0.0, 0.0, 0.0};
+        if (p >= 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                vl[k] = va[12 * p + k]; vr[k] = va[12 * p + 3 + k]; al[k] = va[12 * p + 6 + k]; ar[k] = va[12 * p + 9 + k];
+            }
+        }
+        const double s = sc[i], c = sc[n + i];
+        const double dqi = dq[(size_t)i * ld];
+        rbn_motion(j, s, c, vl, vr);
+        vr[2] += dqi;
+        rbn_motion(j, s, c, al, ar);
+        if (ddq) ar[2] += ddq[(size_t)i * ld];
+        al[0] = fma(vl[1], dqi, al[0]);
+        al[1] = fma(-vl[0], dqi, al[1]);
+        ar[0] = fma(vr[1], dqi, ar[0]);
+        ar[1] = fma(-vr[0], dqi, ar[1]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            va[12 * i + k] = vl[k]; va[12 * i + 3 + k] = vr[k]; va[12 * i + 6 + k] = al[k]; va[12 * i + 9 + k] = ar[k];
+        }
+        double fl[3], fr[3], Il[3], Ir[3];
+        rbn_inertia_mul(j, al, ar, fl, fr);
+        rbn_inertia_mul(j, vl, vr, Il, Ir);
+        fl[0] = fma(vr[1], Il[2], fma(-vr[2], Il[1], fl[0]));
+        fl[1] = fma(vr[2], Il[0], fma(-vr[0], Il[2], fl[1]));
+        fl[2] = fma(vr[0], Il[1], fma(-vr[1], Il[0], fl[2]));
+        fr[0] = fma(vl[1], Il[2], fma(-vl[2], Il[1], fma(vr[1], Ir[2], fma(-vr[2], Ir[1], fr[0]))));
+        fr[1] = fma(vl[2], Il[0], fma(-vl[0], Il[2], fma(vr[2], Ir[0], fma(-vr[0], Ir[2], fr[1]))));
+        fr[2] = fma(vl[0], Il[1], fma(-vl[1], Il[0], fma(vr[0], Ir[1], fma(-vr[1], Ir[0], fr[2]))));
+        const int o = 2 * n + 6 * i;
+        sc[o + 0] = fl[0]; sc[o + 1] = fl[1]; sc[o + 2] = fl[2];
+        sc[o + 3] = fr[0]; sc[o + 4] = fr[1]; sc[o + 5] = fr[2];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        const int o = 2 * n + 6 * i;
+        double fl[3] = {sc[o + 0], sc[o + 1], sc[o + 2]};
+        double fr[3] = {sc[o + 3], sc[o + 4], sc[o + 5]};
+        tau[i] = fr[2];
+        const int p = (int)jt[i].parent;
+        if (p >= 0) {
+            rbn_force(jt[i], sc[i], sc[n + i], fl, fr);
+            const int op = 2 * n + 6 * p;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sc[op + k] += fl[k]; sc[op + 3 + k] += fr[k]; }
+        }
+    }
+}
+
+// ci[9 i + k]: composite (h[3], Ixx Ixy Ixz Iyy Iyz Izz) of the sub-tree rooted at link i; the composite mass is the
+// model constant jt[i].mc.  put(j, i, v) is called for EVERY pair j <= i (zeros where j does not support i).
+template <class Put>
+RB_DI void rbn_tree_crba(const RbJointK* __restrict__ jt, int n, const RbScratch& sc, const RbScratch& ci, Put&& put) {
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ci[9 * i + k] = jt[i].h[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ci[9 * i + 3 + k] = jt[i].I[k];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        const double h[3] = {ci[9 * i], ci[9 * i + 1], ci[9 * i + 2]};
+        const double Ixx = ci[9 * i + 3], Ixy = ci[9 * i + 4], Ixz = ci[9 * i + 5];
+        const double Iyy = ci[9 * i + 6], Iyz = ci[9 * i + 7], Izz = ci[9 * i + 8];
+        put(i, i, Izz);
+        double Fl[3] = {-h[1], h[0], 0.0}, Fr[3] = {Ixz, Iyz, Izz};
+        int cur = i, anc = (int)jt[i].parent;
+        for (int j = i - 1; j >= 0; --j) {
+            if (j == anc) {
+                rbn_force(jt[cur], sc[cur], sc[n + cur], Fl, Fr);
+                put(j, i, Fr[2]);
+                cur = j; anc = (int)jt[j].parent;
+            } else {
+                put(j, i, 0.0);
+            }
+        }
+        const int p = (int)jt[i].parent;
+        if (p >= 0) {
+            const RbJointK& J = jt[i];
+            const double si = sc[i], cs_ = sc[n + i];
+            const double g0 = fma(cs_, h[0], -(si * h[1])), g1 = fma(si, h[0], cs_ * h[1]), g2 = h[2];
+            // A = Rz I Rz^T (full symmetric), then R_p A R_p^T
+            const double A[3][3] = {{fma(cs_, fma(cs_, Ixx, -(si * Ixy)), -(si * fma(cs_, Ixy, -(si * Iyy)))),
+                                     fma(si, fma(cs_, Ixx, -(si * Ixy)), cs_ * fma(cs_, Ixy, -(si * Iyy))),
+                                     fma(cs_, Ixz, -(si * Iyz))},
+                                    {0.0, fma(si, fma(si, Ixx, cs_ * Ixy), cs_ * fma(si, Ixy, cs_ * Iyy)), fma(si, Ixz, cs_ * Iyz)},
+                                    {0.0, 0.0, Izz}};
+            auto As = [&](int r, int k) { return r <= k ? A[r][k] : A[k][r]; };
+            const double q0 = fma(J.R[2], g2, fma(J.R[1], g1, J.R[0] * g0));
+            const double q1 = fma(J.R[5], g2, fma(J.R[4], g1, J.R[3] * g0));
+            const double q2 = fma(J.R[8], g2, fma(J.R[7], g1, J.R[6] * g0));
+            double P[3][3], Jm[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    P[r][k] = fma(J.R[3 * r + 2], As(2, k), fma(J.R[3 * r + 1], As(1, k), J.R[3 * r] * As(0, k)));
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = r; k < 3; ++k)
+                    Jm[r][k] = fma(P[r][2], J.R[3 * k + 2], fma(P[r][1], J.R[3 * k + 1], P[r][0] * J.R[3 * k]));
+            const double hmc = 0.5 * J.mc;
+            const double u0 = fma(J.t[0], hmc, q0), u1 = fma(J.t[1], hmc, q1), u2 = fma(J.t[2], hmc, q2);
+            const double tu0 = J.t[0] * u0, tu1 = J.t[1] * u1, tu2 = J.t[2] * u2;
+            ci[9 * p + 3] += fma(2.0, tu1 + tu2, Jm[0][0]);
+            ci[9 * p + 6] += fma(2.0, tu0 + tu2, Jm[1][1]);
+            ci[9 * p + 8] += fma(2.0, tu0 + tu1, Jm[2][2]);
+            ci[9 * p + 4] += fma(-J.t[1], u0, fma(-J.t[0], u1, Jm[0][1]));
+            ci[9 * p + 5] += fma(-J.t[2], u0, fma(-J.t[0], u2, Jm[0][2]));
+            ci[9 * p + 7] += fma(-J.t[2], u1, fma(-J.t[1], u2, Jm[1][2]));
+            ci[9 * p + 0] += fma(J.t[0], J.mc, q0);
+            ci[9 * p + 1] += fma(J.t[1], J.mc, q1);
+            ci[9 * p + 2] += fma(J.t[2], J.mc, q2);
         }
     }
 }

@@ -135,9 +135,13 @@ double snap(double x) {
 }
 
 void finish_model(RbHostModel& m) {
-    // composite masses, tip to base (multibody.rs:157,170: masses only ever add)
-    double acc = 0.0;
-    for (int i = m.n - 1; i >= 0; --i) { acc += m.jt[i].m; m.jt[i].mc = acc; }
+    // composite (sub-tree) masses, leaves to base (multibody.rs:157,170: masses only ever add)
+    m.serial = true;
+    for (int i = 0; i < m.n; ++i) { m.jt[i].mc = m.jt[i].m; m.serial = m.serial && (int)m.jt[i].parent == i - 1; }
+    for (int i = m.n - 1; i >= 0; --i) {
+        const int p = (int)m.jt[i].parent;
+        if (p >= 0) m.jt[p].mc += m.jt[i].mc;
+    }
 }
 
 // I_o = I_c + m [c]x [c]x^T  (inertia.rs:31-32), six unique entries
@@ -155,7 +159,7 @@ void origin_inertia(double mass, const double c[3], const double Ic[9], double I
 
 // One movable joint as the sources give it: axis and link inertia in the joint's own (child) frame.
 struct RawJoint {
-    double axis[3]; double R[9]; double t[3]; double mass; double com[3]; double Ic[9];
+    double axis[3]; double R[9]; double t[3]; double mass; double com[3]; double Ic[9]; int parent;
 };
 
 void mat3_mul(const double A[9], const double B[9], double C[9]) {
@@ -180,10 +184,14 @@ void mat3_vec(const double A[9], const double v[3], double o[3]) {
 // and everything attached to that frame (link inertia, the next joint's placement) is re-expressed in the rotated
 // frame.  tau, qdd, H and the tip position are invariant; the tip-frame Jacobian needs the last Q back (model.tip).
 int build_model(const std::vector<RawJoint>& raw, RbHostModel& out, std::string& err) {
-    double Qprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    bool prev_identity = true;
+    std::vector<double> Qs(raw.size() * 9);
+    std::vector<char> Qid(raw.size());
     for (size_t i = 0; i < raw.size(); ++i) {
         const RawJoint& j = raw[i];
+        if (j.parent < -1 || j.parent >= (int)i) { err = "parent[i] must be -1 (base) or an earlier joint (topological order)"; return RB_ERR_ARG; }
+        const double Id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        const double* Qprev = j.parent >= 0 ? &Qs[(size_t)j.parent * 9] : Id;
+        const bool prev_identity = j.parent >= 0 ? (bool)Qid[j.parent] : true;
         const double an = std::sqrt(j.axis[0] * j.axis[0] + j.axis[1] * j.axis[1] + j.axis[2] * j.axis[2]);
         if (!(an > 0.0) || !std::isfinite(an)) { err = "joint axis must be a non-zero finite vector"; return RB_ERR_ARG; }
         const double a[3] = {j.axis[0] / an, j.axis[1] / an, j.axis[2] / an};       // UnitVector3::new_normalize (joint.rs:56)
@@ -221,11 +229,12 @@ int build_model(const std::vector<RawJoint>& raw, RbHostModel& out, std::string&
         r.m = j.mass;
         for (int e = 0; e < 3; ++e) r.h[e] = j.mass * com[e];
         origin_inertia(j.mass, com, Ic, r.I);                                        // joint.rs:66
+        r.parent = (double)j.parent;
         out.jt.push_back(r);
-        memcpy(Qprev, Q, sizeof Q);
-        prev_identity = identity;
+        memcpy(&Qs[i * 9], Q, sizeof Q);
+        Qid[i] = identity;
     }
-    mat3_t(Qprev, out.tip);                          // the original last frame seen from the re-based one
+    mat3_t(&Qs[(raw.size() - 1) * 9], out.tip);      // the original last frame seen from the re-based one
     for (int e = 0; e < 9; ++e) out.tip[e] = snap(out.tip[e]);
     out.n = (int)raw.size();
     finish_model(out);
@@ -296,6 +305,7 @@ int rb_model_from_urdf(const char* path, RbHostModel& out, std::string& err) {
         if (raw.size() >= RB_MAX_JOINTS) { err = "more than RB_MAX_JOINTS movable joints"; return RB_ERR_UNSUPPORTED; }
         RawJoint r{};
         memcpy(r.axis, j.axis, sizeof r.axis);
+        r.parent = (int)raw.size() - 1;                                   // serial: f[i-1] (multibody.rs:148)
         // Rotation3::from_euler_angles(roll, pitch, yaw) = Rz(yaw) Ry(pitch) Rx(roll)   (joint.rs:59-63)
         const double sr = std::sin(j.rpy[0]), cr = std::cos(j.rpy[0]);
         const double sp = std::sin(j.rpy[1]), cp = std::cos(j.rpy[1]);
@@ -329,11 +339,8 @@ int rb_model_from_desc(const RbChainDesc* d, RbHostModel& out, std::string& err)
     out = RbHostModel();
     std::vector<RawJoint> raw;
     for (int i = 0; i < d->n_joints; ++i) {
-        if (d->parent && d->parent[i] != i - 1) {
-            err = "only serial chains are supported (parent[i] must be i-1; the reference is serial-only)";
-            return RB_ERR_UNSUPPORTED;
-        }
         RawJoint r{};
+        r.parent = d->parent ? d->parent[i] : i - 1;
         r.axis[0] = 0.0; r.axis[1] = 0.0; r.axis[2] = 1.0;
         if (d->axis) memcpy(r.axis, d->axis + 3 * i, sizeof r.axis);
         const double* R = d->parent_rot + 9 * i;

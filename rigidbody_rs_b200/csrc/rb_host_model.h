@@ -15,6 +15,7 @@ struct RbHostModel {
     std::vector<RbJointK> jt;
     double g[3] = {0.0, 0.0, 9.81};          // multibody.rs:118
     double tip[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    bool serial = true;                      // every joint hangs off the previous one (the reference's only case)
     RbJointLimits lim{};
     std::vector<std::string> names;
 };

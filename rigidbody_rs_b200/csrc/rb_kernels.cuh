@@ -87,6 +87,7 @@ struct RbNParam {
     size_t slots;
     double* hpk;             // packed upper triangles of H for one chunk of states, tile-major [state / 32][n(n+1)/2][state % 32]
     size_t hpk_states;       // states per chunk
+    int tree;                // 1 = some joint's parent is not the previous joint: rbn_tree_* recursions, no warp kernel
 };
 
 // Quiet NaN of the scalar type (marks states whose mass matrix was not positive definite).

@@ -23,7 +23,8 @@ rbn_rnea_kernel(RbNParam P, const double* __restrict__ q, const double* __restri
             sc[i] = sn; sc[n + i] = cs;
         }
         RbScratch out{tau + s, ld};
-        rbn_rnea(jt, g, n, sc, dq + s, ddq + s, ld, out);
+        if (P.tree) rbn_tree_rnea(jt, g, n, sc, RbScratch{P.scratch + tid + (size_t)(8 * n) * P.threads, P.threads}, dq + s, ddq + s, ld, out);
+        else rbn_rnea(jt, g, n, sc, dq + s, ddq + s, ld, out);
     }
 }
 
@@ -53,12 +54,14 @@ rbn_fd_prepare_kernel(RbNParam P, const double* __restrict__ q, const double* __
             sc[i] = sn; sc[n + i] = cs;
         }
         RbScratch x{qdd + s, ld};
-        rbn_rnea(jt, g, n, sc, dq + s, nullptr, ld, x);                       // bias
+        const RbScratch va{P.scratch + tid + (size_t)(8 * n) * P.threads, P.threads};   // trees: link motions, then composites
+        if (P.tree) rbn_tree_rnea(jt, g, n, sc, va, dq + s, nullptr, ld, x);  // bias
+        else rbn_rnea(jt, g, n, sc, dq + s, nullptr, ld, x);
         for (int i = 0; i < n; ++i) x[i] = __ldcs(tau + (size_t)i * ld + s) - x[i];
         double* hp = P.hpk + (s >> 5) * (size_t)(n * (n + 1) / 2) * 32 + (s & 31);    // tile-major: [s / 32][k][s % 32]
-        rbn_crba(jt, n, sc, [&](int r, int c, double v) {
-            __stcs(hp + (size_t)(r * n - r * (r - 1) / 2 + (c - r)) * 32, v);
-        });
+        auto put = [&](int r, int c, double v) { __stcs(hp + (size_t)(r * n - r * (r - 1) / 2 + (c - r)) * 32, v); };
+        if (P.tree) rbn_tree_crba(jt, n, sc, va, put);
+        else rbn_crba(jt, n, sc, put);
     }
 }
 
@@ -186,7 +189,9 @@ rbn_crba_kernel(RbNParam P, const double* __restrict__ q, double* __restrict__ H
         }
         for (int c = 0; c < n; ++c)
             for (int r = c + 1; r < n; ++r) __stcs(Hout + (size_t)(r + n * c) * ld + s, 0.0);
-        rbn_crba(jt, n, sc, [&](int r, int c, double v) { __stcs(Hout + (size_t)(r + n * c) * ld + s, v); });
+        auto put = [&](int r, int c, double v) { __stcs(Hout + (size_t)(r + n * c) * ld + s, v); };
+        if (P.tree) rbn_tree_crba(jt, n, sc, RbScratch{P.scratch + tid + (size_t)(8 * n) * P.threads, P.threads}, put);
+        else rbn_crba(jt, n, sc, put);
     }
 }
 
@@ -201,7 +206,9 @@ rbn_fk_jac_kernel(RbNParam P, const double* __restrict__ q, double* __restrict__
         const double* tip = P.model + (size_t)n * 24 + 3;
         double A[3][3] = {{tip[0], tip[1], tip[2]}, {tip[3], tip[4], tip[5]}, {tip[6], tip[7], tip[8]}};
         double r[3] = {0.0, 0.0, 0.0};
-        for (int i = n - 1; i >= 0; --i) {
+        if (Jout && P.tree)                              // joints that do not support the tip (last link): zero columns
+            for (int k = 0; k < 6 * n; ++k) __stcs(Jout + (size_t)k * ld + s, 0.0);
+        for (int i = n - 1; i >= 0; i = (int)jt[i].parent) {
             const RbJointK& j = jt[i];
             if (Jout) {
 #pragma unroll
@@ -234,7 +241,8 @@ rbn_fk_jac_kernel(RbNParam P, const double* __restrict__ q, double* __restrict__
     }
 }
 
-// scratch slots: [0,2n) sincos, [2n,8n) f, [8n, 8n+n*n) H, n rhs/x, n dinv, 2n carried (q, dq).  The per-step solve
+// scratch slots: [0,2n) sincos, [2n,8n) f, (trees: [8n,20n) link motions / composites,) then n*n H, n rhs/x, n dinv,
+// 2n carried (q, dq).  The per-step solve
 // still factorises H in the per-thread global scratch (slow for long chains; rollouts of long chains are not a
 // BASELINE.json configuration).
 __global__ void __launch_bounds__(RB_BLOCK)
@@ -248,11 +256,13 @@ rbn_rollout_kernel(RbNParam P, const double* __restrict__ q0, const double* __re
     const RbJointK* jt = reinterpret_cast<const RbJointK*>(P.model);
     const double* g = P.model + (size_t)n * 24;
     RbScratch sc{P.scratch + tid, P.threads};
-    RbScratch Hs{P.scratch + tid + (size_t)(8 * n) * P.threads, P.threads};
-    RbScratch x{P.scratch + tid + (size_t)(8 * n + n * n) * P.threads, P.threads};
-    RbScratch dinv{P.scratch + tid + (size_t)(9 * n + n * n) * P.threads, P.threads};
-    RbScratch qs{P.scratch + tid + (size_t)(10 * n + n * n) * P.threads, P.threads};
-    RbScratch dqs{P.scratch + tid + (size_t)(11 * n + n * n) * P.threads, P.threads};
+    const int o = P.tree ? 20 * n : 8 * n;           // trees keep 12n link motions / 9n composites at [8n, 20n)
+    RbScratch va{P.scratch + tid + (size_t)(8 * n) * P.threads, P.threads};
+    RbScratch Hs{P.scratch + tid + (size_t)o * P.threads, P.threads};
+    RbScratch x{P.scratch + tid + (size_t)(o + n * n) * P.threads, P.threads};
+    RbScratch dinv{P.scratch + tid + (size_t)(o + n + n * n) * P.threads, P.threads};
+    RbScratch qs{P.scratch + tid + (size_t)(o + 2 * n + n * n) * P.threads, P.threads};
+    RbScratch dqs{P.scratch + tid + (size_t)(o + 3 * n + n * n) * P.threads, P.threads};
     const size_t step = (size_t)n * ld;
     bool all_ok = true;
     for (size_t s = tid; s < B; s += nthr) {
@@ -265,9 +275,12 @@ rbn_rollout_kernel(RbNParam P, const double* __restrict__ q0, const double* __re
                 sincos(qs[i], &sn, &cs);
                 sc[i] = sn; sc[n + i] = cs;
             }
-            rbn_rnea(jt, g, n, sc, dqs.base, nullptr, dqs.stride, x);
+            if (P.tree) rbn_tree_rnea(jt, g, n, sc, va, dqs.base, nullptr, dqs.stride, x);
+            else rbn_rnea(jt, g, n, sc, dqs.base, nullptr, dqs.stride, x);
             for (int i = 0; i < n; ++i) x[i] = __ldcs(tau + (size_t)t * step + (size_t)i * ld + s) - x[i];
-            rbn_crba(jt, n, sc, [&](int r, int c, double v) { Hs[r * n + c] = v; });
+            auto put = [&](int r, int c, double v) { Hs[r * n + c] = v; };
+            if (P.tree) rbn_tree_crba(jt, n, sc, va, put);
+            else rbn_crba(jt, n, sc, put);
             ok_s = rbn_ldlt_solve(n, Hs, x, dinv) && ok_s;
             double c = 0.0;
             for (int i = 0; i < n; ++i) {
@@ -351,7 +364,7 @@ namespace {
 cudaError_t n_fd(const void* param, const double* q, const double* dq, const double* tau, double* qdd, size_t B, size_t ld, int* status, cudaStream_t st) {
     const RbNParam* P = (const RbNParam*)param;
 #if RB_WARP_FD
-    if (P->n <= 32)                                                  // warp-per-state, nothing leaves the SM (rb_kernels_warp.cu)
+    if (P->n <= 32 && !P->tree)                                      // warp-per-state, nothing leaves the SM (rb_kernels_warp.cu)
         return rb_launch_warp_fd(P->model, P->n, q, dq, tau, qdd, B, ld, status, st);
 #endif
     for (size_t off = 0; off < B; off += P->hpk_states) {

@@ -13,10 +13,11 @@ struct RbJointK {
     double R[9];   // parent_rot, row-major: child-frame vector -> parent-frame vector (before the joint rotation)
     double t[3];   // parent_trans
     double m;      // mass
-    double mc;     // composite mass of links i..n-1 (a model constant: CRBA's running mass, multibody.rs:170)
+    double mc;     // composite mass of the sub-tree rooted at link i (links i..n-1 of a serial chain): a model
+                   // constant, CRBA's running mass (multibody.rs:170)
     double h[3];   // m * com
     double I[6];   // inertia about the link origin: xx xy xz yy yz zz   (inertia.rs:31-32)
-    double pad;    // keeps the row at 24 doubles = 192 B
+    double parent; // index of the parent link, -1 = base (i-1 for the reference's serial chains); row = 24 doubles = 192 B
 };
 
 template <int N>

@@ -341,6 +341,50 @@ def test_long_random_chains(rb, n, seed):
     assert np.abs(J - ch.jac(q[:32])).max() < TOL
 
 
+@pytest.mark.parametrize("n,seed", [(5, 1), (9, 2), (20, 3), (40, 4)])
+def test_kinematic_trees(rb, n, seed):
+    """Branching trees (parent[i] < i): run-time-n kernels with the parent-indexed recursions; the reference has only
+    the serial case (multibody.rs:148,165), so the checker is the twin's tree form (pinned by energy identities in
+    tests/test_host.py).  Oblique joint axes ride along."""
+    from test_host import _random_chain, _random_tree
+    from oracle.rb_oracle_np import ChainNP
+    R, t, m, c, Ic = _random_chain(n, 70 + seed)
+    par = _random_tree(n, seed)
+    ax = np.random.default_rng(seed).normal(size=(n, 3))
+    ch = ChainNP.from_arrays(R, t, m, c, Ic, axis=ax, parent=par)
+    mb = rb.Multibody.from_descriptor(R, t, m, c, Ic, axis=ax, parent=par)
+    assert mb.kernel_variant == "generic-n" and "tree" in mb._note()
+    rng = np.random.default_rng(seed)
+    B = 257
+    q, dq, ddq = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n))
+    tau = ch.rnea(q, dq, ddq)
+    assert state_err(mb.rnea(q, dq, ddq, layout="aos"), tau, 1).max() < TOL
+    assert state_err(mb.forward_dynamics(q, dq, tau, layout="aos"), ddq, 1).max() < 1e-7
+    H = mb.crba(q[:32], layout="aos").reshape(32, n, n).transpose(0, 2, 1)
+    Href = ch.crba(q[:32])
+    assert np.abs(H - Href).max() < TOL * max(1.0, np.abs(Href).max())
+    assert (Href == 0).sum() > 32 * n * (n - 1) // 2                  # branch-induced zeros above the diagonal too
+    assert np.abs(mb.fwd_kin(q[:32], layout="aos") - ch.fwd_kin(q[:32])[1]).max() < TOL
+    J = mb.jac(q[:32], layout="aos").reshape(32, n, 6).transpose(0, 2, 1)
+    assert np.abs(J - ch.jac(q[:32])).max() < TOL
+    # three semi-implicit Euler steps against the twin's forward dynamics
+    qs, dqs = q[:16].copy(), dq[:16].copy()
+    taus = rng.uniform(-5, 5, (3, 16, n))
+    for k in range(3):
+        a = ch.forward_dynamics(qs, dqs, taus[k])
+        dqs = dqs + 1e-3 * a
+        qs = qs + 1e-3 * dqs
+    qf, dqf = mb.rollout(np.ascontiguousarray(q[:16].T), np.ascontiguousarray(dq[:16].T),
+                         np.ascontiguousarray(taus.transpose(0, 2, 1)), 1e-3, trajectory=False, final=True)
+    assert np.abs(qf - qs.T).max() < 1e-9 and np.abs(dqf - dqs.T).max() < 1e-8
+    with pytest.raises(rb.RigidBodyError):
+        os.environ["RIGIDBODY_B200_VARIANT"] = "jit-specialised"
+        try:
+            rb.Multibody.from_descriptor(R, t, m, c, Ic, parent=par)
+        finally:
+            os.environ.pop("RIGIDBODY_B200_VARIANT", None)
+
+
 @pytest.mark.parametrize("n", [7, 4])
 def test_general_joint_axes_all_families(rb, n):
     """Joint axes other than +z (x, y, -z, unnormalised, oblique): the loader re-bases the frames, every kernel family

@@ -108,7 +108,7 @@ def test_null_and_bad_arguments(rb):
     assert lib.multibody_gpu_new(C.byref(d), 0, C.byref(out)) == _lib.RB_ERR_ARG
     d.n_joints = 65
     assert lib.multibody_gpu_new(C.byref(d), 0, C.byref(out)) == _lib.RB_ERR_UNSUPPORTED
-    # branching tree -> unsupported (reference is serial-only, multibody.rs:148)
+    # parents must come first (topological order); a valid tree gets past the loader (and stops at "no CUDA device" here)
     n = 2
     R = np.tile(np.eye(3).reshape(-1), n); t = np.zeros(3 * n); m = np.ones(n); c = np.zeros(3 * n)
     Ic = np.tile(np.eye(3).reshape(-1), n); par = np.array([-1, -1], dtype=np.int32)
@@ -116,7 +116,15 @@ def test_null_and_bad_arguments(rb):
     d.n_joints = n
     d.parent_rot, d.parent_trans, d.mass, d.com, d.inertia_com = dp(R), dp(t), dp(m), dp(c), dp(Ic)
     d.parent = par.ctypes.data_as(C.POINTER(C.c_int32))
-    assert lib.multibody_gpu_new(C.byref(d), 0, C.byref(out)) == _lib.RB_ERR_UNSUPPORTED
+    par[:] = [-1, 1]
+    assert lib.multibody_gpu_new(C.byref(d), 0, C.byref(out)) == _lib.RB_ERR_ARG
+    assert b"topological" in lib.multibody_last_error()
+    par[:] = [-1, -1]
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.multibody_gpu_new(C.byref(d), 0, C.byref(out)) == _lib.RB_ERR_CUDA
+    log = C.create_string_buffer(1024)
+    assert lib.multibody_jit_precompile(C.byref(d), None, log, 1024) == _lib.RB_ERR_UNSUPPORTED     # trees are not unrolled
     assert b"serial" in lib.multibody_last_error()
 
 
@@ -194,11 +202,22 @@ def _axis_urdf(path, R_rpy, t, m, c, Ic, axes):
     return str(path)
 
 
-def test_twin_with_general_axes_is_self_consistent():
-    """The numpy twin's S = (axis; 0) generalisation, checked against physics it does not assume: gravity torque =
-    dU/dq (central differences), H = d tau / d ddq, H SPD, and for +z axes it is the old z-only code path."""
+def _random_tree(n, seed):
+    """parent[i] drawn from the earlier joints (or the base): a random kinematic tree in topological order."""
+    rng = np.random.default_rng(1000 + seed)
+    par = np.array([-1] + [int(rng.integers(-1 if i > 2 else 0, i)) for i in range(1, n)], dtype=np.int32)
+    par[n - 1] = max(par[n - 1], 0)                      # give the tip at least one supporting joint
+    return par
+
+
+@pytest.mark.parametrize("tree", [False, True])
+def test_twin_with_general_axes_is_self_consistent(tree):
+    """The numpy twin's S = (axis; 0) and parent-index generalisations, checked against physics they do not assume:
+    gravity torque = dU/dq (central differences), H = d tau / d ddq, H SPD, power balance of the Coriolis terms."""
     R, t, m, c, Ic = _random_chain(7, 5)
-    ch = ChainNP.from_arrays(R, t, m, c, Ic, axis=AXES)
+    ch = ChainNP.from_arrays(R, t, m, c, Ic, axis=AXES, parent=_random_tree(7, 3) if tree else None)
+    if tree:
+        assert not np.array_equal(ch.parent, np.arange(7) - 1)
     rng = np.random.default_rng(0)
     q, dq, ddq = rng.uniform(-2, 2, (3, 6, 7))
     g = ch.rnea(q, 0 * q, 0 * q)
