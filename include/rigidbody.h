@@ -186,6 +186,18 @@ int multibody_forward_dynamics_batch_f32(RbGpu* g, const float* q, const float* 
 int multibody_crba_batch(RbGpu* g, const double* q, double* H,
                          size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
 
+/* New (README.md:18 lists "Differentiability" as not done): analytical first derivatives, for serial chains of at most
+ * 12 joints (the register-resident kernel families; RB_ERR_UNSUPPORTED otherwise).
+ * multibody_rnea_derivatives_batch: out holds 2 n*n entries per state, block 0 = d tau / d q, block 1 = d tau / d dq of
+ *   tau = rnea(q, dq, ddq); within a block entry k = r + n*c is d tau_r / d x_c (column-major, like crba).
+ *   (d tau / d ddq is crba(q).)   SOA: out[(blk*n*n + k)*ld + s];  AOS: out[s*2*n*n + blk*n*n + k].
+ * multibody_fd_derivatives_batch: out holds 3 n*n entries per state: d qdd / d q, d qdd / d dq and H^-1 = d qdd / d tau
+ *   of qdd = forward_dynamics(q, dq, tau); same entry convention.  States with a non-SPD mass matrix get NaN. */
+int multibody_rnea_derivatives_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, double* out,
+                                     size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+int multibody_fd_derivatives_batch(RbGpu* g, const double* q, const double* dq, const double* tau, double* out,
+                                   size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
 /* Tip translation: multibody_fwd_kin (lib.rs:46-57).  3 entries per state (SOA: xyz[k*ld + s]; AOS: xyz[3s + k]). */
 int multibody_fwd_kin_batch(RbGpu* g, const double* q, double* xyz,
                             size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);

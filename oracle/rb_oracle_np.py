@@ -98,7 +98,9 @@ class ChainNP:
 
     def rnea(self, q, dq, ddq):
         """q, dq, ddq: [B, n] -> tau [B, n]  (multibody.rs:111-153)"""
-        q, dq, ddq = (np.atleast_2d(np.asarray(x, dtype=np.float64)) for x in (q, dq, ddq))
+        q, dq, ddq = (np.atleast_2d(np.asarray(x)) for x in (q, dq, ddq))
+        dt = np.result_type(q.dtype, dq.dtype, ddq.dtype, np.float64)       # complex inputs: complex-step derivatives
+        q, dq, ddq = q.astype(dt), dq.astype(dt), ddq.astype(dt)
         B, n = q.shape
         R = [self._R(i, q[:, i]) for i in range(n)]
         base = (np.zeros((B, 3)), np.zeros((B, 3)), np.tile(np.array([0.0, 0.0, GRAVITY]), (B, 1)), np.zeros((B, 3)))
@@ -123,7 +125,7 @@ class ChainNP:
             Iv_l, Iv_r = self._Imul(i, v_lin, v_rot)
             f_lin.append(Ia_l + np.cross(v_rot, Iv_l))
             f_rot.append(Ia_r + np.cross(v_rot, Iv_r) + np.cross(v_lin, Iv_l))
-        tau = np.zeros((B, n))
+        tau = np.zeros((B, n), dtype=dt)
         for i in range(n - 1, -1, -1):
             tau[:, i] = f_rot[i] @ self.axis[i]
             p = self.parent[i]
@@ -184,6 +186,28 @@ class ChainNP:
         L = np.linalg.cholesky(H)
         y = np.linalg.solve(L, (tau - c)[..., None])
         return np.linalg.solve(np.swapaxes(L, 1, 2), y)[..., 0]
+
+    def rnea_derivatives(self, q, dq, ddq):
+        """(d tau / d q, d tau / d dq), each [B, n, n] with [b, r, c] = d tau_r / d x_c, by complex-step
+        differentiation of `rnea` itself (h = 1e-30: exact to rounding, no subtraction) -- independent of the
+        world-frame closed form the CUDA kernels use."""
+        q, dq, ddq = (np.atleast_2d(np.asarray(x, dtype=np.float64)) for x in (q, dq, ddq))
+        B, n = q.shape
+        h = 1e-30
+        Dq, Dv = np.zeros((B, n, n)), np.zeros((B, n, n))
+        for c in range(n):
+            e = np.zeros(n, dtype=complex); e[c] = 1j * h
+            Dq[:, :, c] = self.rnea(q + e, dq, ddq).imag / h
+            Dv[:, :, c] = self.rnea(q, dq + e, ddq).imag / h
+        return Dq, Dv
+
+    def fd_derivatives(self, q, dq, tau):
+        """(d qdd / d q, d qdd / d dq, H^-1 = d qdd / d tau) of qdd = forward_dynamics(q, dq, tau):
+        d qdd / d x = -H^-1 (d rnea / d x at ddq = qdd)."""
+        qdd = self.forward_dynamics(q, dq, tau)
+        Dq, Dv = self.rnea_derivatives(q, dq, qdd)
+        Minv = np.linalg.inv(self.crba(q, symmetric=True))
+        return -Minv @ Dq, -Minv @ Dv, Minv
 
     def fwd_kin(self, q):
         """q [B,n] -> (R [B,3,3], p [B,3]) of the tip in the base frame (multibody.rs:87-93)."""

@@ -246,6 +246,25 @@ class Multibody:
             return self._call_f32(lib.multibody_forward_dynamics_batch_f32, q, dq, tau, out)
         return self._call(lib.multibody_forward_dynamics_batch, (q, dq, tau), ("q", "dq", "tau"), (n, n, n), n, layout, out)
 
+    def rnea_derivatives(self, q, dq, ddq, layout="soa", out=None):
+        """Analytical d tau / d q and d tau / d dq of tau = rnea(q, dq, ddq), packed as the C ABI returns them
+        (include/rigidbody.h multibody_rnea_derivatives_batch): 2 n*n entries per state, block b entry r + n*c.
+        soa -> [2*n*n, B]; aos -> [B, 2*n*n]; one state -> the pair of [n, n] matrices (D[r, c] = d tau_r / d x_c)."""
+        n = self.n
+        D = self._call(lib.multibody_rnea_derivatives_batch, (q, dq, ddq), ("q", "dq", "ddq"), (n, n, n), 2 * n * n, layout, out)
+        if len(D.shape) == 1:
+            return tuple(D[b * n * n:(b + 1) * n * n].reshape(n, n).T for b in range(2))
+        return D
+
+    def fd_derivatives(self, q, dq, tau, layout="soa", out=None):
+        """Analytical d qdd / d q, d qdd / d dq and H^-1 = d qdd / d tau of qdd = forward_dynamics(q, dq, tau):
+        3 n*n entries per state, same packing as `rnea_derivatives`; one state -> three [n, n] matrices."""
+        n = self.n
+        D = self._call(lib.multibody_fd_derivatives_batch, (q, dq, tau), ("q", "dq", "tau"), (n, n, n), 3 * n * n, layout, out)
+        if len(D.shape) == 1:
+            return tuple(D[b * n * n:(b + 1) * n * n].reshape(n, n).T for b in range(3))
+        return D
+
     def crba(self, q, layout="soa", out=None):
         """Joint-space mass matrix, reference convention (multibody.rs:155-174; FFI lib.rs:32-43): n*n entries per
         state, entry r + n*c, upper triangle + diagonal filled, strict lower 0.  One state -> [n, n] matrix H[r, c]."""

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "multibody_forward_dynamics_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_rnea_batch_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
     "multibody_forward_dynamics_batch_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
+    "multibody_rnea_derivatives_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
+    "multibody_fd_derivatives_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_crba_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_fwd_kin_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_jac_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),

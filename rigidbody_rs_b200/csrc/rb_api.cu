@@ -571,6 +571,33 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }
 
+// ---- analytical derivatives (rb_deriv.cuh): the register-resident families only ----
+extern "C" int multibody_rnea_derivatives_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, double* out,
+                                                size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    if (!g->ops->rnea_deriv)
+        return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no derivative kernels (serial chains of at most 12 joints)");
+    const int n = g->model.n;
+    OpDesc op{3, {q, dq, ddq}, {n, n, n}, out, 2 * n * n,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  return g->ops->rnea_deriv(g->param.data(), in[0], in[1], in[2], out, B, ld, st);
+              }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, false);
+}
+
+extern "C" int multibody_fd_derivatives_batch(RbGpu* g, const double* q, const double* dq, const double* tau, double* out,
+                                              size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    if (!g->ops->fd_deriv)
+        return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no derivative kernels (serial chains of at most 12 joints)");
+    const int n = g->model.n;
+    OpDesc op{3, {q, dq, tau}, {n, n, n}, out, 3 * n * n,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  return g->ops->fd_deriv(g->param.data(), in[0], in[1], in[2], out, B, ld, g->d_status, st);
+              }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, true);
+}
+
 // ---- optional fp32 mode: device-resident SoA batches only ----
 namespace {
 int f32_common(RbGpu* g, const void* a, const void* b, const void* c, const void* out, size_t n_states, size_t& ld) {

@@ -314,6 +314,78 @@ def test_jit_random_chains_match_matrix_oracle(rb, n, seed):
     assert np.abs(J - ch.jac(q[:64])).max() < TOL
 
 
+def _unpack(D, n, blocks):
+    """[B, blocks*n*n] (aos packing of the C ABI: block b, entry r + n*c) -> list of [B, n, n] with [b, r, c]."""
+    B = D.shape[0]
+    return [D[:, b * n * n:(b + 1) * n * n].reshape(B, n, n).transpose(0, 2, 1) for b in range(blocks)]
+
+
+def test_analytical_derivatives_fr3_all_families(rb, oracle_fr3):
+    """d tau / d (q, dq) and d qdd / d (q, dq, tau) against complex-step differentiation of the
+    twin's link-frame rnea.  Bar: |err| <= 1e-10 * max(1, max|ref|) per state (FD derivatives: 1e-8, they carry H^-1)."""
+    from oracle.rb_oracle_np import ChainNP
+    ch = ChainNP(oracle_fr3.model)
+    B = 300
+    q, dq, ddq, tau = (x.T.copy() for x in _states(oracle_fr3, B))
+    Dq, Dv = ch.rnea_derivatives(q, dq, ddq)
+    Aq, Av, Mi = ch.fd_derivatives(q, dq, tau)
+    fams = []
+    for mb in _variants(rb, FR3):
+        if mb.kernel_variant == "generic-n":
+            with pytest.raises(rb.RigidBodyError):
+                mb.rnea_derivatives(q, dq, ddq, layout="aos")
+            continue
+        fams.append(mb.kernel_variant)
+        gq, gv = _unpack(mb.rnea_derivatives(q, dq, ddq, layout="aos"), 7, 2)
+        for got, want in ((gq, Dq), (gv, Dv)):
+            err = np.abs(got - want).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(want).reshape(B, -1).max(1))
+            assert err.max() < TOL, (mb.kernel_variant, err.max())
+        fq, fv, fm = _unpack(mb.fd_derivatives(q, dq, tau, layout="aos"), 7, 3)
+        for got, want in ((fq, Aq), (fv, Av), (fm, Mi)):
+            err = np.abs(got - want).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(want).reshape(B, -1).max(1))
+            assert err.max() < 1e-8, (mb.kernel_variant, err.max())
+    assert fams == ["fr3-specialised", "jit-specialised", "generic-7"]
+    # device SoA tensors, and one state
+    import torch
+    mb = rb.Multibody.from_urdf(FR3)
+    dev = torch.device("cuda:0")
+    tq, tdq, tddq = (torch.from_numpy(np.ascontiguousarray(x.T)).to(dev) for x in (q, dq, ddq))
+    D = mb.rnea_derivatives(tq, tdq, tddq)
+    mb.sync()
+    assert tuple(D.shape) == (98, B)
+    gq, gv = _unpack(D.cpu().numpy().T.copy(), 7, 2)
+    assert np.abs(gq - Dq).max() < 1e-9 and np.abs(gv - Dv).max() < 1e-9
+    one_q, one_v = mb.rnea_derivatives(q[0], dq[0], ddq[0])
+    assert np.abs(one_q - Dq[0]).max() < 1e-9 and np.abs(one_v - Dv[0]).max() < 1e-9
+    # d tau / d ddq is the mass matrix: consistency of the three blocks with a finite step of the kernels themselves
+    e = 1e-6 * np.random.default_rng(0).normal(size=q.shape)
+    lin = np.einsum("brc,bc->br", Dq, e)
+    assert np.abs(mb.rnea(q + e, dq, ddq, layout="aos") - mb.rnea(q, dq, ddq, layout="aos") - lin).max() < 1e-8
+
+
+@pytest.mark.parametrize("n,seed", [(2, 31), (5, 32), (10, 33)])
+def test_analytical_derivatives_random_chains(rb, n, seed):
+    from test_host import _random_chain, AXES
+    from oracle.rb_oracle_np import ChainNP
+    R, t, m, c, Ic = _random_chain(n, seed)
+    ax = (AXES + AXES)[:n]
+    mb = rb.Multibody.from_descriptor(R, t, m, c, Ic, axis=ax)
+    assert mb.kernel_variant == "jit-specialised"
+    ch = ChainNP.from_arrays(R, t, m, c, Ic, axis=ax)
+    rng = np.random.default_rng(seed)
+    B = 200
+    q, dq, ddq = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n))
+    Dq, Dv = ch.rnea_derivatives(q, dq, ddq)
+    gq, gv = _unpack(mb.rnea_derivatives(q, dq, ddq, layout="aos"), n, 2)
+    assert np.abs(gq - Dq).max() < TOL * max(1.0, np.abs(Dq).max())
+    assert np.abs(gv - Dv).max() < TOL * max(1.0, np.abs(Dv).max())
+    tau = ch.rnea(q, dq, ddq)
+    Aq, Av, Mi = ch.fd_derivatives(q, dq, tau)
+    fq, fv, fm = _unpack(mb.fd_derivatives(q, dq, tau, layout="aos"), n, 3)
+    for got, want in ((fq, Aq), (fv, Av), (fm, Mi)):
+        assert np.abs(got - want).max() < 1e-8 * max(1.0, np.abs(want).max())
+
+
 @pytest.mark.parametrize("n,seed", [(13, 1), (24, 2), (32, 3), (33, 4), (64, 5)])
 def test_long_random_chains(rb, n, seed):
     """Chains beyond the register-resident limit: run-time-n kernels; forward dynamics by the warp-per-state kernel

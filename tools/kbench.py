@@ -39,6 +39,13 @@ for op in a.ops.split(","):
         qc = q[:, :Bc].contiguous(); Hout = torch.empty((n * n, Bc), dtype=torch.float64, device=dev)
         fn = lambda: mb.crba(qc, out=Hout)
         units = Bc
+    elif op in ("rnea_deriv", "fd_deriv"):
+        Bc = min(B, 1 << 21)
+        blocks = 2 if op == "rnea_deriv" else 3
+        qc, dqc, xc = (t[:, :Bc].contiguous() for t in (q, dq, x3))
+        Dout = torch.empty((blocks * n * n, Bc), dtype=torch.float64, device=dev)
+        fn = (lambda: mb.rnea_derivatives(qc, dqc, xc, out=Dout)) if op == "rnea_deriv" else (lambda: mb.fd_derivatives(qc, dqc, xc, out=Dout))
+        units = Bc
     else:
         if a.dtype == "f32":
             q32, dq32, x32, o32 = (t.float() for t in (q, dq, x3, out))
