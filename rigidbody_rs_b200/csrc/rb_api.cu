@@ -61,6 +61,7 @@ struct RbGpu {
     RbHostModel model;
     const RbOps* ops = nullptr;
     std::vector<unsigned char> param;     // host image of the kernel-parameter block `ops` expects
+    std::vector<double> flat;             // the model rows as uploaded (rb_model.h layout)
     const RbOps* ops2 = nullptr;          // fallback table for entries `ops` leaves null (run-time-n family)
     std::vector<unsigned char> param2;
     size_t hpk_states = 0;
@@ -157,7 +158,8 @@ int pick_ops(RbGpu* g) {
     const char* force = getenv("RIGIDBODY_B200_VARIANT");
     const std::string want = force ? force : "auto";
     const int n = g->model.n;
-    std::vector<double> flat = rb_model_flat(g->model);
+    g->flat = rb_model_flat(g->model);
+    const std::vector<double>& flat = g->flat;
     if (!g->model.serial) {
         // kinematic trees (parent[i] != i-1): the run-time-n family only; every other family unrolls a serial chain
         if (want != "auto" && want != "generic-n")
@@ -575,12 +577,12 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
 extern "C" int multibody_rnea_derivatives_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, double* out,
                                                 size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
-    if (!g->ops->rnea_deriv)
-        return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no derivative kernels (serial chains of at most 12 joints)");
     const int n = g->model.n;
+    if (n > RB_DERIV_MAX_N || !g->model.serial)
+        return fail(RB_ERR_UNSUPPORTED, "derivative kernels serve serial chains of at most 12 joints");
     OpDesc op{3, {q, dq, ddq}, {n, n, n}, out, 2 * n * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return g->ops->rnea_deriv(g->param.data(), in[0], in[1], in[2], out, B, ld, st);
+                  return rb_launch_rnea_deriv(g->model.n, g->flat.data(), in[0], in[1], in[2], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
 }
@@ -588,12 +590,12 @@ extern "C" int multibody_rnea_derivatives_batch(RbGpu* g, const double* q, const
 extern "C" int multibody_fd_derivatives_batch(RbGpu* g, const double* q, const double* dq, const double* tau, double* out,
                                               size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
-    if (!g->ops->fd_deriv)
-        return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no derivative kernels (serial chains of at most 12 joints)");
     const int n = g->model.n;
+    if (n > RB_DERIV_MAX_N || !g->model.serial)
+        return fail(RB_ERR_UNSUPPORTED, "derivative kernels serve serial chains of at most 12 joints");
     OpDesc op{3, {q, dq, tau}, {n, n, n}, out, 3 * n * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return g->ops->fd_deriv(g->param.data(), in[0], in[1], in[2], out, B, ld, g->d_status, st);
+                  return rb_launch_fd_deriv(g->model.n, g->flat.data(), in[0], in[1], in[2], out, B, ld, g->d_status, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }

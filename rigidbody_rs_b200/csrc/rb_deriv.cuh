@@ -19,7 +19,7 @@
 //   d tau_m / d x_j = s_m . G_j             (m <= j)
 //                   = da0_j . A_m + dv_j . B_m   (m > j)
 //
-// (the term from d s_m / d q_j cancels against s_j x* F^c_m).  About 8 RNEA evaluations of work for both matrices.
+// (the term from d s_m / d q_j cancels against s_j x* F^c_m).
 // tests/ check it against complex-step differentiation of an independent link-frame rnea.
 #pragma once
 #include "rb_dyn.cuh"
@@ -75,64 +75,89 @@ RB_DI double rb_dot6(const double (&a)[6], const double (&b)[6]) {
     return fma(a[0], b[0], fma(a[1], b[1], fma(a[2], b[2], fma(a[3], b[3], fma(a[4], b[4], a[5] * b[5])))));
 }
 
-// put_q(m, j, v): d tau_m / d q_j;  put_v(m, j, v): d tau_m / d dq_j  (m, j are RbIC constants).
-template <class M, class PutQ, class PutV>
-RB_DI void rb_rnea_derivatives(const typename M::Param& p, const double (&sn)[M::N], const double (&cs)[M::N],
-                               const double (&dq)[M::N], const double (&ddq)[M::N], PutQ&& put_q, PutV&& put_v) {
-    constexpr int N = M::N;
-    double S[N][6], DV[N][6], DA[N][6];                     // screws; dv and da0 of the d/dq columns (d/d dq: S, 2 DV)
+// One link back along the chain: (R, P) of link i -> link i-1.  R <- R Rz(q_i)^T R_p^T,  P <- P - R t_i.
+RB_DI void rb_pose_back(const RbJointK& J, double sn, double cs, double (&R)[3][3], double (&P)[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double u0 = fma(cs, R[r][0], -(sn * R[r][1])), u1 = fma(sn, R[r][0], cs * R[r][1]), u2 = R[r][2];
+        R[r][0] = fma(J.R[0], u0, fma(J.R[1], u1, J.R[2] * u2));
+        R[r][1] = fma(J.R[3], u0, fma(J.R[4], u1, J.R[5] * u2));
+        R[r][2] = fma(J.R[6], u0, fma(J.R[7], u1, J.R[8] * u2));
+        P[r] = fma(-R[r][0], J.t[0], fma(-R[r][1], J.t[1], fma(-R[r][2], J.t[2], P[r])));
+    }
+}
+// One link out: (R, P) of link i-1 -> link i.  P <- P + R t_i,  R <- R R_p Rz(q_i).
+RB_DI void rb_pose_out(const RbJointK& J, double sn, double cs, double (&R)[3][3], double (&P)[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        P[r] = fma(R[r][0], J.t[0], fma(R[r][1], J.t[1], fma(R[r][2], J.t[2], P[r])));
+        const double t0 = fma(R[r][0], J.R[0], fma(R[r][1], J.R[3], R[r][2] * J.R[6]));
+        const double t1 = fma(R[r][0], J.R[1], fma(R[r][1], J.R[4], R[r][2] * J.R[7]));
+        const double t2 = fma(R[r][0], J.R[2], fma(R[r][1], J.R[5], R[r][2] * J.R[8]));
+        R[r][0] = fma(cs, t0, sn * t1);
+        R[r][1] = fma(cs, t1, -(sn * t0));
+        R[r][2] = t2;
+    }
+}
+// Screw of the joint whose frame is (R, P), and the two d/dq column vectors of a body moving with (v, a):
+//   s = (z ; P x z),  dv = v x s,  da0 = a x s + v x dv.
+RB_DI void rb_screw_cols(const double (&R)[3][3], const double (&P)[3], const double (&v)[6], const double (&a)[6],
+                         double (&s)[6], double (&dv)[6], double (&da)[6]) {
+    const double z[3] = {R[0][2], R[1][2], R[2][2]};
+    double pz[3];
+    rb_cross3(P, z, pz);
+    s[0] = z[0]; s[1] = z[1]; s[2] = z[2]; s[3] = pz[0]; s[4] = pz[1]; s[5] = pz[2];
+    rb_mcross(v, s, dv);
+    double t6[6];
+    rb_mcross(a, s, da);
+    rb_mcross(v, dv, t6);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) da[k] += t6[k];
+}
+
+// put(blk, r, c, v): blk 0 = d tau_r / d q_c, blk 1 = d tau_r / d dq_c.
+// Real loops over the joints (model rows from the constant bank by index), and no per-joint arrays: a thread cannot
+// hold N screws and column vectors next to the composites -- the first, fully unrolled version did and spilled 4 KB
+// per thread through L2 to HBM (5x the algorithmic write traffic).  Instead, for every pair (i, j < i) the inward
+// sweep walks a copy of (pose, v, a) back from link i to link j and rebuilds s_j, dv_j, da0_j there: ~160 FP64
+// instructions per pair, all in registers.  sn, cs, dq, ddq are indexed at run time (thread-local memory, L1).
+template <int N, class Put>
+RB_DI void rb_rnea_derivatives(const RbModelK<N>& p, const double* sn, const double* cs, const double* dq, const double* ddq,
+                               Put&& put) {
     double R[3][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}}, P[3] = {0.0, 0.0, 0.0};
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    double a[6] = {0.0, 0.0, 0.0, M::template g<0>(p), M::template g<1>(p), M::template g<2>(p)};
-    // ---- outward: world poses, screws, velocities, accelerations
-    rb_for_up<0, N>([&](auto ic) {
-        constexpr int I = decltype(ic)::value;
-        double T[3][3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            P[r] = k_dot3_acc<KC(I, RB_F_T, 0), KC(I, RB_F_T, 1), KC(I, RB_F_T, 2)>(P[r], KV(I, RB_F_T, 0), KV(I, RB_F_T, 1), KV(I, RB_F_T, 2), R[r][0], R[r][1], R[r][2]);
-            T[r][0] = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 3), KC(I, RB_F_R, 6)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 3), KV(I, RB_F_R, 6), R[r][0], R[r][1], R[r][2]);
-            T[r][1] = k_dot3<KC(I, RB_F_R, 1), KC(I, RB_F_R, 4), KC(I, RB_F_R, 7)>(KV(I, RB_F_R, 1), KV(I, RB_F_R, 4), KV(I, RB_F_R, 7), R[r][0], R[r][1], R[r][2]);
-            T[r][2] = k_dot3<KC(I, RB_F_R, 2), KC(I, RB_F_R, 5), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 2), KV(I, RB_F_R, 5), KV(I, RB_F_R, 8), R[r][0], R[r][1], R[r][2]);
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            R[r][0] = fma(cs[I], T[r][0], sn[I] * T[r][1]);
-            R[r][1] = fma(cs[I], T[r][1], -(sn[I] * T[r][0]));
-            R[r][2] = T[r][2];
-        }
+    double a[6] = {0.0, 0.0, 0.0, p.g[0], p.g[1], p.g[2]};
+    // ---- outward: world pose, velocity and acceleration of the last link
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+        rb_pose_out(p.jt[i], sn[i], cs[i], R, P);
         const double z[3] = {R[0][2], R[1][2], R[2][2]};
-        double pz[3];
+        double pz[3], s6[6], dv[6];
         rb_cross3(P, z, pz);
-        S[I][0] = z[0]; S[I][1] = z[1]; S[I][2] = z[2]; S[I][3] = pz[0]; S[I][4] = pz[1]; S[I][5] = pz[2];
+        s6[0] = z[0]; s6[1] = z[1]; s6[2] = z[2]; s6[3] = pz[0]; s6[4] = pz[1]; s6[5] = pz[2];
+        const double dqi = dq[i], ddqi = ddq[i];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) v[k] = fma(S[I][k], dq[I], v[k]);
-        rb_mcross(v, S[I], DV[I]);                           // v_I x s_I
+        for (int k = 0; k < 6; ++k) v[k] = fma(s6[k], dqi, v[k]);
+        rb_mcross(v, s6, dv);                                // v_i x s_i
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a[k] = fma(S[I][k], ddq[I], fma(DV[I][k], dq[I], a[k]));
-        double t6[6];
-        rb_mcross(a, S[I], DA[I]);
-        rb_mcross(v, DV[I], t6);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) DA[I][k] += t6[k];
-    });
+        for (int k = 0; k < 6; ++k) a[k] = fma(s6[k], ddqi, fma(dv[k], dqi, a[k]));
+    }
     // ---- inward: composites, the per-joint vectors, and the entries
     double Hc[3] = {0.0, 0.0, 0.0}, Ic[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};           // I^c (mass: model constant)
     double dHc[3] = {0.0, 0.0, 0.0}, dIc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};         // Idot^c
     double hc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, Fc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    rb_for_down<N - 1>([&](auto ic) {
-        constexpr int I = decltype(ic)::value;
-        {   // link I about the world origin
-            const double m = KV(I, RB_F_M, 0);
-            const double h[3] = {KV(I, RB_F_H, 0), KV(I, RB_F_H, 1), KV(I, RB_F_H, 2)};
-            const double Io[6] = {KV(I, RB_F_I, 0), KV(I, RB_F_I, 1), KV(I, RB_F_I, 2), KV(I, RB_F_I, 3), KV(I, RB_F_I, 4), KV(I, RB_F_I, 5)};
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; --i) {
+        const RbJointK& Jt = p.jt[i];
+        {   // link i about the world origin
+            const double m = Jt.m;
             double hw[3], T[3][3], Hm[3], IO[6];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                hw[r] = fma(R[r][0], h[0], fma(R[r][1], h[1], R[r][2] * h[2]));
-                T[r][0] = fma(R[r][0], Io[0], fma(R[r][1], Io[1], R[r][2] * Io[2]));
-                T[r][1] = fma(R[r][0], Io[1], fma(R[r][1], Io[3], R[r][2] * Io[4]));
-                T[r][2] = fma(R[r][0], Io[2], fma(R[r][1], Io[4], R[r][2] * Io[5]));
+                hw[r] = fma(R[r][0], Jt.h[0], fma(R[r][1], Jt.h[1], R[r][2] * Jt.h[2]));
+                T[r][0] = fma(R[r][0], Jt.I[0], fma(R[r][1], Jt.I[1], R[r][2] * Jt.I[2]));
+                T[r][1] = fma(R[r][0], Jt.I[1], fma(R[r][1], Jt.I[3], R[r][2] * Jt.I[4]));
+                T[r][2] = fma(R[r][0], Jt.I[2], fma(R[r][1], Jt.I[4], R[r][2] * Jt.I[5]));
             }
             double u[3];
 #pragma unroll
@@ -169,56 +194,53 @@ RB_DI void rb_rnea_derivatives(const typename M::Param& p, const double (&sn)[M:
 #pragma unroll
             for (int k = 0; k < 6; ++k) { Ic[k] += IO[k]; hc[k] += h6[k]; Fc[k] += f6[k]; }
         }
-        const double mc = KV(I, RB_F_M, 1);
-        double A[6], Bv[6], G[6], Gp[6], dv2[6];
-        rb_wimul<false>(mc, Hc, Ic, S[I], A);
-        rb_wimul<false>(0.0, dHc, dIc, S[I], Bv);            // Idot^c s
+        const double mc = Jt.mc;
+        double sI[6], dvI[6], daI[6];
+        rb_screw_cols(R, P, v, a, sI, dvI, daI);
+        double A[6], Bv[6], G[6], Gp[6];
+        {
+            double dv2[6], sh[6];
+            rb_wimul<false>(mc, Hc, Ic, sI, A);
+            rb_wimul<false>(0.0, dHc, dIc, sI, Bv);          // Idot^c s
+            rb_fcross<false>(sI, hc, sh);                    // s x* h^c
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { Gp[k] = Bv[k]; dv2[k] = 2.0 * DV[I][k]; }
-        double sh[6];
-        rb_fcross<false>(S[I], hc, sh);                      // s x* h^c
+            for (int k = 0; k < 6; ++k) { Gp[k] = Bv[k] + sh[k]; Bv[k] -= sh[k]; dv2[k] = 2.0 * dvI[k]; }
+            rb_wimul<true>(mc, Hc, Ic, dv2, Gp);
+            rb_fcross<false>(sI, Fc, G);
+            rb_wimul<true>(mc, Hc, Ic, daI, G);
+            rb_wimul<true>(0.0, dHc, dIc, dvI, G);
+            rb_fcross<true>(dvI, hc, G);
+        }
+        put(0, i, i, rb_dot6(sI, G));
+        put(1, i, i, rb_dot6(sI, Gp));
+        // walk a copy back to every j < i:  column i above the diagonal, row i below it
+        double Rt[3][3], Pt[3], vt[6], at[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { Bv[k] -= sh[k]; Gp[k] += sh[k]; }
-        rb_wimul<true>(mc, Hc, Ic, dv2, Gp);
-        rb_fcross<false>(S[I], Fc, G);
-        rb_wimul<true>(mc, Hc, Ic, DA[I], G);
-        rb_wimul<true>(0.0, dHc, dIc, DV[I], G);
-        rb_fcross<true>(DV[I], hc, G);
-        rb_for_up<0, I + 1>([&](auto mcn) {                  // rows m <= I of column I
-            constexpr int Mm = decltype(mcn)::value;
-            put_q(mcn, ic, rb_dot6(S[Mm], G));
-            put_v(mcn, ic, rb_dot6(S[Mm], Gp));
-        });
-        rb_for_up<0, I>([&](auto jc) {                       // row I of the columns j < I
-            constexpr int J = decltype(jc)::value;
-            put_q(ic, jc, fma(DA[J][0], A[0], fma(DA[J][1], A[1], fma(DA[J][2], A[2], fma(DA[J][3], A[3], fma(DA[J][4], A[4], DA[J][5] * A[5]))))) + rb_dot6(DV[J], Bv));
-            put_v(ic, jc, 2.0 * rb_dot6(DV[J], A) + rb_dot6(S[J], Bv));
-        });
-        if constexpr (I > 0) {
-            // step back to link I-1: velocities, accelerations, pose
+        for (int r = 0; r < 3; ++r) { Pt[r] = P[r]; Rt[r][0] = R[r][0]; Rt[r][1] = R[r][1]; Rt[r][2] = R[r][2]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { vt[k] = v[k]; at[k] = a[k]; }
+#pragma unroll 1
+        for (int j = i - 1; j >= 0; --j) {                   // leaving link j+1, whose screw / dv are in sI / dvI
+            const double dqn = dq[j + 1], ddqn = ddq[j + 1];
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                a[k] = fma(-S[I][k], ddq[I], fma(-DV[I][k], dq[I], a[k]));
-                v[k] = fma(-S[I][k], dq[I], v[k]);
+                at[k] = fma(-sI[k], ddqn, fma(-dvI[k], dqn, at[k]));
+                vt[k] = fma(-sI[k], dqn, vt[k]);
             }
-            double U[3][3];
+            rb_pose_back(p.jt[j + 1], sn[j + 1], cs[j + 1], Rt, Pt);
+            rb_screw_cols(Rt, Pt, vt, at, sI, dvI, daI);
+            put(0, j, i, rb_dot6(sI, G));
+            put(1, j, i, rb_dot6(sI, Gp));
+            put(0, i, j, rb_dot6(daI, A) + rb_dot6(dvI, Bv));
+            put(1, i, j, fma(2.0, rb_dot6(dvI, A), rb_dot6(sI, Bv)));
+            if (j == i - 1) {                                // the first step back is also the main state's
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                U[r][0] = fma(cs[I], R[r][0], -(sn[I] * R[r][1]));
-                U[r][1] = fma(sn[I], R[r][0], cs[I] * R[r][1]);
-                U[r][2] = R[r][2];
+                for (int r = 0; r < 3; ++r) { P[r] = Pt[r]; R[r][0] = Rt[r][0]; R[r][1] = Rt[r][1]; R[r][2] = Rt[r][2]; }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { v[k] = vt[k]; a[k] = at[k]; }
             }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                R[r][0] = k_dot3<KC(I, RB_F_R, 0), KC(I, RB_F_R, 1), KC(I, RB_F_R, 2)>(KV(I, RB_F_R, 0), KV(I, RB_F_R, 1), KV(I, RB_F_R, 2), U[r][0], U[r][1], U[r][2]);
-                R[r][1] = k_dot3<KC(I, RB_F_R, 3), KC(I, RB_F_R, 4), KC(I, RB_F_R, 5)>(KV(I, RB_F_R, 3), KV(I, RB_F_R, 4), KV(I, RB_F_R, 5), U[r][0], U[r][1], U[r][2]);
-                R[r][2] = k_dot3<KC(I, RB_F_R, 6), KC(I, RB_F_R, 7), KC(I, RB_F_R, 8)>(KV(I, RB_F_R, 6), KV(I, RB_F_R, 7), KV(I, RB_F_R, 8), U[r][0], U[r][1], U[r][2]);
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-                P[r] = -k_dot3_acc<KC(I, RB_F_T, 0), KC(I, RB_F_T, 1), KC(I, RB_F_T, 2)>(-P[r], KV(I, RB_F_T, 0), KV(I, RB_F_T, 1), KV(I, RB_F_T, 2), R[r][0], R[r][1], R[r][2]);
         }
-    });
+    }
 }
 
 // LDL^T of the upper triangle in place (A(j,i) <- L(i,j) for i > j; the diagonal keeps d_j) and its application to

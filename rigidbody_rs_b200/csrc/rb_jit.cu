@@ -80,8 +80,7 @@ const char* const kKernelExprs[RB_JIT_KERNELS] = {
     "rb_fd_kernel<CtModel<TabJit>, false>",   "rb_fd_kernel<CtModel<TabJit>, true>",
     "rb_crba_kernel<CtModel<TabJit>>",        "rb_fwd_kin_kernel<CtModel<TabJit>>",
     "rb_jac_kernel<CtModel<TabJit>>",         "rb_rollout_kernel<CtModel<TabJit>>",
-    "rb_rnea_kernel<CtModel<TabJit, float>, false>", "rb_fd_kernel<CtModel<TabJit, float>, false>",
-    "rb_rnea_deriv_kernel<CtModel<TabJit>>",  "rb_fd_deriv_kernel<CtModel<TabJit>>"};
+    "rb_rnea_kernel<CtModel<TabJit, float>, false>", "rb_fd_kernel<CtModel<TabJit, float>, false>"};
 const char* const kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DRB_DEVICE_ONLY=1"};
 
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -101,13 +100,13 @@ void mkdirs(const std::string& path) {
         if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0755);
 }
 
-// Cache file: "RBJ2" | n_names | (len, bytes)* | cubin_len | cubin
+// Cache file: "RBJ1" | n_names | (len, bytes)* | cubin_len | cubin
 bool cache_read(const std::string& file, RbJitImage& img) {
     std::ifstream f(file, std::ios::binary);
     if (!f) return false;
     char magic[4]; uint32_t cnt = 0;
     f.read(magic, 4); f.read((char*)&cnt, 4);
-    if (!f || memcmp(magic, "RBJ2", 4) != 0 || cnt != RB_JIT_KERNELS) return false;
+    if (!f || memcmp(magic, "RBJ1", 4) != 0 || cnt != RB_JIT_KERNELS) return false;
     img.lowered.clear();
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t len = 0; f.read((char*)&len, 4);
@@ -127,7 +126,7 @@ void cache_write(const std::string& file, const RbJitImage& img) {
         std::ofstream f(tmp, std::ios::binary);
         if (!f) return;
         uint32_t cnt = (uint32_t)img.lowered.size();
-        f.write("RBJ2", 4); f.write((const char*)&cnt, 4);
+        f.write("RBJ1", 4); f.write((const char*)&cnt, 4);
         for (const auto& s : img.lowered) { uint32_t len = (uint32_t)s.size(); f.write((const char*)&len, 4); f.write(s.data(), len); }
         uint64_t clen = img.cubin.size(); f.write((const char*)&clen, 8); f.write(img.cubin.data(), (std::streamsize)clen);
         if (!f) { remove(tmp.c_str()); return; }
@@ -275,24 +274,10 @@ cudaError_t j_fd_f32(const void* param, const float* q, const float* dq, const f
     void* args[] = {&ep, &q, &dq, &tau, &qdd, &B, &ld, &status};
     return cudaLaunchKernel((const void*)P->k[RB_JK_FD_F32], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
 }
-cudaError_t j_rnea_deriv(const void* param, const double* q, const double* dq, const double* ddq, double* out, size_t B, size_t ld, cudaStream_t st) {
-    const RbJitParam* P = (const RbJitParam*)param;
-    if (B == 0) return cudaSuccess;
-    RbEmptyParam ep{0};
-    void* args[] = {&ep, &q, &dq, &ddq, &out, &B, &ld};
-    return cudaLaunchKernel((const void*)P->k[RB_JK_RNEA_DERIV], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
-}
-cudaError_t j_fd_deriv(const void* param, const double* q, const double* dq, const double* tau, double* out, size_t B, size_t ld, int* status, cudaStream_t st) {
-    const RbJitParam* P = (const RbJitParam*)param;
-    if (B == 0) return cudaSuccess;
-    RbEmptyParam ep{0};
-    void* args[] = {&ep, &q, &dq, &tau, &out, &B, &ld, &status};
-    return cudaLaunchKernel((const void*)P->k[RB_JK_FD_DERIV], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
-}
 }  // namespace
 
 const RbOps* rb_ops_jit() {
     static const RbOps ops = {"jit-specialised", 0, sizeof(RbJitParam), false, &j_rnea, &j_fd, &j_rnea_aos, &j_fd_aos,
-                              &j_crba, &j_fk, &j_jac, &j_rollout, &j_rnea_f32, &j_fd_f32, &j_rnea_deriv, &j_fd_deriv};
+                              &j_crba, &j_fk, &j_jac, &j_rollout, &j_rnea_f32, &j_fd_f32};
     return &ops;
 }

@@ -5,9 +5,9 @@
 #include "rb_host_model.h"
 
 #define RB_JIT_MAX_N 12        // longest chain the register-resident unrolled kernels are compiled for
-#define RB_JIT_KERNELS 12
+#define RB_JIT_KERNELS 10
 enum : int { RB_JK_RNEA = 0, RB_JK_RNEA_AOS, RB_JK_FD, RB_JK_FD_AOS, RB_JK_CRBA, RB_JK_FK, RB_JK_JAC, RB_JK_ROLLOUT,
-             RB_JK_RNEA_F32, RB_JK_FD_F32, RB_JK_RNEA_DERIV, RB_JK_FD_DERIV };
+             RB_JK_RNEA_F32, RB_JK_FD_F32 };
 
 struct RbJitImage {             // what the compiler produces / the disk cache holds
     std::vector<char> cubin;

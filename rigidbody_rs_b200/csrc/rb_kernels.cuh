@@ -18,7 +18,6 @@ typedef unsigned long long uint64_t;
 typedef unsigned long uintptr_t;
 #endif
 #include "rb_dyn.cuh"
-#include "rb_deriv.cuh"
 #include "rb_tma.cuh"
 
 #define RB_BLOCK 128
@@ -67,12 +66,6 @@ struct RbOps {
                             size_t B, size_t ld, cudaStream_t st);
     cudaError_t (*fd_f32)(const void* param, const float* q, const float* dq, const float* tau, float* qdd,
                           size_t B, size_t ld, int* status, cudaStream_t st);
-    // optional analytical derivatives (rb_deriv.cuh), device SoA: out = [2 n^2][ld] (d tau/d q, d tau/d dq) resp.
-    // [3 n^2][ld] (d qdd/d q, d qdd/d dq, H^-1), entry r + n c of each block.  null = family has none
-    cudaError_t (*rnea_deriv)(const void* param, const double* q, const double* dq, const double* ddq, double* out,
-                              size_t B, size_t ld, cudaStream_t st);
-    cudaError_t (*fd_deriv)(const void* param, const double* q, const double* dq, const double* tau, double* out,
-                            size_t B, size_t ld, int* status, cudaStream_t st);
 };
 
 const RbOps* rb_ops_fr3();        // compile-time FR3 model (rb_kernels_fr3.cu)
@@ -204,69 +197,6 @@ rb_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict
         rb_aos_store<N>(qdd, B, rb_aos_buf, x);
     } else {
         rb_store<N>(qdd, ld, s, x);
-    }
-}
-
-// ------------------------------------------------------------------ analytical derivatives (rb_deriv.cuh)
-#ifndef RB_MINB_DERIV
-#define RB_MINB_DERIV 2
-#endif
-// out: [2 N^2][ld]: d tau_r / d q_c at entry r + N c, then d tau_r / d dq_c at N^2 + r + N c.
-template <class M>
-__global__ void __launch_bounds__(RB_BLOCK, RB_MINB_DERIV)
-rb_rnea_deriv_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
-                     const double* __restrict__ ddq, double* __restrict__ out, size_t B, size_t ld) {
-    constexpr int N = M::N;
-    const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    if (s >= B) return;
-    double a[N], b[N], c[N], sn[N], cs[N];
-    rb_load<N>(q, ld, s, a);
-    rb_sincos_all<N>(a, sn, cs);
-    rb_load<N>(dq, ld, s, b);
-    rb_load<N>(ddq, ld, s, c);
-    double* o = out + s;
-    rb_rnea_derivatives<M>(p, sn, cs, b, c,
-        [&](auto rc, auto cc, double v) { __stcs(o + (size_t)(decltype(rc)::value + N * decltype(cc)::value) * ld, v); },
-        [&](auto rc, auto cc, double v) { __stcs(o + (size_t)(N * N + decltype(rc)::value + N * decltype(cc)::value) * ld, v); });
-}
-
-// out: [3 N^2][ld]: d qdd / d q, d qdd / d dq, H^-1 (= d qdd / d tau), each entry r + N c.
-//   qdd = FD(q, dq, tau);  d qdd / d x = -H^-1 (d rnea / d x at ddq = qdd).
-// The two d rnea matrices pass through `out` (written, then read back column by column by the same thread).
-template <class M>
-__global__ void __launch_bounds__(RB_BLOCK, RB_MINB_DERIV)
-rb_fd_deriv_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
-                   const double* __restrict__ tau, double* __restrict__ out, size_t B, size_t ld, int* __restrict__ status) {
-    constexpr int N = M::N;
-    const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    if (s >= B) return;
-    double a[N], b[N], x[N], sn[N], cs[N], H[N][N], dinv[N];
-    rb_load<N>(q, ld, s, a);
-    rb_sincos_all<N>(a, sn, cs);
-    rb_load<N>(dq, ld, s, b);
-    {
-        double t[N];
-        rb_load<N>(tau, ld, s, t);
-        rb_rnea<M, false>(p, sn, cs, b, b /*unused*/, x);
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = t[i] - x[i];
-    }
-    rb_crba<M>(p, sn, cs, H);
-    const bool ok = rb_ldlt_factor<N>(H, dinv);
-    rb_ldlt_apply<N>(H, dinv, x);                            // qdd
-    double* o = out + s;
-    rb_rnea_derivatives<M>(p, sn, cs, b, x,
-        [&](auto rc, auto cc, double v) { o[(size_t)(decltype(rc)::value + N * decltype(cc)::value) * ld] = v; },
-        [&](auto rc, auto cc, double v) { o[(size_t)(N * N + decltype(rc)::value + N * decltype(cc)::value) * ld] = v; });
-    if (!ok) atomicOr(status, RB_STATUS_NOT_SPD);
-#pragma unroll 1
-    for (int c = 0; c < 3 * N; ++c) {                        // columns of the three blocks
-        double y[N];
-#pragma unroll
-        for (int r = 0; r < N; ++r) y[r] = c < 2 * N ? -o[(size_t)(r + N * c) * ld] : (r == c - 2 * N ? 1.0 : 0.0);
-        rb_ldlt_apply<N>(H, dinv, y);
-#pragma unroll
-        for (int r = 0; r < N; ++r) __stcs(o + (size_t)(r + N * c) * ld, ok ? y[r] : rb_nan<double>());
     }
 }
 
@@ -559,18 +489,6 @@ struct RbLaunch {
                                                           q_fin, dq_fin, B, ld, status, cost_w, cost);
         return cudaGetLastError();
     }
-    static cudaError_t rnea_deriv(const void* param, const double* q, const double* dq, const double* ddq, double* out,
-                                  size_t B, size_t ld, cudaStream_t st) {
-        if (B == 0) return cudaSuccess;
-        rb_rnea_deriv_kernel<M><<<grid(B), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, ddq, out, B, ld);
-        return cudaGetLastError();
-    }
-    static cudaError_t fd_deriv(const void* param, const double* q, const double* dq, const double* tau, double* out,
-                                size_t B, size_t ld, int* status, cudaStream_t st) {
-        if (B == 0) return cudaSuccess;
-        rb_fd_deriv_kernel<M><<<grid(B), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, tau, out, B, ld, status);
-        return cudaGetLastError();
-    }
     // M32 = the same policy with Real = float (fp32 mode)
     template <class M32>
     static cudaError_t rnea_f32(const void* param, const float* q, const float* dq, const float* ddq, float* tau,
@@ -593,7 +511,6 @@ struct RbLaunch {
         o.rnea = &rnea; o.fd = &fd; o.rnea_aos = &rnea_aos; o.fd_aos = &fd_aos;
         o.crba = &crba; o.fwd_kin = &fwd_kin; o.jac = &jac; o.rollout = &rollout;
         o.rnea_f32 = nullptr; o.fd_f32 = nullptr;
-        o.rnea_deriv = &rnea_deriv; o.fd_deriv = &fd_deriv;
         if constexpr (!std::is_void<M32>::value) { o.rnea_f32 = &rnea_f32<M32>; o.fd_f32 = &fd_f32<M32>; }
         return o;
     }

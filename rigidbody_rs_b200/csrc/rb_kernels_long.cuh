@@ -72,7 +72,7 @@ struct RbLaunchLong {
         RbOps o;
         o.name = name; o.n = M::N; o.param_bytes = sizeof(MP); o.shared_scratch = false;
         o.rnea = &rnea; o.fd = nullptr; o.rnea_aos = nullptr; o.fd_aos = nullptr; o.crba = &crba; o.fwd_kin = nullptr; o.jac = nullptr; o.rollout = nullptr;
-        o.rnea_f32 = nullptr; o.fd_f32 = nullptr; o.rnea_deriv = nullptr; o.fd_deriv = nullptr;
+        o.rnea_f32 = nullptr; o.fd_f32 = nullptr;
         return o;
     }
 };

@@ -406,7 +406,7 @@ cudaError_t n_rollout(const void* param, const double* q0, const double* dq0, co
 }  // namespace
 
 const RbOps* rb_ops_generic_n() {
-    static const RbOps ops = {"generic-n", 0, sizeof(RbNParam), true, &n_rnea, &n_fd, nullptr, nullptr, &n_crba, &n_fk, &n_jac, &n_rollout, nullptr, nullptr, nullptr, nullptr};
+    static const RbOps ops = {"generic-n", 0, sizeof(RbNParam), true, &n_rnea, &n_fd, nullptr, nullptr, &n_crba, &n_fk, &n_jac, &n_rollout, nullptr, nullptr};
     return &ops;
 }
 

@@ -330,11 +330,7 @@ def test_analytical_derivatives_fr3_all_families(rb, oracle_fr3):
     Dq, Dv = ch.rnea_derivatives(q, dq, ddq)
     Aq, Av, Mi = ch.fd_derivatives(q, dq, tau)
     fams = []
-    for mb in _variants(rb, FR3):
-        if mb.kernel_variant == "generic-n":
-            with pytest.raises(rb.RigidBodyError):
-                mb.rnea_derivatives(q, dq, ddq, layout="aos")
-            continue
+    for mb in _variants(rb, FR3):                # the derivative kernels are model-agnostic: same code under every family
         fams.append(mb.kernel_variant)
         gq, gv = _unpack(mb.rnea_derivatives(q, dq, ddq, layout="aos"), 7, 2)
         for got, want in ((gq, Dq), (gv, Dv)):
@@ -344,7 +340,10 @@ def test_analytical_derivatives_fr3_all_families(rb, oracle_fr3):
         for got, want in ((fq, Aq), (fv, Av), (fm, Mi)):
             err = np.abs(got - want).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(want).reshape(B, -1).max(1))
             assert err.max() < 1e-8, (mb.kernel_variant, err.max())
-    assert fams == ["fr3-specialised", "jit-specialised", "generic-7"]
+    assert fams == ["fr3-specialised", "jit-specialised", "generic-7", "generic-n"]
+    with pytest.raises(rb.RigidBodyError):       # beyond 12 joints: unsupported, not wrong
+        z = np.zeros((2, 32))
+        rb.Multibody.from_urdf(CHAIN32).rnea_derivatives(z, z, z, layout="aos")
     # device SoA tensors, and one state
     import torch
     mb = rb.Multibody.from_urdf(FR3)
