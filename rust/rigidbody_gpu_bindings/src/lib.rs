@@ -61,7 +61,31 @@ extern "C" {
     fn multibody_rollout(g: *mut RbGpu, q0: *const f64, dq0: *const f64, tau: *const f64, dt: f64, horizon: c_int,
                          q_traj: *mut f64, dq_traj: *mut f64, q_final: *mut f64, dq_final: *mut f64,
                          n_traj: usize, ld: usize, layout: RbLayout, mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_fwd_kin_batch(g: *mut RbGpu, q: *const f64, xyz: *mut f64, n_states: usize, ld: usize, layout: RbLayout,
+                               mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_jac_batch(g: *mut RbGpu, q: *const f64, j: *mut f64, n_states: usize, ld: usize, layout: RbLayout,
+                           mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_rollout_cost(g: *mut RbGpu, q0: *const f64, dq0: *const f64, tau: *const f64, dt: f64, horizon: c_int,
+                              w: *const RbQuadCost, cost: *mut f64, q_final: *mut f64, dq_final: *mut f64,
+                              n_traj: usize, ld: usize, layout: RbLayout, mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_rnea_derivatives_batch(g: *mut RbGpu, q: *const f64, dq: *const f64, ddq: *const f64, out: *mut f64,
+                                        n_states: usize, ld: usize, layout: RbLayout, mem: RbMem, stream: *mut c_void) -> c_int;
+    fn multibody_fd_derivatives_batch(g: *mut RbGpu, q: *const f64, dq: *const f64, tau: *const f64, out: *mut f64,
+                                      n_states: usize, ld: usize, layout: RbLayout, mem: RbMem, stream: *mut c_void) -> c_int;
     fn multibody_gpu_sync(g: *mut RbGpu) -> c_int;
+}
+
+/// Quadratic running / terminal cost of `multibody_rollout_cost` (include/rigidbody.h RbQuadCost): six host arrays of
+/// n per-joint values each; a null pointer means zeros.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct RbQuadCost {
+    pub q_ref: *const f64,
+    pub w_q: *const f64,
+    pub w_dq: *const f64,
+    pub w_tau: *const f64,
+    pub w_q_final: *const f64,
+    pub w_dq_final: *const f64,
 }
 
 #[derive(Debug)]
@@ -79,7 +103,9 @@ fn check(rc: c_int) -> Result<(), RbError> {
 }
 
 // ------------------------------------------------------------------ Multibody -> flattened descriptor
-/// Owned arrays behind an `RbChainDesc`; joint i's parent is joint i-1 (the reference is a serial chain).
+/// Owned arrays behind an `RbChainDesc`; joint i's parent is joint i-1 (the reference is a serial chain; the C side
+/// also accepts a `parent` index array for kinematic trees, which `Multibody` cannot express).  Axes other than +z
+/// are honoured by the engine (the reference's rnea / crba ignore them, multibody.rs:29,130).
 pub struct ChainArrays {
     pub axis: Vec<f64>,
     pub parent_rot: Vec<f64>,
@@ -186,6 +212,50 @@ impl GpuMultibody {
         }
         check(unsafe { multibody_rollout(self.raw, q0.as_ptr(), dq0.as_ptr(), tau.as_ptr(), dt, horizon as c_int, q_traj.as_mut_ptr(), dq_traj.as_mut_ptr(),
                                          ptr::null_mut(), ptr::null_mut(), n_traj, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// Tip translations (lib.rs:46-57) and tip-frame Jacobians (lib.rs:60-70), batched; host slices.
+    pub fn fwd_kin_batch(&mut self, q: &[f64], xyz: &mut [f64], n_states: usize, layout: RbLayout) -> Result<(), RbError> {
+        self.check_len("q", q.len(), self.n, n_states)?;
+        self.check_len("xyz", xyz.len(), 3, n_states)?;
+        check(unsafe { multibody_fwd_kin_batch(self.raw, q.as_ptr(), xyz.as_mut_ptr(), n_states, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    pub fn jac_batch(&mut self, q: &[f64], jac: &mut [f64], n_states: usize, layout: RbLayout) -> Result<(), RbError> {
+        self.check_len("q", q.len(), self.n, n_states)?;
+        self.check_len("jac", jac.len(), 6 * self.n, n_states)?;
+        check(unsafe { multibody_jac_batch(self.raw, q.as_ptr(), jac.as_mut_ptr(), n_states, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// Rollout fused with a quadratic cost: one scalar per trajectory (sampling-based MPC); nothing but `tau` is read
+    /// per step and no trajectory is written.
+    #[allow(clippy::too_many_arguments)]
+    pub fn rollout_cost(&mut self, q0: &[f64], dq0: &[f64], tau: &[f64], dt: f64, horizon: usize, w: &RbQuadCost, cost: &mut [f64],
+                        n_traj: usize, layout: RbLayout) -> Result<(), RbError> {
+        self.check_len("q0", q0.len(), self.n, n_traj)?;
+        self.check_len("dq0", dq0.len(), self.n, n_traj)?;
+        self.check_len("tau", tau.len(), self.n * horizon, n_traj)?;
+        self.check_len("cost", cost.len(), 1, n_traj)?;
+        check(unsafe { multibody_rollout_cost(self.raw, q0.as_ptr(), dq0.as_ptr(), tau.as_ptr(), dt, horizon as c_int, w, cost.as_mut_ptr(),
+                                              ptr::null_mut(), ptr::null_mut(), n_traj, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// d tau / d q and d tau / d dq (2 n*n doubles per state, block b entry r + n*c); chains of at most 12 joints.
+    pub fn rnea_derivatives_batch(&mut self, q: &[f64], dq: &[f64], ddq: &[f64], out: &mut [f64], n_states: usize, layout: RbLayout) -> Result<(), RbError> {
+        for (w, s) in [("q", q.len()), ("dq", dq.len()), ("ddq", ddq.len())] {
+            self.check_len(w, s, self.n, n_states)?;
+        }
+        self.check_len("out", out.len(), 2 * self.n * self.n, n_states)?;
+        check(unsafe { multibody_rnea_derivatives_batch(self.raw, q.as_ptr(), dq.as_ptr(), ddq.as_ptr(), out.as_mut_ptr(), n_states, 0, layout, RbMem::Host, ptr::null_mut()) })
+    }
+
+    /// d qdd / d q, d qdd / d dq and H^-1 (3 n*n doubles per state) of qdd = forward_dynamics(q, dq, tau).
+    pub fn fd_derivatives_batch(&mut self, q: &[f64], dq: &[f64], tau: &[f64], out: &mut [f64], n_states: usize, layout: RbLayout) -> Result<(), RbError> {
+        for (w, s) in [("q", q.len()), ("dq", dq.len()), ("tau", tau.len())] {
+            self.check_len(w, s, self.n, n_states)?;
+        }
+        self.check_len("out", out.len(), 3 * self.n * self.n, n_states)?;
+        check(unsafe { multibody_fd_derivatives_batch(self.raw, q.as_ptr(), dq.as_ptr(), tau.as_ptr(), out.as_mut_ptr(), n_states, 0, layout, RbMem::Host, ptr::null_mut()) })
     }
 
     /// Raw handle for device-pointer calls (RbMem::Device) from CUDA-aware callers.
