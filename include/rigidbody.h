@@ -186,6 +186,13 @@ int multibody_forward_dynamics_batch_f32(RbGpu* g, const float* q, const float* 
 int multibody_crba_batch(RbGpu* g, const double* q, double* H,
                          size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
 
+/* New: inverse AND forward dynamics of the same states in one call -- tau = rnea(q, dq, ddq) and
+ * qdd = forward_dynamics(q, dq, tau_in).  Same kernels and results as the two separate calls; q and dq cross the bus
+ * (host batches) and are staged once instead of twice.  out holds 2n entries per state: tau then qdd
+ * (SOA: out[(blk*n + i)*ld + s];  AOS: out[s*2n + blk*n + i]). */
+int multibody_rnea_fd_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, const double* tau_in,
+                            double* out, size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
+
 /* New (README.md:18 lists "Differentiability" as not done): analytical first derivatives, for serial chains of at most
  * 12 joints (the register-resident kernel families; RB_ERR_UNSUPPORTED otherwise).
  * multibody_rnea_derivatives_batch: out holds 2 n*n entries per state, block 0 = d tau / d q, block 1 = d tau / d dq of

@@ -246,6 +246,16 @@ class Multibody:
             return self._call_f32(lib.multibody_forward_dynamics_batch_f32, q, dq, tau, out)
         return self._call(lib.multibody_forward_dynamics_batch, (q, dq, tau), ("q", "dq", "tau"), (n, n, n), n, layout, out)
 
+    def rnea_fd(self, q, dq, ddq, tau, layout="soa", out=None):
+        """tau_out = rnea(q, dq, ddq) and qdd = forward_dynamics(q, dq, tau) of the same states in one call
+        (include/rigidbody.h multibody_rnea_fd_batch): q and dq are transferred once.  Returns the packed result,
+        soa [2n, B] (rows 0..n-1 tau, n..2n-1 qdd) or aos [B, 2n]; one state -> (tau, qdd)."""
+        n = self.n
+        D = self._call(lib.multibody_rnea_fd_batch, (q, dq, ddq, tau), ("q", "dq", "ddq", "tau"), (n, n, n, n), 2 * n, layout, out)
+        if len(D.shape) == 1:
+            return D[:n], D[n:]
+        return D
+
     def rnea_derivatives(self, q, dq, ddq, layout="soa", out=None):
         """Analytical d tau / d q and d tau / d dq of tau = rnea(q, dq, ddq), packed as the C ABI returns them
         (include/rigidbody.h multibody_rnea_derivatives_batch): 2 n*n entries per state, block b entry r + n*c.

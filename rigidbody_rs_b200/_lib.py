@@ -63,6 +63,7 @@ PROTOTYPES = {
     "multibody_forward_dynamics_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_rnea_batch_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
     "multibody_forward_dynamics_batch_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
+    "multibody_rnea_fd_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_rnea_derivatives_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_fd_derivatives_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),
     "multibody_crba_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _i, _vp]),

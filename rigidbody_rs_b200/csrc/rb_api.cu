@@ -268,8 +268,8 @@ int fetch_status(RbGpu* g) {
 // ---- a batched op, described once, run from device or host memory ----
 struct OpDesc {
     int n_in;                    // number of input state arrays
-    const double* in[3];
-    int in_per[3];               // doubles per state of each input
+    const double* in[4];
+    int in_per[4];               // doubles per state of each input
     double* out;
     int out_per;                 // doubles per state of the output
     // launch on SoA device buffers with leading dimension ld
@@ -312,7 +312,7 @@ int run_device(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout,
     for (int k = 0; k < op.n_in; ++k) in_d += (size_t)op.in_per[k];
     int rc = g->in[0].ensure(in_d * B * sizeof(double)); if (rc) return rc;
     rc = g->out[0].ensure((size_t)op.out_per * B * sizeof(double)); if (rc) return rc;
-    const double* soa_in[3]; size_t off = 0;
+    const double* soa_in[4]; size_t off = 0;
     for (int k = 0; k < op.n_in; ++k) {
         double* dst = g->in[0].p + off * B;
         cudaError_t e = rb_launch_aos_to_soa(op.in[k], dst, op.in_per[k], B, B, st);
@@ -355,7 +355,7 @@ int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
         if (c >= kSlots) RB_CUDA(cudaStreamWaitEvent(g->s_h2d, g->ev_comp[s], 0));
         // AoS: the landing zone tmp[s] also carried chunk c-kSlots' output to the host
         if (c >= kSlots && aos) RB_CUDA(cudaStreamWaitEvent(g->s_h2d, g->ev_d2h[s], 0));
-        const double* soa_in[3]; size_t off = 0;
+        const double* soa_in[4]; size_t off = 0;
         for (int k = 0; k < op.n_in; ++k) {
             double* dst = g->in[s].p + off * chunk;
             if (!aos) {
@@ -373,7 +373,7 @@ int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
         if (c >= kSlots) RB_CUDA(cudaStreamWaitEvent(g->stream, g->ev_d2h[s], 0));   // output slot drained
         if (aos && direct_aos) {
             // inputs landed in tmp[s] as AoS; the kernel reads them there and writes AoS output into out[s]
-            const double* aos_in[3]; off = 0;
+            const double* aos_in[4]; off = 0;
             for (int k = 0; k < op.n_in; ++k) { aos_in[k] = g->tmp[s].p + off * chunk; off += (size_t)op.in_per[k]; }
             cudaError_t e = op.launch_aos(g, aos_in, g->out[s].p, cnt, g->stream);
             g->launches += 1;
@@ -570,6 +570,26 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
                   return g->ops->fd_aos(g->param.data(), in[0], in[1], in[2], out, B, g->d_status, st);
               },
               [](RbGpu* g) { return g->ops->fd_aos != nullptr; }};
+    return run_op(g, op, n_states, ld, layout, mem, stream, true);
+}
+
+// ---- inverse and forward dynamics of the same states in one call: q and dq travel (and are staged) once ----
+extern "C" int multibody_rnea_fd_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, const double* tau_in,
+                                       double* out, size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    const int n = g->model.n;
+    OpDesc op{4, {q, dq, ddq, tau_in}, {n, n, n, n}, out, 2 * n,
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+                  const int n = g->model.n;
+                  {
+                      ScratchOrder so(g, RB_TABLE(g, rnea), st);
+                      cudaError_t e = RB_TABLE(g, rnea)->rnea(RB_PARAM(g, rnea), in[0], in[1], in[2], out, B, ld, st);
+                      if (e != cudaSuccess) return e;
+                  }
+                  g->launches += 1;
+                  ScratchOrder so(g, RB_TABLE(g, fd), st);
+                  return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[3], out + (size_t)n * ld, B, ld, g->d_status, st);
+              }};
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }
 

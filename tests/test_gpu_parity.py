@@ -121,6 +121,28 @@ def test_rnea_fd_host_batches(mb_fr3, oracle_fr3, B, layout):
     assert state_err(mb_fr3.forward_dynamics(q, dq, tau, layout=layout), want_a, ax).max() < TOL
 
 
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_rnea_fd_one_call_equals_two_calls(rb, mb_fr3, oracle_fr3, layout):
+    """multibody_rnea_fd_batch: same kernels, q and dq staged once; host and device, both layouts, chunked sizes."""
+    import torch
+    B = 3000
+    q, dq, ddq, tau = _states(oracle_fr3, B)
+    if layout == "aos":
+        q, dq, ddq, tau = (np.ascontiguousarray(x.T) for x in (q, dq, ddq, tau))
+    both = mb_fr3.rnea_fd(q, dq, ddq, tau, layout=layout)
+    t, a = mb_fr3.rnea(q, dq, ddq, layout=layout), mb_fr3.forward_dynamics(q, dq, tau, layout=layout)
+    want = np.concatenate([t, a], axis=0 if layout == "soa" else 1)
+    assert both.shape == want.shape and np.array_equal(both, want)
+    dev = torch.device("cuda:0")
+    tq, tdq, tddq, ttau = (torch.from_numpy(x).to(dev) for x in (q, dq, ddq, tau))
+    got = mb_fr3.rnea_fd(tq, tdq, tddq, ttau, layout=layout)
+    mb_fr3.sync()
+    assert np.array_equal(got.cpu().numpy(), want)
+    t1, a1 = mb_fr3.rnea_fd(q[0] if layout == "aos" else q[:, 0], dq[0] if layout == "aos" else dq[:, 0],
+                            ddq[0] if layout == "aos" else ddq[:, 0], tau[0] if layout == "aos" else tau[:, 0])
+    assert np.array_equal(t1, t[0] if layout == "aos" else t[:, 0]) and np.array_equal(a1, a[0] if layout == "aos" else a[:, 0])
+
+
 def test_empty_batch_and_bad_shapes(mb_fr3):
     z = np.zeros((7, 0))
     assert mb_fr3.rnea(z, z, z).shape == (7, 0)
