@@ -472,7 +472,7 @@ rbh_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
     double* wsm = rbw_sm + RBH_MODEL + (size_t)w * RBH_PER_WARP;
     double* Lt = wsm + h * 32 * RBW_LDL;                     // this state's [32][RBW_LDL] columns of L D
     double* Sb = wsm + RBH_LT + h * 32 * 6;                  // this state's [32][6] screws
-    double* Fb = Lt;                                         // hand-over buffer [32][8] (dead before Lt is written)
+    double* Fb = Lt;                                         // hand-over buffer [7][32] (dead before Lt is written)
     double* io = wsm + RBH_LT + 2 * 32 * 6;                  // [3][32][RBW_IOS]
     double* ob = io + 3 * 32 * RBW_IOS;                      // [32][RBW_IOS]
     if (w == 0) {                                            // model -> shared memory; idle joints: identity, no mass
@@ -609,27 +609,28 @@ rbh_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             suffix2<9>(ci0, ci1, r);
             {
                 const double2 mc = mdl2(22);
-                double Fn[3], Ff[3];
+                double Fn0[3], Ff0[3], Fn1[3], Ff1[3];
                 double2* S2 = reinterpret_cast<double2*>(Sb + j0 * 6);
-                double2* F2 = reinterpret_cast<double2*>(Fb + j0 * 8);
-                comp_times_screw(mc.x, ci0, z0, v0, Fn, Ff);
+                comp_times_screw(mc.x, ci0, z0, v0, Fn0, Ff0);
+                comp_times_screw(mc.y, ci1, z1, v1, Fn1, Ff1);
                 S2[0] = make_double2(z0[0], z0[1]); S2[1] = make_double2(z0[2], v0[0]); S2[2] = make_double2(v0[1], v0[2]);
-                F2[0] = make_double2(Fn[0], Fn[1]); F2[1] = make_double2(Fn[2], Ff[0]); F2[2] = make_double2(Ff[1], Ff[2]);
-                F2[3] = make_double2(act0 ? b0 : 0.0, 0.0);
-                comp_times_screw(mc.y, ci1, z1, v1, Fn, Ff);
                 S2[3] = make_double2(z1[0], z1[1]); S2[4] = make_double2(z1[2], v1[0]); S2[5] = make_double2(v1[1], v1[2]);
-                F2[4] = make_double2(Fn[0], Fn[1]); F2[5] = make_double2(Fn[2], Ff[0]); F2[6] = make_double2(Ff[1], Ff[2]);
-                F2[7] = make_double2(act1 ? b1 : 0.0, 0.0);
+                // hand-over buffer, component-major [7][32]: the lane's two joints are one 16-byte store per component
+                // (a joint-major [32][8] layout cost 16-way bank conflicts on both sides)
+                double2* F2 = reinterpret_cast<double2*>(Fb + j0);
+                F2[0 * 16] = make_double2(Fn0[0], Fn1[0]); F2[1 * 16] = make_double2(Fn0[1], Fn1[1]); F2[2 * 16] = make_double2(Fn0[2], Fn1[2]);
+                F2[3 * 16] = make_double2(Ff0[0], Ff1[0]); F2[4 * 16] = make_double2(Ff0[1], Ff1[1]); F2[5 * 16] = make_double2(Ff0[2], Ff1[2]);
+                F2[6 * 16] = make_double2(act0 ? b0 : 0.0, act1 ? b1 : 0.0);
             }
             __syncwarp();
             // ================= matrix phase: lane r <-> rows r (lo) and r + 16 (hi) of state st
             double alo[16], ahi[32], blo, bhi;
             {
-                const double2* FL = reinterpret_cast<const double2*>(Fb + r * 8);
-                const double2* FH = reinterpret_cast<const double2*>(Fb + (r + 16) * 8);
-                const double2 l0 = FL[0], l1 = FL[1], l2 = FL[2], l3 = FL[3];
-                const double2 h0 = FH[0], h1 = FH[1], h2 = FH[2], h3 = FH[3];
-                blo = l3.x; bhi = h3.x;
+                double2 l0, l1, l2, h0, h1, h2;
+                l0.x = Fb[0 * 32 + r]; l0.y = Fb[1 * 32 + r]; l1.x = Fb[2 * 32 + r]; l1.y = Fb[3 * 32 + r]; l2.x = Fb[4 * 32 + r]; l2.y = Fb[5 * 32 + r];
+                h0.x = Fb[0 * 32 + r + 16]; h0.y = Fb[1 * 32 + r + 16]; h1.x = Fb[2 * 32 + r + 16]; h1.y = Fb[3 * 32 + r + 16];
+                h2.x = Fb[4 * 32 + r + 16]; h2.y = Fb[5 * 32 + r + 16];
+                blo = Fb[6 * 32 + r]; bhi = Fb[6 * 32 + r + 16];
                 __syncwarp();                                // Fb (= Lt) is free from here on
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
