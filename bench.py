@@ -358,7 +358,7 @@ def run_other(args, rank, local_rank, world):
         def step():
             mb.rnea(q, dq, x3, out=out)
             mb.forward_dynamics(q, dq, tau_in, out=out2)
-        units_rank, flops, label = 2.0 * B, (9476.0 + 53800.0) / 2, "rb_long_rnea_kernel + rbw_fd_kernel"
+        units_rank, flops, label = 2.0 * B, (9476.0 + 53800.0) / 2, "rb_long_rnea_kernel + rbh_fd_kernel"
     for _ in range(args.warmup):
         step()
     fp64_peak = mb.fp64_peak_tflops(100)

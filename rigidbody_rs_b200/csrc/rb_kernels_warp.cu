@@ -1,4 +1,5 @@
-// rb_kernels_warp.cu -- forward dynamics of long chains (13..32 joints): one WARP per state, one LANE per joint.
+// rb_kernels_warp.cu -- forward dynamics of long chains (13..32 joints): the chain spread over the lanes of a warp
+// (rbw_fd_kernel: one warp per state, one lane per joint; rbh_fd_kernel, the default: half a warp per state).
 //
 // A 32-joint state needs a 528-entry mass matrix: no thread can hold it, and streaming it through HBM made the
 // first long-chain path spend its time on memory and on a 400 KB unrolled CRBA.  Here a warp owns a state and
