@@ -363,7 +363,8 @@ rbw_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
 #ifndef RBW_HWARPS
 #define RBW_HWARPS 8
 #endif
-constexpr int RBH_LT = 2 * 32 * RBW_LDL;                                  // stored columns of L D, both states
+constexpr int RBH_LTS = 16 * RBW_LDL;                                     // stored columns of L D of one state, folded
+constexpr int RBH_LT = 2 * RBH_LTS;
 constexpr int RBH_PER_WARP = RBH_LT + 2 * 32 * 6 + 4 * 32 * RBW_IOS;      // + screws + staging (in 3, out 1)
 constexpr int RBH_MODEL = 24 * 32;                                        // block-shared model constants [e][joint]
 
@@ -471,7 +472,9 @@ rbh_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
     const int h = lane >> 4, r = lane & 15;
     double* msm = rbw_sm;                                    // [24][32] model constants, [23][*] = composite mass
     double* wsm = rbw_sm + RBH_MODEL + (size_t)w * RBH_PER_WARP;
-    double* Lt = wsm + h * 32 * RBW_LDL;                     // this state's [32][RBW_LDL] columns of L D
+    // this state's columns of L D, folded into 16 rows: column k < 16 sits in row k at positions k..31, column k >= 16 in
+    // the unused head of row 31-k at positions 0..31-k (its last entry lands on row 31-k's diagonal, long dead by then)
+    double* Lt = wsm + h * RBH_LTS;
     double* Sb = wsm + RBH_LT + h * 32 * 6;                  // this state's [32][6] screws
     double* Fb = Lt;                                         // hand-over buffer [7][32] (dead before Lt is written)
     double* io = wsm + RBH_LT + 2 * 32 * 6;                  // [3][32][RBW_IOS]
@@ -653,11 +656,17 @@ rbh_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             double dinv_lo = 0.0, dinv_hi = 0.0;
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-                if (k < 16) Lt[k * RBW_LDL + r] = alo[k & 15];
-                Lt[k * RBW_LDL + r + 16] = ahi[k];
+                // column k, entry i at COL + i
+                const int COL = k < 16 ? k * RBW_LDL : (31 - k) * RBW_LDL - k;
+                if (k < 16) {
+                    Lt[COL + r] = alo[k & 15];
+                    Lt[COL + r + 16] = ahi[k];
+                } else if (r + 16 >= k) {
+                    Lt[COL + r + 16] = ahi[k];
+                }
                 const double bk = __shfl_sync(FULL, k < 16 ? blo : bhi, k & 15, 16);
                 __syncwarp();
-                const double d = Lt[k * RBW_LDL + k];
+                const double d = Lt[COL + k];
                 ok = ok && (d > 0.0);
                 const double dinv = rb_rcp_pos(d);
                 if (k < 16) { if (r == k) dinv_lo = dinv; } else { if (r + 16 == k) dinv_hi = dinv; }
@@ -665,14 +674,17 @@ rbh_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
                 bhi = fma(nhi, bk, bhi);
                 double nlo = 0.0;
                 if (k < 15) { nlo = (r > k) ? -alo[k & 15] * dinv : 0.0; blo = fma(nlo, bk, blo); }
+                const bool aligned = ((COL & 1) == 0);       // pairs (even i, i + 1) are 16-byte aligned
                 if (((k + 1) & 1) && k + 1 < 32) {
-                    const double c1 = Lt[k * RBW_LDL + k + 1];
+                    const double c1 = Lt[COL + k + 1];
                     ahi[(k + 1) & 31] = fma(nhi, c1, ahi[(k + 1) & 31]);
                     if (k + 1 < 16) alo[(k + 1) & 15] = fma(nlo, c1, alo[(k + 1) & 15]);
                 }
 #pragma unroll
                 for (int i = (k + 2) & ~1; i < 32; i += 2) {
-                    const double2 c2 = *reinterpret_cast<const double2*>(Lt + k * RBW_LDL + i);
+                    double2 c2;
+                    if (aligned) c2 = *reinterpret_cast<const double2*>(Lt + COL + i);
+                    else { c2.x = Lt[COL + i]; c2.y = Lt[COL + i + 1]; }
                     ahi[i] = fma(nhi, c2.x, ahi[i]);
                     ahi[i + 1] = fma(nhi, c2.y, ahi[i + 1]);
                     if (i + 1 < 16) {
@@ -688,8 +700,8 @@ rbh_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
                 const double mine = i < 16 ? xlo * dinv_lo : xhi * dinv_hi;
                 const double xi = __shfl_sync(FULL, mine, i & 15, 16);
                 if (i < 16) { if (r == i) xlo = xi; } else { if (r + 16 == i) xhi = xi; }
-                if (i > 16) { const double c = Lt[(r + 16) * RBW_LDL + i]; if (r + 16 < i) xhi = fma(-c, xi, xhi); }
-                const double c = Lt[r * RBW_LDL + i];
+                if (i > 16 && r + 16 < i) xhi = fma(-Lt[(15 - r) * RBW_LDL - (r + 16) + i], xi, xhi);   // column r + 16, entry i
+                const double c = Lt[r * RBW_LDL + i];                                                  // column r, entry i
                 if (r < i) xlo = fma(-c, xi, xlo);
             }
             if (r == 0) xlo *= dinv_lo;
