@@ -316,6 +316,45 @@ rbn_rollout_kernel(RbNParam P, const double* __restrict__ q0, const double* __re
     if (!all_ok) atomicOr(status, RB_STATUS_NOT_SPD);
 }
 
+// ---- rollout of serial chains of <= 32 joints: one forward-dynamics launch (rb_kernels_warp.cu) + one integration
+// launch per step.  The per-thread factorisation of rbn_rollout_kernel touches O(n^3) scratch words per step; here the
+// state (q, dq) and qdd of all trajectories live in three [n][B] scratch arrays between the launches.
+__global__ void __launch_bounds__(RB_BLOCK)
+rbn_euler_kernel(int n, double dt, double* __restrict__ qc, double* __restrict__ dqc, const double* __restrict__ qdd,
+                 const double* __restrict__ tau_t, double* __restrict__ q_out, double* __restrict__ dq_out, size_t B, size_t ldc,
+                 size_t ld, const double* __restrict__ cost_w, double* __restrict__ cost, int first, int last,
+                 double* __restrict__ q_fin, double* __restrict__ dq_fin) {
+    const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
+    if (s >= B) return;
+    double c = 0.0, term = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double dqn = fma(dt, qdd[(size_t)i * ldc + s], dqc[(size_t)i * ldc + s]);
+        const double qn = fma(dt, dqn, qc[(size_t)i * ldc + s]);
+        dqc[(size_t)i * ldc + s] = dqn; qc[(size_t)i * ldc + s] = qn;
+        if (q_out) __stcs(q_out + (size_t)i * ld + s, qn);
+        if (dq_out) __stcs(dq_out + (size_t)i * ld + s, dqn);
+        if (last) {
+            if (q_fin) q_fin[(size_t)i * ld + s] = qn;
+            if (dq_fin) dq_fin[(size_t)i * ld + s] = dqn;
+        }
+        if (cost) {
+            const double e = qn - cost_w[RB_CW_QREF * RB_MAX_N + i];
+            const double u = __ldcs(tau_t + (size_t)i * ld + s);
+            c = fma(cost_w[RB_CW_Q * RB_MAX_N + i] * e, e, c);
+            c = fma(cost_w[RB_CW_DQ * RB_MAX_N + i] * dqn, dqn, c);
+            c = fma(cost_w[RB_CW_TAU * RB_MAX_N + i] * u, u, c);
+            if (last) {
+                term = fma(cost_w[RB_CW_QF * RB_MAX_N + i] * e, e, term);
+                term = fma(cost_w[RB_CW_DQF * RB_MAX_N + i] * dqn, dqn, term);
+            }
+        }
+    }
+    if (cost) {
+        const double J = fma(dt, c, first ? 0.0 : cost[s]);
+        cost[s] = last ? J + term : J;                       // a non-SPD step leaves NaN in qdd, hence in q, hence here
+    }
+}
+
 namespace {
 unsigned ngrid(const RbNParam* P, size_t B) {
     size_t want = (B + RB_BLOCK - 1) / RB_BLOCK;
@@ -400,6 +439,36 @@ cudaError_t n_rollout(const void* param, const double* q0, const double* dq0, co
                       const double* cost_w, double* cost, cudaStream_t st) {
     const RbNParam* P = (const RbNParam*)param;
     if (B == 0) return cudaSuccess;
+#if RB_WARP_FD
+    if (P->n <= 32 && !P->tree && horizon > 0) {
+        const int n = P->n;
+        const size_t cap = P->slots * P->threads / ((size_t)4 * n);          // trajectories the scratch holds at once
+        for (size_t off = 0; off < B; off += cap) {
+            const size_t cnt = B - off < cap ? B - off : cap;
+            double* qc = P->scratch; double* dqc = qc + (size_t)n * cnt; double* tc = dqc + (size_t)n * cnt; double* acc = tc + (size_t)n * cnt;
+            cudaError_t e = cudaMemcpy2DAsync(qc, cnt * sizeof(double), q0 + off, ld * sizeof(double), cnt * sizeof(double), n, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpy2DAsync(dqc, cnt * sizeof(double), dq0 + off, ld * sizeof(double), cnt * sizeof(double), n, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            const size_t step = (size_t)n * ld;
+            for (int t = 0; t < horizon; ++t) {
+                const double* tau_t = tau + (size_t)t * step + off;
+                // tau rows have stride ld, the carried state stride cnt: one kernel call wants one stride
+                e = cudaMemcpy2DAsync(tc, cnt * sizeof(double), tau_t, ld * sizeof(double), cnt * sizeof(double), n, cudaMemcpyDeviceToDevice, st);
+                if (e != cudaSuccess) return e;
+                e = rb_launch_warp_fd(P->model, n, qc, dqc, tc, acc, cnt, cnt, status, st);
+                if (e != cudaSuccess) return e;
+                rbn_euler_kernel<<<(unsigned)((cnt + RB_BLOCK - 1) / RB_BLOCK), RB_BLOCK, 0, st>>>(
+                    n, dt, qc, dqc, acc, tau_t, q_traj ? q_traj + (size_t)t * step + off : nullptr,
+                    dq_traj ? dq_traj + (size_t)t * step + off : nullptr, cnt, cnt, ld, cost_w, cost ? cost + off : nullptr,
+                    t == 0, t == horizon - 1, q_fin ? q_fin + off : nullptr, dq_fin ? dq_fin + off : nullptr);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+            }
+        }
+        return cudaSuccess;
+    }
+#endif
     rbn_rollout_kernel<<<ngrid(P, B), RB_BLOCK, 0, st>>>(*P, q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_fin, dq_fin, B, ld, status, cost_w, cost);
     return cudaGetLastError();
 }

@@ -244,6 +244,23 @@ def test_rollout_matches_oracle(rb, oracle_fr3):
         np.testing.assert_array_equal(qa.transpose(0, 2, 1), qt)
 
 
+def test_rollout_chain32(rb, mb_chain32, oracle_chain32):
+    """Long-chain rollouts: one forward-dynamics launch (lane-per-joint kernel) + one integration launch per step."""
+    B, H, dt = 70, 12, 1e-3
+    rng = np.random.default_rng(5)
+    q, dq = rng.uniform(-3, 3, (32, B)), rng.uniform(-1, 1, (32, B))
+    tau = rng.uniform(-20, 20, (H, 32, B))
+    oq, odq = oracle_chain32.rollout_batch(q, dq, tau, dt)
+    qt, dqt, qf, dqf = mb_chain32.rollout(q, dq, tau, dt, final=True)
+    assert state_err(qt, oq, 1).max() < 1e-9 and state_err(dqt, odq, 1).max() < 1e-8
+    np.testing.assert_array_equal(qf, qt[-1]); np.testing.assert_array_equal(dqf, dqt[-1])
+    w = np.linspace(0.5, 2.0, 32)
+    c = mb_chain32.rollout_cost(q, dq, tau, dt, w_q=w, w_dq=0.1 * w, w_tau=1e-3 * w, w_q_final=3 * w)
+    want = ((w[None, :, None] * qt ** 2).sum(1) + (0.1 * w[None, :, None] * dqt ** 2).sum(1) + (1e-3 * w[None, :, None] * tau ** 2).sum(1)).sum(0) * dt \
+        + (3 * w[:, None] * qt[-1] ** 2).sum(0)
+    np.testing.assert_allclose(c, want, rtol=1e-12)
+
+
 def test_rollout_cost_matches_trajectory_cost(rb, oracle_fr3):
     """The fused rollout+cost kernel returns exactly the quadratic cost of the trajectory the oracle integrates."""
     import torch
