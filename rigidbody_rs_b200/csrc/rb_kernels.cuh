@@ -200,6 +200,78 @@ rb_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict
     }
 }
 
+// ------------------------------------------------------------------ persistent variants with register prefetch (experiment)
+// A thread walks states s, s + T, s + 2T, ... and issues the loads of its NEXT state before computing the current one,
+// so every warp always has arithmetic to overlap its own memory latency (the one-shot kernels rely on other warps).
+#ifndef RB_PREFETCH
+#define RB_PREFETCH 0
+#endif
+#if RB_PREFETCH
+#ifndef RB_PF_MINB_RNEA
+#define RB_PF_MINB_RNEA 3
+#endif
+#ifndef RB_PF_MINB_FD
+#define RB_PF_MINB_FD 3
+#endif
+template <class M>
+__global__ void __launch_bounds__(RB_BLOCK, RB_PF_MINB_RNEA)
+rb_rnea_pf_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
+                  const double* __restrict__ ddq, double* __restrict__ tau, size_t B, size_t ld) {
+    constexpr int N = M::N;
+    const size_t nthr = (size_t)gridDim.x * RB_BLOCK;
+    size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
+    if (s >= B) return;
+    double a[N], b[N], c[N];
+    rb_load<N>(q, ld, s, a); rb_load<N>(dq, ld, s, b); rb_load<N>(ddq, ld, s, c);
+    while (true) {
+        const size_t s2 = s + nthr;
+        const bool more = s2 < B;
+        double a2[N], b2[N], c2[N];
+        if (more) { rb_load<N>(q, ld, s2, a2); rb_load<N>(dq, ld, s2, b2); rb_load<N>(ddq, ld, s2, c2); }
+        double sn[N], cs[N], t[N];
+        rb_sincos_all<N>(a, sn, cs);
+        rb_rnea<M, true>(p, sn, cs, b, c, t);
+        rb_store<N>(tau, ld, s, t);
+        if (!more) break;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a[i] = a2[i]; b[i] = b2[i]; c[i] = c2[i]; }
+        s = s2;
+    }
+}
+template <class M>
+__global__ void __launch_bounds__(RB_BLOCK, RB_PF_MINB_FD)
+rb_fd_pf_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
+                const double* __restrict__ tau, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
+    constexpr int N = M::N;
+    const size_t nthr = (size_t)gridDim.x * RB_BLOCK;
+    size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
+    if (s >= B) return;
+    double a[N], b[N], c[N];
+    rb_load<N>(q, ld, s, a); rb_load<N>(dq, ld, s, b); rb_load<N>(tau, ld, s, c);
+    bool all_ok = true;
+    while (true) {
+        const size_t s2 = s + nthr;
+        const bool more = s2 < B;
+        double a2[N], b2[N], c2[N];
+        if (more) { rb_load<N>(q, ld, s2, a2); rb_load<N>(dq, ld, s2, b2); rb_load<N>(tau, ld, s2, c2); }
+        double sn[N], cs[N], x[N];
+        rb_sincos_all<N>(a, sn, cs);
+        const bool ok = rb_forward_dynamics<M>(p, sn, cs, b, c, x);
+        if (!ok) {
+            all_ok = false;
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = rb_nan<double>();
+        }
+        rb_store<N>(qdd, ld, s, x);
+        if (!more) break;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a[i] = a2[i]; b[i] = b2[i]; c[i] = c2[i]; }
+        s = s2;
+    }
+    if (!all_ok) atomicOr(status, RB_STATUS_NOT_SPD);
+}
+#endif
+
 // ------------------------------------------------------------------ streaming (persistent, TMA-fed) RNEA / FD
 // The one-tile-per-block kernels above leave each warp's 21 input loads exposed at the start of its life, so
 // HBM latency is hidden only by other resident warps -- and registers cap those at 16-20 per SM.  Here a
@@ -439,6 +511,13 @@ struct RbLaunch {
                             size_t B, size_t ld, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
         size_t done = 0;
+#if RB_PREFETCH
+        if constexpr (std::is_same<typename M::Real, double>::value) {
+            const size_t cap = (size_t)sm_count() * RB_PF_MINB_RNEA, want = (B + RB_BLOCK - 1) / RB_BLOCK;
+            rb_rnea_pf_kernel<M><<<(unsigned)(want < cap ? want : cap), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, ddq, tau, B, ld);
+            return cudaGetLastError();
+        }
+#endif
         cudaError_t e = stream3<RB_MINB_RNEA, false>(*(const P*)param, q, dq, ddq, tau, B, ld, nullptr, st, &done);
         if (e != cudaSuccess || done == B) return e;
         rb_rnea_kernel<M><<<grid(B - done), RB_BLOCK, 0, st>>>(*(const P*)param, q + done, dq + done, ddq + done, tau + done, B - done, ld);
@@ -448,6 +527,13 @@ struct RbLaunch {
                           size_t B, size_t ld, int* status, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
         size_t done = 0;
+#if RB_PREFETCH
+        if constexpr (std::is_same<typename M::Real, double>::value) {
+            const size_t cap = (size_t)sm_count() * RB_PF_MINB_FD, want = (B + RB_BLOCK - 1) / RB_BLOCK;
+            rb_fd_pf_kernel<M><<<(unsigned)(want < cap ? want : cap), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, tau, qdd, B, ld, status);
+            return cudaGetLastError();
+        }
+#endif
         cudaError_t e = stream3<RB_MINB_FD, true>(*(const P*)param, q, dq, tau, qdd, B, ld, status, st, &done);
         if (e != cudaSuccess || done == B) return e;
         rb_fd_kernel<M><<<grid(B - done), RB_BLOCK, 0, st>>>(*(const P*)param, q + done, dq + done, tau + done, qdd + done, B - done, ld, status);
