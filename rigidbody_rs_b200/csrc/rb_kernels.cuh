@@ -20,7 +20,9 @@ typedef unsigned long uintptr_t;
 #include "rb_dyn.cuh"
 #include "rb_tma.cuh"
 
+#ifndef RB_BLOCK
 #define RB_BLOCK 128
+#endif
 // Minimum resident blocks per SM requested from ptxas (register cap = 65536 / (RB_BLOCK * min_blocks)).
 #ifndef RB_MINB_RNEA
 #define RB_MINB_RNEA 5
