@@ -261,6 +261,51 @@ def test_rollout_chain32(rb, mb_chain32, oracle_chain32):
     np.testing.assert_allclose(c, want, rtol=1e-12)
 
 
+@pytest.mark.parametrize("n,seed", [(1, 91), (2, 92), (6, 93)])
+def test_runtime_n_family_on_short_chains(rb, n, seed):
+    """What a chain gets when the run-time compiler is unavailable: the run-time-n kernels, including the lane-per-joint
+    forward dynamics with most lanes idle."""
+    from test_host import _random_chain
+    from oracle.rb_oracle_np import ChainNP
+    R, t, m, c, Ic = _random_chain(n, seed)
+    os.environ["RIGIDBODY_B200_VARIANT"] = "generic-n"
+    try:
+        mb = rb.Multibody.from_descriptor(R, t, m, c, Ic)
+    finally:
+        os.environ.pop("RIGIDBODY_B200_VARIANT", None)
+    assert mb.kernel_variant == "generic-n"
+    ch = ChainNP.from_arrays(R, t, m, c, Ic)
+    rng = np.random.default_rng(seed)
+    B = 1027
+    q, dq, ddq = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n))
+    tau = ch.rnea(q, dq, ddq)
+    assert state_err(mb.rnea(q, dq, ddq, layout="aos"), tau, 1).max() < TOL
+    assert state_err(mb.forward_dynamics(q, dq, tau, layout="aos"), ddq, 1).max() < 1e-9
+
+
+def test_stepwise_rollout_in_chunks(rb, mb_fr3):
+    """The run-time-n rollout carries its state in engine scratch; more trajectories than fit are processed in chunks."""
+    import torch
+    os.environ["RIGIDBODY_B200_VARIANT"] = "generic-n"
+    try:
+        mb = rb.Multibody.from_urdf(FR3)
+    finally:
+        os.environ.pop("RIGIDBODY_B200_VARIANT", None)
+    B, H = 1_000_003, 2                                   # scratch holds ~720 k 7-joint trajectories at once
+    dev = torch.device("cuda:0")
+    lim = mb.limits()
+    q = torch.empty((7, B), dtype=torch.float64, device=dev); dq = torch.empty_like(q)
+    tau = torch.empty((H, 7, B), dtype=torch.float64, device=dev)
+    mb.fill(q, 7, 0, lim["lower"], lim["upper"]); mb.fill(dq, 7, 1, -lim["velocity"], lim["velocity"])
+    for t in range(H):
+        mb.fill(tau[t], 7, 2 + t, -lim["effort"], lim["effort"])
+    got = mb.rollout(q, dq, tau, 1e-3, final=True)
+    want = mb_fr3.rollout(q, dq, tau, 1e-3, final=True)
+    mb.sync(); mb_fr3.sync()
+    for g, w in zip(got, want):
+        assert float((g - w).abs().max()) < 1e-10
+
+
 def test_rollout_cost_matches_trajectory_cost(rb, oracle_fr3):
     """The fused rollout+cost kernel returns exactly the quadratic cost of the trajectory the oracle integrates."""
     import torch
