@@ -161,9 +161,27 @@ int pick_ops(RbGpu* g) {
     g->flat = rb_model_flat(g->model);
     const std::vector<double>& flat = g->flat;
     if (!g->model.serial) {
-        // kinematic trees (parent[i] != i-1): the run-time-n family only; every other family unrolls a serial chain
-        if (want != "auto" && want != "generic-n")
-            return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=" + want + " serves serial chains only; trees run on generic-n");
+        // kinematic trees (parent[i] != i-1): run-time specialised kernels up to 12 joints (the unrolled templates follow
+        // the compile-time parent table, rb_dyn_tree.cuh), the run-time-n family otherwise
+        if (want != "auto" && want != "generic-n" && want != "jit-specialised")
+            return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=" + want + " serves serial chains only; trees run on jit-specialised or generic-n");
+        const char* jit_env = getenv("RIGIDBODY_B200_JIT");
+        const bool jit_on = !(jit_env && std::string(jit_env) == "0");
+        if (want != "generic-n" && (jit_on || want == "jit-specialised") && n <= RB_JIT_MAX_N) {
+            RbJitImage img; std::string log;
+            int rc = rb_jit_compile(g->model, img, log);
+            if (rc == RB_OK) { std::string err; rc = rb_jit_load(img, n, g->jit, err); if (rc != RB_OK) log = err; }
+            if (rc == RB_OK) {
+                g->ops = rb_ops_jit();
+                g->param.assign(sizeof(RbJitParam), 0);
+                memcpy(g->param.data(), &g->jit, sizeof(RbJitParam));
+                g->family_note = std::string("kinematic tree: ") + (img.from_cache ? "kernels from the disk cache" : "kernels compiled with NVRTC");
+                return RB_OK;
+            }
+            if (want == "jit-specialised") return fail(rc, "run-time specialisation failed: " + log);
+        } else if (want == "jit-specialised") {
+            return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-specialised needs a chain of at most 12 joints");
+        }
         g->family_note = "kinematic tree: run-time-n kernels (rbn_tree_* recursions)";
         return setup_generic_n(g, flat, &g->ops, &g->param);
     }

@@ -73,6 +73,8 @@ struct RtModel {
     template <int K> static constexpr int gcls() { return RB_GEN; }
     template <int K> static RB_DI Real g(const Param& p) { return (Real)p.g[K]; }
     template <int K> static RB_DI Real tip(const Param& p) { return (Real)p.tip[K]; }
+    static constexpr bool kTree = false;     // run-time constants: serial chains only
+    template <int I> static constexpr int parent() { return I - 1; }
 };
 
 // Compile-time model: Tab supplies `static constexpr int N; static constexpr double T[N][24]; G[3]`
@@ -97,6 +99,15 @@ struct CtModel {
     template <int K> static constexpr int gcls() { return rb_classify(Tab::G[K]); }
     template <int K> static RB_DI Real g(const Param&) { constexpr Real v = (Real)Tab::G[K]; return v; }
     template <int K> static RB_DI Real tip(const Param&) { constexpr Real v = (Real)Tab::TIP[K]; return v; }
+    // parent link of joint I (slot 23 of the row); a table whose joints do not all hang off their predecessor is a
+    // kinematic tree and takes the rb_*_tree forms (rb_dyn_tree.cuh)
+    template <int I> static constexpr int parent() { return (int)Tab::T[I][23]; }
+    static constexpr bool tree_() {
+        for (int i = 0; i < Tab::N; ++i)
+            if ((int)Tab::T[i][23] != i - 1) return true;
+        return false;
+    }
+    static constexpr bool kTree = tree_();
 };
 
 #define KV(I, F, K) M::template val<I, F, K>(p)
@@ -188,10 +199,22 @@ RB_DI void rb_rotate_in(const typename M::Param& p, RB_R s, RB_R c, const RB_R (
     o[0] = fma(c, y0, s * y1);  o[1] = fma(c, y1, -(s * y0));  o[2] = y2;
 }
 
+// kinematic-tree forms (rb_dyn_tree.cuh), taken when M::kTree
+template <class M, bool HAS_DDQ>
+RB_DI void rb_rnea_tree(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
+                        const RB_R (&dq)[M::N], const RB_R (&ddq)[M::N], RB_R (&tau)[M::N]);
+template <class M, class Put>
+RB_DI void rb_crba_put_tree(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], Put&& put);
+template <class M>
+RB_DI void rb_fwd_kin_tree(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], RB_R (&pos)[3]);
+template <class M>
+RB_DI void rb_jac_tree(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], RB_R (&J)[M::N][6]);
+
 template <class M, bool HAS_DDQ>
 RB_DI void rb_rnea(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
                    const RB_R (&dq)[M::N], const RB_R (&ddq)[M::N], RB_R (&tau)[M::N]) {
     constexpr int N = M::N;
+    if constexpr (M::kTree) { rb_rnea_tree<M, HAS_DDQ>(p, s, c, dq, ddq, tau); return; }
     RB_R fl[N][3], fr[N][3];
     RB_R w[3], al[3], ac[3];            // omega, alpha, a' of the current link, in its own frame
     rb_for_up<0, N>([&](auto ic) {
@@ -291,6 +314,7 @@ RB_DI void rb_rnea(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R
 template <class M, class Put>
 RB_DI void rb_crba_put(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], Put&& put) {
     constexpr int N = M::N;
+    if constexpr (M::kTree) { rb_crba_put_tree<M>(p, s, c, put); return; }
     RB_R h[3] = {KV(N - 1, RB_F_H, 0), KV(N - 1, RB_F_H, 1), KV(N - 1, RB_F_H, 2)};            // :157
     RB_R Ixx = KV(N - 1, RB_F_I, 0), Ixy = KV(N - 1, RB_F_I, 1), Ixz = KV(N - 1, RB_F_I, 2);
     RB_R Iyy = KV(N - 1, RB_F_I, 3), Iyz = KV(N - 1, RB_F_I, 4), Izz = KV(N - 1, RB_F_I, 5);
@@ -365,6 +389,12 @@ RB_DI void rb_crba_put(const typename M::Param& p, const RB_R (&s)[M::N], const 
 template <class M>
 RB_DI void rb_crba(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
                    RB_R (&H)[M::N][M::N]) {
+    if constexpr (M::kTree) {                        // entries whose row joint does not support the column joint stay 0
+#pragma unroll
+        for (int r = 0; r < M::N; ++r)
+#pragma unroll
+            for (int k = 0; k < M::N; ++k) H[r][k] = RB_R(0);
+    }
     rb_crba_put<M>(p, s, c, [&](auto jc, auto ic, RB_R v) { H[decltype(jc)::value][decltype(ic)::value] = v; });
 }
 
@@ -438,6 +468,7 @@ RB_DI bool rb_forward_dynamics(const typename M::Param& p, const RB_R (&s)[M::N]
 template <class M>
 RB_DI void rb_fwd_kin(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], RB_R (&pos)[3]) {
     constexpr int N = M::N;
+    if constexpr (M::kTree) { rb_fwd_kin_tree<M>(p, s, c, pos); return; }
     pos[0] = 0.0; pos[1] = 0.0; pos[2] = 0.0;
     rb_for_down<N - 1>([&](auto ic) {
         constexpr int I = decltype(ic)::value;
@@ -454,6 +485,7 @@ RB_DI void rb_fwd_kin(const typename M::Param& p, const RB_R (&s)[M::N], const R
 template <class M>
 RB_DI void rb_jac(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], RB_R (&J)[M::N][6]) {
     constexpr int N = M::N;
+    if constexpr (M::kTree) { rb_jac_tree<M>(p, s, c, J); return; }
     // orientation of the reference's tip frame in the model's last frame (identity unless the last axis was re-based)
     RB_R A[3][3] = {{M::template tip<0>(p), M::template tip<1>(p), M::template tip<2>(p)},
                     {M::template tip<3>(p), M::template tip<4>(p), M::template tip<5>(p)},
@@ -489,3 +521,5 @@ RB_DI void rb_jac(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R 
         }
     });
 }
+
+#include "rb_dyn_tree.cuh"

@@ -138,7 +138,6 @@ void cache_write(const std::string& file, const RbJitImage& img) {
 
 int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     if (m.n < 1 || m.n > RB_JIT_MAX_N) { log = "chain too long for register-resident kernels"; return RB_ERR_UNSUPPORTED; }
-    if (!m.serial) { log = "the specialised kernels unroll a serial chain; trees run on the run-time-n family"; return RB_ERR_UNSUPPORTED; }
     std::string err;
     const Nvrtc* nv = load_nvrtc(err);
     if (!nv) { log = err; return RB_ERR_UNSUPPORTED; }

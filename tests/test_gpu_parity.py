@@ -496,9 +496,11 @@ def test_long_random_chains(rb, n, seed):
     assert np.abs(J - ch.jac(q[:32])).max() < TOL
 
 
-@pytest.mark.parametrize("n,seed", [(5, 1), (9, 2), (20, 3), (40, 4)])
-def test_kinematic_trees(rb, n, seed):
-    """Branching trees (parent[i] < i): run-time-n kernels with the parent-indexed recursions; the reference has only
+@pytest.mark.parametrize("n,seed,variant", [(5, 1, "auto"), (9, 2, "auto"), (12, 5, "auto"), (5, 1, "generic-n"), (9, 2, "generic-n"),
+                                            (20, 3, "auto"), (40, 4, "auto")])
+def test_kinematic_trees(rb, n, seed, variant):
+    """Branching trees (parent[i] < i): up to 12 joints the unrolled templates follow the compile-time parent table
+    (run-time specialised), beyond that the run-time-n kernels with the parent-indexed recursions; the reference has only
     the serial case (multibody.rs:148,165), so the checker is the twin's tree form (pinned by energy identities in
     tests/test_host.py).  Oblique joint axes ride along."""
     from test_host import _random_chain, _random_tree
@@ -507,8 +509,12 @@ def test_kinematic_trees(rb, n, seed):
     par = _random_tree(n, seed)
     ax = np.random.default_rng(seed).normal(size=(n, 3))
     ch = ChainNP.from_arrays(R, t, m, c, Ic, axis=ax, parent=par)
-    mb = rb.Multibody.from_descriptor(R, t, m, c, Ic, axis=ax, parent=par)
-    assert mb.kernel_variant == "generic-n" and "tree" in mb._note()
+    os.environ["RIGIDBODY_B200_VARIANT"] = variant
+    try:
+        mb = rb.Multibody.from_descriptor(R, t, m, c, Ic, axis=ax, parent=par)
+    finally:
+        os.environ.pop("RIGIDBODY_B200_VARIANT", None)
+    assert mb.kernel_variant == ("jit-specialised" if n <= 12 and variant == "auto" else "generic-n") and "tree" in mb._note()
     rng = np.random.default_rng(seed)
     B = 257
     q, dq, ddq = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n))
@@ -533,11 +539,14 @@ def test_kinematic_trees(rb, n, seed):
                          np.ascontiguousarray(taus.transpose(0, 2, 1)), 1e-3, trajectory=False, final=True)
     assert np.abs(qf - qs.T).max() < 1e-9 and np.abs(dqf - dqs.T).max() < 1e-8
     with pytest.raises(rb.RigidBodyError):
-        os.environ["RIGIDBODY_B200_VARIANT"] = "jit-specialised"
+        os.environ["RIGIDBODY_B200_VARIANT"] = "generic-7"
         try:
             rb.Multibody.from_descriptor(R, t, m, c, Ic, parent=par)
         finally:
             os.environ.pop("RIGIDBODY_B200_VARIANT", None)
+    if n <= 12:                                        # analytical derivatives are for serial chains
+        with pytest.raises(rb.RigidBodyError):
+            mb.rnea_derivatives(q, dq, ddq, layout="aos")
 
 
 @pytest.mark.parametrize("n", [7, 4])
