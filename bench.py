@@ -276,6 +276,26 @@ def run_ours(args, rank, local_rank, world):
     same = bool(np.array_equal(htau[:, :4096], tau[:, :4096].cpu().numpy())) and bool(np.array_equal(hout[:n], htau)) \
         and bool(np.array_equal(hout[n:], hqdd))
 
+    # optional assembly of the sharded result on every rank: ONE NCCL all-gather of tau, outside the timed
+    # region and reported separately -- the compute path itself exchanges nothing
+    gather = None
+    if world > 1:
+        Bg = min(B, 1 << 22)                              # 235 MB per rank: enough to see the NVLink rate
+        part = tau[:, :Bg].contiguous()
+        full = torch.empty((world, n, Bg), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full, part)           # warm-up (communicator set-up)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        dist.all_gather_into_tensor(full, part)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = max_over_ranks(g0.elapsed_time(g1), dev)
+        ok_g = bool(torch.equal(full[rank], part))
+        gather = {"collective": "ncclAllGather(tau)", "ms": gms, "bytes_per_rank": int(part.numel() * 8),
+                  "recv_GB_per_s_per_rank": (world - 1) * part.numel() * 8 / (gms * 1e-3) / 1e9, "own_slice_intact": ok_g}
+
     hbm_peak, hbm_src = measured_peaks()
     rnea_s, fd_s = ms_rnea * 1e-3, ms_fd * 1e-3
 
@@ -312,6 +332,8 @@ def run_ours(args, rank, local_rank, world):
                                    "api": "Multibody.rnea + Multibody.forward_dynamics -> multibody_{rnea,forward_dynamics}_batch(RB_MEM_HOST)"}},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if gather is not None:
+        line["gather"] = gather
     if rank == 0 and world == 1 and not args.no_cpu:
         cb, _, _ = cpu_arm(None, 2, 1)
         line["cpu_baseline"] = cb
