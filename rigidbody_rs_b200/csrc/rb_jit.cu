@@ -150,6 +150,16 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     h = fnv1a(h, main_src.data(), main_src.size());
     for (int k = 0; k < rb_jit_src_count; ++k) h = fnv1a(h, rb_jit_src_texts[k], strlen(rb_jit_src_texts[k]));
     for (const char* o : kOptions) h = fnv1a(h, o, strlen(o));
+    // tuning knob: extra whitespace-separated compiler options (e.g. "-DRB_MINB_FD=2"), part of the cache key
+    std::vector<std::string> extra;
+    if (const char* e = getenv("RIGIDBODY_B200_JIT_FLAGS")) {
+        std::string cur;
+        for (const char* c = e;; ++c) {
+            if (*c == ' ' || *c == '\0') { if (!cur.empty()) extra.push_back(cur); cur.clear(); if (!*c) break; }
+            else cur += *c;
+        }
+    }
+    for (const std::string& o : extra) h = fnv1a(h, o.data(), o.size());
     h = fnv1a(h, &vmaj, sizeof vmaj); h = fnv1a(h, &vmin, sizeof vmin);
     char keybuf[32]; snprintf(keybuf, sizeof keybuf, "%016llx", (unsigned long long)h);
     const std::string dir = cache_dir(), file = dir + "/" + keybuf + ".rbjit";
@@ -161,7 +171,9 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
         log = "nvrtcCreateProgram failed"; return RB_ERR_CUDA;
     }
     for (const char* e : kKernelExprs) nv->AddNameExpression(prog, e);
-    const int rc = nv->CompileProgram(prog, (int)(sizeof kOptions / sizeof kOptions[0]), kOptions);
+    std::vector<const char*> opts(kOptions, kOptions + sizeof kOptions / sizeof kOptions[0]);
+    for (const std::string& o : extra) opts.push_back(o.c_str());
+    const int rc = nv->CompileProgram(prog, (int)opts.size(), opts.data());
     size_t ls = 0;
     nv->GetProgramLogSize(prog, &ls);
     if (ls > 1) { std::string l(ls, '\0'); nv->GetProgramLog(prog, &l[0]); log = l; }

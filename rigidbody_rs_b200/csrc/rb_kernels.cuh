@@ -31,6 +31,13 @@ typedef unsigned long uintptr_t;
 #define RB_MINB_FD 4
 #endif
 // The run-time-constant family executes ~1.7-2x the instructions with more live values: it wants more registers.
+// chains of 9..12 joints (run-time specialised): fewer, fatter blocks (profiles/r1_kbench_jit_launch_bounds.txt)
+#ifndef RB_MINB_RNEA_LONG
+#define RB_MINB_RNEA_LONG 4
+#endif
+#ifndef RB_MINB_FD_LONG
+#define RB_MINB_FD_LONG 3
+#endif
 #ifndef RB_MINB_RNEA_RT
 #define RB_MINB_RNEA_RT 3
 #endif
@@ -145,7 +152,7 @@ RB_DI void rb_aos_store(T* __restrict__ out, size_t B, T* buf, const T (&v)[N]) 
 }
 
 template <class M, bool AOS = false>
-__global__ void __launch_bounds__(RB_BLOCK, M::kSpecialised ? RB_MINB_RNEA : RB_MINB_RNEA_RT)
+__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_RNEA_RT : (M::N <= 8 ? RB_MINB_RNEA : RB_MINB_RNEA_LONG))
 rb_rnea_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
                const RB_R* __restrict__ ddq, RB_R* __restrict__ tau, size_t B, size_t ld) {
     constexpr int N = M::N;
@@ -170,7 +177,7 @@ rb_rnea_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restri
 }
 
 template <class M, bool AOS = false>
-__global__ void __launch_bounds__(RB_BLOCK, M::kSpecialised ? RB_MINB_FD : RB_MINB_FD_RT)
+__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_FD_RT : (M::N <= 7 ? RB_MINB_FD : RB_MINB_FD_LONG))
 rb_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
              const RB_R* __restrict__ tau, RB_R* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
