@@ -176,6 +176,46 @@ def test_ragged_leading_dimension_device(rb, mb_fr3, oracle_fr3):
     assert rc == _lib.RB_ERR_ARG
 
 
+def test_ragged_leading_dimension_long_chain_and_derivatives(rb, mb_fr3, mb_chain32, oracle_chain32):
+    """ld > n_states with NaN-poisoned padding through the lane-per-joint FD kernel (odd tail: half-warp pairs, staging
+    groups) and the derivative kernels: results right, padding untouched."""
+    import torch
+    from rigidbody_rs_b200 import _lib
+    from oracle.rb_oracle_np import ChainNP
+    dev = torch.device("cuda:0")
+    nan = float("nan")
+    for B in (1, 2, 3, 5, 127):
+        ld = B + 9
+        rng = np.random.default_rng(B)
+        q, dq, tau = rng.uniform(-3, 3, (32, B)), rng.uniform(-1, 1, (32, B)), rng.uniform(-20, 20, (32, B))
+        bufs = [torch.full((32, ld), nan, dtype=torch.float64, device=dev) for _ in range(4)]
+        for b, x in zip(bufs, (q, dq, tau)):
+            b[:, :B] = torch.from_numpy(x).to(dev)
+        torch.cuda.synchronize()
+        rc = _lib.lib.multibody_forward_dynamics_batch(mb_chain32._h, *[C.c_void_p(b.data_ptr()) for b in bufs], B, ld,
+                                                       _lib.RB_LAYOUT_SOA, _lib.RB_MEM_DEVICE, None)
+        assert rc == 0, _lib.lib.multibody_last_error()
+        mb_chain32.sync()
+        out = bufs[3].cpu().numpy()
+        assert state_err(out[:, :B], oracle_chain32.forward_dynamics_batch(q, dq, tau), 0).max() < 1e-9
+        assert np.isnan(out[:, B:]).all()
+    B, ld = 37, 64
+    rng = np.random.default_rng(1)
+    q, dq, ddq = rng.uniform(-2, 2, (3, 7, B))
+    ins = [torch.full((7, ld), nan, dtype=torch.float64, device=dev) for _ in range(3)]
+    for b, x in zip(ins, (q, dq, ddq)):
+        b[:, :B] = torch.from_numpy(x).to(dev)
+    out = torch.full((147, ld), nan, dtype=torch.float64, device=dev)
+    rc = _lib.lib.multibody_fd_derivatives_batch(mb_fr3._h, *[C.c_void_p(b.data_ptr()) for b in ins], C.c_void_p(out.data_ptr()), B, ld,
+                                                 _lib.RB_LAYOUT_SOA, _lib.RB_MEM_DEVICE, None)
+    assert rc == 0, _lib.lib.multibody_last_error()
+    mb_fr3.sync()
+    o = out.cpu().numpy()
+    assert np.isnan(o[:, B:]).all() and np.isfinite(o[:, :B]).all()
+    want = mb_fr3.fd_derivatives(np.ascontiguousarray(q), np.ascontiguousarray(dq), np.ascontiguousarray(ddq))
+    np.testing.assert_array_equal(o[:, :B], want)
+
+
 def test_device_tensors_all_ops_medium_batch(rb, oracle_fr3):
     import torch
     B = 200_000
