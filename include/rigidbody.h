@@ -194,8 +194,8 @@ int multibody_crba_batch(RbGpu* g, const double* q, double* H,
 int multibody_rnea_fd_batch(RbGpu* g, const double* q, const double* dq, const double* ddq, const double* tau_in,
                             double* out, size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream);
 
-/* New (README.md:18 lists "Differentiability" as not done): analytical first derivatives, for serial chains of at most
- * 12 joints (the register-resident kernel families; RB_ERR_UNSUPPORTED otherwise).
+/* New (README.md:18 lists "Differentiability" as not done): analytical first derivatives of serial chains: inverse
+ * dynamics up to 32 joints, forward dynamics up to 12 (RB_ERR_UNSUPPORTED otherwise, and for kinematic trees).
  * multibody_rnea_derivatives_batch: out holds 2 n*n entries per state, block 0 = d tau / d q, block 1 = d tau / d dq of
  *   tau = rnea(q, dq, ddq); within a block entry k = r + n*c is d tau_r / d x_c (column-major, like crba).
  *   (d tau / d ddq is crba(q).)   SOA: out[(blk*n*n + k)*ld + s];  AOS: out[s*2*n*n + blk*n*n + k].

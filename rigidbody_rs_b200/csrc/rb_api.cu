@@ -616,8 +616,8 @@ extern "C" int multibody_rnea_derivatives_batch(RbGpu* g, const double* q, const
                                                 size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
-    if (n > RB_DERIV_MAX_N || !g->model.serial)
-        return fail(RB_ERR_UNSUPPORTED, "derivative kernels serve serial chains of at most 12 joints");
+    if (n > RB_RNEA_DERIV_MAX_N || !g->model.serial)
+        return fail(RB_ERR_UNSUPPORTED, "inverse-dynamics derivative kernels serve serial chains of at most 32 joints");
     OpDesc op{3, {q, dq, ddq}, {n, n, n}, out, 2 * n * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
                   return rb_launch_rnea_deriv(g->model.n, g->flat.data(), in[0], in[1], in[2], out, B, ld, st);
@@ -630,7 +630,7 @@ extern "C" int multibody_fd_derivatives_batch(RbGpu* g, const double* q, const d
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
     if (n > RB_DERIV_MAX_N || !g->model.serial)
-        return fail(RB_ERR_UNSUPPORTED, "derivative kernels serve serial chains of at most 12 joints");
+        return fail(RB_ERR_UNSUPPORTED, "forward-dynamics derivative kernels serve serial chains of at most 12 joints");
     OpDesc op{3, {q, dq, tau}, {n, n, n}, out, 3 * n * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
                   return rb_launch_fd_deriv(g->model.n, g->flat.data(), in[0], in[1], in[2], out, B, ld, g->d_status, st);

@@ -1,7 +1,8 @@
-// rb_kernels_deriv.cu -- analytical-derivative kernels (rb_deriv.cuh), one instantiation per chain length 1..12.
+// rb_kernels_deriv.cu -- analytical-derivative kernels (rb_deriv.cuh), one instantiation per chain length
+// (inverse dynamics: 1..32 joints; forward dynamics, which also unrolls FD itself: 1..12).
 // Unlike the other register-resident kernels these are NOT specialised on the model: the algebra runs in the world
 // frame, where the zeros of a particular robot's fixed rotations buy little, and real loops over the joints keep the
-// code small and the register allocation sane.  The model travels as a __grid_constant__ parameter (<= 2.4 KB).
+// code small and the register allocation sane.  The model travels as a __grid_constant__ parameter (<= 6.2 KB).
 #include "rb_kernels.cuh"
 #include "rb_deriv.cuh"
 #include "rb_util.cuh"
@@ -90,6 +91,19 @@ cudaError_t launch_fd(const double* flat, const double* q, const double* dq, con
 cudaError_t rb_launch_rnea_deriv(int n, const double* flat_model, const double* q, const double* dq, const double* ddq,
                                  double* out, size_t B, size_t ld, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
+    switch (n) {                                             // the rolled recursion has no per-joint state: any length
+        case 13: return launch_rnea<13>(flat_model, q, dq, ddq, out, B, ld, st); case 14: return launch_rnea<14>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 15: return launch_rnea<15>(flat_model, q, dq, ddq, out, B, ld, st); case 16: return launch_rnea<16>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 17: return launch_rnea<17>(flat_model, q, dq, ddq, out, B, ld, st); case 18: return launch_rnea<18>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 19: return launch_rnea<19>(flat_model, q, dq, ddq, out, B, ld, st); case 20: return launch_rnea<20>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 21: return launch_rnea<21>(flat_model, q, dq, ddq, out, B, ld, st); case 22: return launch_rnea<22>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 23: return launch_rnea<23>(flat_model, q, dq, ddq, out, B, ld, st); case 24: return launch_rnea<24>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 25: return launch_rnea<25>(flat_model, q, dq, ddq, out, B, ld, st); case 26: return launch_rnea<26>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 27: return launch_rnea<27>(flat_model, q, dq, ddq, out, B, ld, st); case 28: return launch_rnea<28>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 29: return launch_rnea<29>(flat_model, q, dq, ddq, out, B, ld, st); case 30: return launch_rnea<30>(flat_model, q, dq, ddq, out, B, ld, st);
+        case 31: return launch_rnea<31>(flat_model, q, dq, ddq, out, B, ld, st); case 32: return launch_rnea<32>(flat_model, q, dq, ddq, out, B, ld, st);
+        default: break;
+    }
     RB_DERIV_CASES(launch_rnea, flat_model, q, dq, ddq, out, B, ld, st)
 }
 cudaError_t rb_launch_fd_deriv(int n, const double* flat_model, const double* q, const double* dq, const double* tau,

@@ -25,7 +25,8 @@ cudaError_t rb_launch_warp_fd(const double* model, int n, const double* q, const
 #endif
 // Analytical derivatives (rb_kernels_deriv.cu) of serial chains of n <= RB_DERIV_MAX_N joints; `flat_model` = HOST rows in
 // the rb_model.h layout (passed on as a kernel parameter).  out: [2 n^2][ld] resp. [3 n^2][ld], see include/rigidbody.h.
-#define RB_DERIV_MAX_N 12
+#define RB_DERIV_MAX_N 12        // forward-dynamics derivatives
+#define RB_RNEA_DERIV_MAX_N 32   // inverse-dynamics derivatives
 cudaError_t rb_launch_rnea_deriv(int n, const double* flat_model, const double* q, const double* dq, const double* ddq,
                                  double* out, size_t B, size_t ld, cudaStream_t st);
 cudaError_t rb_launch_fd_deriv(int n, const double* flat_model, const double* q, const double* dq, const double* tau,

@@ -465,9 +465,9 @@ def test_analytical_derivatives_fr3_all_families(rb, oracle_fr3):
             err = np.abs(got - want).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(want).reshape(B, -1).max(1))
             assert err.max() < 1e-8, (mb.kernel_variant, err.max())
     assert fams == ["fr3-specialised", "jit-specialised", "generic-7", "generic-n"]
-    with pytest.raises(rb.RigidBodyError):       # beyond 12 joints: unsupported, not wrong
+    with pytest.raises(rb.RigidBodyError):       # forward-dynamics derivatives beyond 12 joints: unsupported, not wrong
         z = np.zeros((2, 32))
-        rb.Multibody.from_urdf(CHAIN32).rnea_derivatives(z, z, z, layout="aos")
+        rb.Multibody.from_urdf(CHAIN32).fd_derivatives(z, z, z, layout="aos")
     # device SoA tensors, and one state
     import torch
     mb = rb.Multibody.from_urdf(FR3)
@@ -507,6 +507,19 @@ def test_analytical_derivatives_random_chains(rb, n, seed):
     fq, fv, fm = _unpack(mb.fd_derivatives(q, dq, tau, layout="aos"), n, 3)
     for got, want in ((fq, Aq), (fv, Av), (fm, Mi)):
         assert np.abs(got - want).max() < 1e-8 * max(1.0, np.abs(want).max())
+
+
+def test_inverse_dynamics_derivatives_chain32(rb, mb_chain32, oracle_chain32):
+    """The rolled derivative recursion keeps no per-joint state, so it serves long chains too (inverse dynamics only)."""
+    from oracle.rb_oracle_np import ChainNP
+    ch = ChainNP(oracle_chain32.model)
+    rng = np.random.default_rng(8)
+    B = 24
+    q, dq, ddq = rng.uniform(-3, 3, (B, 32)), rng.uniform(-1, 1, (B, 32)), rng.uniform(-5, 5, (B, 32))
+    Dq, Dv = ch.rnea_derivatives(q, dq, ddq)
+    gq, gv = _unpack(mb_chain32.rnea_derivatives(q, dq, ddq, layout="aos"), 32, 2)
+    assert np.abs(gq - Dq).max() < TOL * max(1.0, np.abs(Dq).max())
+    assert np.abs(gv - Dv).max() < TOL * max(1.0, np.abs(Dv).max())
 
 
 @pytest.mark.parametrize("n,seed", [(13, 1), (24, 2), (32, 3), (33, 4), (64, 5)])
