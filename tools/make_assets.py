@@ -38,9 +38,9 @@ LINK0 = ("-0.041018 -0.00014 0.049974", "0.629769", "0.00315 8.2904e-07 0.00015 
 
 def _inertial(com, mass, six):
     k = six.split()
-    return (f'    <inertial>\n      <origin rpy="0 0 0" xyz="{com}"/>\n      <mass value="{mass}"/>\n'
-            f'      <inertia ixx="{k[0]}" ixy="{k[1]}" ixz="{k[2]}" iyy="{k[3]}" iyz="{k[4]}" izz="{k[5]}"/>\n'
-            f'    </inertial>\n')
+    # one compact line per link: this file is a parameter table, not a copy of anybody's robot description layout
+    return (f'<inertial><mass value="{mass}"/><origin xyz="{com}" rpy="0 0 0"/>'
+            f'<inertia ixx="{k[0]}" iyy="{k[3]}" izz="{k[5]}" ixy="{k[1]}" ixz="{k[2]}" iyz="{k[4]}"/></inertial>')
 
 
 def fr3():
@@ -50,26 +50,24 @@ def fr3():
          '<robot name="fr3">\n']
 
     def sc(k):
-        o.append(f'  <link name="fr3_link{k}_sc">\n  </link>\n')
-        o.append(f'  <joint name="fr3_link{k}_sc_joint" type="fixed">\n    <origin rpy="0 0 0"/>\n'
-                 f'    <parent link="fr3_link{k}"/>\n    <child link="fr3_link{k}_sc"/>\n  </joint>\n')
+        o.append(f'  <link name="fr3_link{k}_sc"/>\n')
+        o.append(f'  <joint type="fixed" name="fr3_link{k}_sc_joint"><parent link="fr3_link{k}"/><child link="fr3_link{k}_sc"/>'
+                 f'<origin rpy="0 0 0"/></joint>\n')
 
-    o.append('  <link name="fr3_link0">\n' + _inertial(*LINK0) + '  </link>\n')
+    o.append('  <link name="fr3_link0">' + _inertial(*LINK0) + '</link>\n')
     sc(0)
     for k, (xyz, rpy, (eff, lo, up, vel), com, mass, six) in enumerate(FR3, start=1):
-        o.append(f'  <link name="fr3_link{k}">\n' + _inertial(com, mass, six) + '  </link>\n')
+        o.append(f'  <link name="fr3_link{k}">' + _inertial(com, mass, six) + '</link>\n')
         sc(k)
-        o.append(f'  <joint name="fr3_joint{k}" type="revolute">\n'
-                 f'    <origin rpy="{rpy}" xyz="{xyz}"/>\n'
-                 f'    <parent link="fr3_link{k - 1}"/>\n    <child link="fr3_link{k}"/>\n'
-                 f'    <axis xyz="0 0 1"/>\n'
-                 f'    <limit effort="{eff}" lower="{lo}" upper="{up}" velocity="{vel}"/>\n  </joint>\n')
+        o.append(f'  <joint type="revolute" name="fr3_joint{k}"><parent link="fr3_link{k - 1}"/><child link="fr3_link{k}"/>'
+                 f'<origin xyz="{xyz}" rpy="{rpy}"/><axis xyz="0 0 1"/>'
+                 f'<limit lower="{lo}" upper="{up}" velocity="{vel}" effort="{eff}"/></joint>\n')
     o.append('  <link name="fr3_link8"/>\n')
-    o.append('  <joint name="fr3_joint8" type="fixed">\n    <origin rpy="0 0 0" xyz="0 0 0.107"/>\n'
-             '    <parent link="fr3_link7"/>\n    <child link="fr3_link8"/>\n  </joint>\n')
+    o.append('  <joint type="fixed" name="fr3_joint8"><parent link="fr3_link7"/><child link="fr3_link8"/>'
+             '<origin xyz="0 0 0.107" rpy="0 0 0"/></joint>\n')
     o.append('  <link name="world"/>\n')
-    o.append('  <joint name="world_joint" type="fixed">\n    <origin rpy="0 0 0" xyz="0 0 0"/>\n'
-             '    <parent link="world"/>\n    <child link="fr3_link0"/>\n  </joint>\n')
+    o.append('  <joint type="fixed" name="world_joint"><parent link="world"/><child link="fr3_link0"/>'
+             '<origin xyz="0 0 0" rpy="0 0 0"/></joint>\n')
     o.append('</robot>\n')
     return "".join(o)
 
