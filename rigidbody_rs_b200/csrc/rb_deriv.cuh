@@ -248,33 +248,32 @@ RB_DI void rb_rnea_derivatives(const RbModelK<N>& p, const double* sn, const dou
 template <int N>
 RB_DI bool rb_ldlt_factor(double (&A)[N][N], double (&dinv)[N]) {
     bool ok = true;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const double d = A[j][j];
+    rb_for_up<0, N>([&](auto jc) {                           // compile-time indices: see rb_ldlt_solve_static
+        constexpr int J = decltype(jc)::value;
+        const double d = A[J][J];
         ok = ok && (d > 0.0);
-        dinv[j] = rb_rcp_pos(d);
-#pragma unroll
-        for (int i = j + 1; i < N; ++i) {
-            const double l = A[j][i] * dinv[j];
-#pragma unroll
-            for (int k = i; k < N; ++k) A[i][k] = fma(-l, A[j][k], A[i][k]);
-            A[j][i] = l;
-        }
-    }
+        dinv[J] = rb_rcp_pos(d);
+        rb_for_up<J + 1, N>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            const double l = A[J][I] * dinv[J];
+            rb_for_up<I, N>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                A[I][K] = fma(-l, A[J][K], A[I][K]);
+            });
+            A[J][I] = l;
+        });
+    });
     return ok;
 }
 template <int N>
 RB_DI void rb_ldlt_apply(const double (&A)[N][N], const double (&dinv)[N], double (&x)[N]) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-#pragma unroll
-        for (int i = j + 1; i < N; ++i) x[i] = fma(-A[j][i], x[j], x[i]);
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) x[j] *= dinv[j];
-#pragma unroll
-    for (int i = N - 1; i >= 0; --i) {
-#pragma unroll
-        for (int k = i + 1; k < N; ++k) x[i] = fma(-A[i][k], x[k], x[i]);
-    }
+    rb_for_up<0, N>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        rb_for_up<J + 1, N>([&](auto ic) { constexpr int I = decltype(ic)::value; x[I] = fma(-A[J][I], x[J], x[I]); });
+    });
+    rb_for_up<0, N>([&](auto jc) { constexpr int J = decltype(jc)::value; x[J] *= dinv[J]; });
+    rb_for_down<N - 1>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        rb_for_up<I + 1, N>([&](auto kc) { constexpr int K = decltype(kc)::value; x[I] = fma(-A[I][K], x[K], x[I]); });
+    });
 }

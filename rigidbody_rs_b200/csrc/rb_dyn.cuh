@@ -446,6 +446,40 @@ RB_DI bool rb_ldlt_solve(T (&A)[N][N], T (&x)[N]) {
     return ok;
 }
 
+// The same factorisation with compile-time loop indices (template recursion instead of `#pragma unroll`): beyond
+// 7-8 joints nvcc stops unrolling the triple loop of rb_ldlt_solve, indexes H dynamically and so moves the whole
+// matrix to local memory (1.2-1.6 KB stack frame at N = 12).  Same operations in the same order.
+template <int N, class T>
+RB_DI bool rb_ldlt_solve_static(T (&A)[N][N], T (&x)[N]) {
+    T dinv[N];
+    bool ok = true;
+    rb_for_up<0, N>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        const T d = A[J][J];
+        ok = ok && (d > T(0));
+        dinv[J] = rb_rcp_pos(d);
+        rb_for_up<J + 1, N>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            const T l = A[J][I] * dinv[J];
+            rb_for_up<I, N>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                A[I][K] = fma(-l, A[J][K], A[I][K]);
+            });
+            A[J][I] = l;
+        });
+    });
+    rb_for_up<0, N>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        rb_for_up<J + 1, N>([&](auto ic) { constexpr int I = decltype(ic)::value; x[I] = fma(-A[J][I], x[J], x[I]); });
+    });
+    rb_for_up<0, N>([&](auto jc) { constexpr int J = decltype(jc)::value; x[J] *= dinv[J]; });
+    rb_for_down<N - 1>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        rb_for_up<I + 1, N>([&](auto kc) { constexpr int K = decltype(kc)::value; x[I] = fma(-A[I][K], x[K], x[I]); });
+    });
+    return ok;
+}
+
 // ------------------------------------------------------------------ forward dynamics
 // qdd = solve(sym(crba(q)), tau - rnea(q, dq, 0)); sin/cos computed once and shared by both halves.
 template <class M>
@@ -460,7 +494,8 @@ RB_DI bool rb_forward_dynamics(const typename M::Param& p, const RB_R (&s)[M::N]
     }
     RB_R H[N][N];
     rb_crba<M>(p, s, c, H);
-    return rb_ldlt_solve<N>(H, qdd);
+    if constexpr (N > 7) return rb_ldlt_solve_static<N>(H, qdd);
+    else return rb_ldlt_solve<N>(H, qdd);
 }
 
 // ------------------------------------------------------------------ forward kinematics / Jacobian

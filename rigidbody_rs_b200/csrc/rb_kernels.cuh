@@ -36,7 +36,7 @@ typedef unsigned long uintptr_t;
 #define RB_MINB_RNEA_LONG 4
 #endif
 #ifndef RB_MINB_FD_LONG
-#define RB_MINB_FD_LONG 3
+#define RB_MINB_FD_LONG 2      // 12 joints: the 78-entry matrix wants all 255 registers
 #endif
 #ifndef RB_MINB_RNEA_RT
 #define RB_MINB_RNEA_RT 3
@@ -177,7 +177,7 @@ rb_rnea_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restri
 }
 
 template <class M, bool AOS = false>
-__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_FD_RT : (M::N <= 7 ? RB_MINB_FD : RB_MINB_FD_LONG))
+__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_FD_RT : (M::N <= 11 ? RB_MINB_FD : RB_MINB_FD_LONG))
 rb_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
              const RB_R* __restrict__ tau, RB_R* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
