@@ -88,7 +88,7 @@ typedef struct RbChainDesc {
     int32_t n_joints;             /* 1..RB_MAX_JOINTS */
     const int32_t* parent;        /* [n] parent link index, -1 = base, parent[i] < i (topological order).  NULL = serial
                                      chain (i-1), the reference's only case (multibody.rs:148,165) and the one the
-                                     ahead-of-time kernel families serve; a branching tree gets run-time specialised kernels (<= 12
+                                     ahead-of-time kernel families serve; a branching tree gets run-time specialised kernels (<= 18
                                      joints) or the run-time-n family.
                                      The tip of fwd_kin / jac is the last link; H(j, i) = 0 and the Jacobian column
                                      of j is 0 where joint j does not support link i / the tip. */

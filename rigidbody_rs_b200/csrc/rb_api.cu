@@ -161,7 +161,7 @@ int pick_ops(RbGpu* g) {
     g->flat = rb_model_flat(g->model);
     const std::vector<double>& flat = g->flat;
     if (!g->model.serial) {
-        // kinematic trees (parent[i] != i-1): run-time specialised kernels up to 12 joints (the unrolled templates follow
+        // kinematic trees (parent[i] != i-1): run-time specialised kernels up to RB_JIT_MAX_N joints (the unrolled templates follow
         // the compile-time parent table, rb_dyn_tree.cuh), the run-time-n family otherwise
         if (want != "auto" && want != "generic-n" && want != "jit-specialised")
             return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=" + want + " serves serial chains only; trees run on jit-specialised or generic-n");
@@ -180,7 +180,7 @@ int pick_ops(RbGpu* g) {
             }
             if (want == "jit-specialised") return fail(rc, "run-time specialisation failed: " + log);
         } else if (want == "jit-specialised") {
-            return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-specialised needs a chain of at most 12 joints");
+            return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-specialised needs a chain of at most 18 joints");
         }
         g->family_note = "kinematic tree: run-time-n kernels (rbn_tree_* recursions)";
         return setup_generic_n(g, flat, &g->ops, &g->param);
@@ -210,7 +210,7 @@ int pick_ops(RbGpu* g) {
         if (want == "jit-specialised") return fail(rc, "run-time specialisation failed: " + log);
         g->family_note = "run-time specialisation unavailable (" + log.substr(0, 200) + "); using run-time-constant kernels";
     } else if (want == "jit-specialised") {
-        return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-specialised needs a chain of at most 12 joints");
+        return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-specialised needs a chain of at most 18 joints");
     }
     if ((want == "auto" || want == "generic-7") && n == 7) {
         g->ops = rb_ops_rt7();

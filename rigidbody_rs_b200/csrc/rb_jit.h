@@ -4,7 +4,7 @@
 #include <vector>
 #include "rb_host_model.h"
 
-#define RB_JIT_MAX_N 12        // longest chain the register-resident unrolled kernels are compiled for
+#define RB_JIT_MAX_N 18        // longest chain the register-resident unrolled kernels are compiled for (FD falls off a cliff at 20)
 #define RB_JIT_KERNELS 10
 enum : int { RB_JK_RNEA = 0, RB_JK_RNEA_AOS, RB_JK_FD, RB_JK_FD_AOS, RB_JK_CRBA, RB_JK_FK, RB_JK_JAC, RB_JK_ROLLOUT,
              RB_JK_RNEA_F32, RB_JK_FD_F32 };

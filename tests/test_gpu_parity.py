@@ -522,7 +522,7 @@ def test_inverse_dynamics_derivatives_chain32(rb, mb_chain32, oracle_chain32):
     assert np.abs(gv - Dv).max() < TOL * max(1.0, np.abs(Dv).max())
 
 
-@pytest.mark.parametrize("n,seed", [(13, 1), (24, 2), (32, 3), (33, 4), (64, 5)])
+@pytest.mark.parametrize("n,seed", [(13, 1), (19, 6), (24, 2), (32, 3), (33, 4), (64, 5)])
 def test_long_random_chains(rb, n, seed):
     """Chains beyond the register-resident limit: run-time-n kernels; forward dynamics by the warp-per-state kernel
     up to 32 joints (idle lanes padded) and by the shared-memory tile solver beyond."""
@@ -531,7 +531,7 @@ def test_long_random_chains(rb, n, seed):
     R, t, m, c, Ic = _random_chain(n, seed)
     t = t * (8.0 / n)                                    # keep the reach (and cond(H)) comparable across lengths
     mb = rb.Multibody.from_descriptor(R, t, m, c, Ic)
-    assert mb.kernel_variant == "generic-n"
+    assert mb.kernel_variant == ("jit-specialised" if n <= 18 else "generic-n")     # 13: the longest unrolled kernels the tests compile
     ch = ChainNP.from_arrays(R, t, m, c, Ic)
     rng = np.random.default_rng(seed)
     B = 333
@@ -552,7 +552,7 @@ def test_long_random_chains(rb, n, seed):
 @pytest.mark.parametrize("n,seed,variant", [(5, 1, "auto"), (9, 2, "auto"), (12, 5, "auto"), (5, 1, "generic-n"), (9, 2, "generic-n"),
                                             (20, 3, "auto"), (40, 4, "auto")])
 def test_kinematic_trees(rb, n, seed, variant):
-    """Branching trees (parent[i] < i): up to 12 joints the unrolled templates follow the compile-time parent table
+    """Branching trees (parent[i] < i): up to 18 joints the unrolled templates follow the compile-time parent table
     (run-time specialised), beyond that the run-time-n kernels with the parent-indexed recursions; the reference has only
     the serial case (multibody.rs:148,165), so the checker is the twin's tree form (pinned by energy identities in
     tests/test_host.py).  Oblique joint axes ride along."""
@@ -567,7 +567,7 @@ def test_kinematic_trees(rb, n, seed, variant):
         mb = rb.Multibody.from_descriptor(R, t, m, c, Ic, axis=ax, parent=par)
     finally:
         os.environ.pop("RIGIDBODY_B200_VARIANT", None)
-    assert mb.kernel_variant == ("jit-specialised" if n <= 12 and variant == "auto" else "generic-n") and "tree" in mb._note()
+    assert mb.kernel_variant == ("jit-specialised" if n <= 18 and variant == "auto" else "generic-n") and "tree" in mb._note()
     rng = np.random.default_rng(seed)
     B = 257
     q, dq, ddq = rng.uniform(-3, 3, (B, n)), rng.uniform(-2, 2, (B, n)), rng.uniform(-10, 10, (B, n))
@@ -597,7 +597,7 @@ def test_kinematic_trees(rb, n, seed, variant):
             rb.Multibody.from_descriptor(R, t, m, c, Ic, parent=par)
         finally:
             os.environ.pop("RIGIDBODY_B200_VARIANT", None)
-    if n <= 12:                                        # analytical derivatives are for serial chains
+    if n <= 18:                                        # analytical derivatives are for serial chains
         with pytest.raises(rb.RigidBodyError):
             mb.rnea_derivatives(q, dq, ddq, layout="aos")
 
