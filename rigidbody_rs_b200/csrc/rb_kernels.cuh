@@ -35,6 +35,9 @@ typedef unsigned long uintptr_t;
 #ifndef RB_MINB_RNEA_LONG
 #define RB_MINB_RNEA_LONG 4
 #endif
+#ifndef RB_MINB_RNEA_XLONG
+#define RB_MINB_RNEA_XLONG 3   // 15..18 joints
+#endif
 #ifndef RB_MINB_FD_LONG
 #define RB_MINB_FD_LONG 2      // 12 joints: the 78-entry matrix wants all 255 registers
 #endif
@@ -152,7 +155,7 @@ RB_DI void rb_aos_store(T* __restrict__ out, size_t B, T* buf, const T (&v)[N]) 
 }
 
 template <class M, bool AOS = false>
-__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_RNEA_RT : (M::N <= 8 ? RB_MINB_RNEA : RB_MINB_RNEA_LONG))
+__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_RNEA_RT : (M::N <= 8 ? RB_MINB_RNEA : (M::N <= 14 ? RB_MINB_RNEA_LONG : RB_MINB_RNEA_XLONG)))
 rb_rnea_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
                const RB_R* __restrict__ ddq, RB_R* __restrict__ tau, size_t B, size_t ld) {
     constexpr int N = M::N;
