@@ -131,7 +131,8 @@ void multibody_gpu_free(RbGpu* g);
 int multibody_gpu_n_joints(const RbGpu* g);
 int multibody_gpu_device(const RbGpu* g);
 /* Which kernel family serves this chain: "fr3-specialised" / "chain32-specialised" (compiled in), "jit-specialised"
- * (the same kernels compiled for this chain's constants at load time with NVRTC, cached on disk), "generic-7",
+ * (the same kernels compiled for this chain's constants at load time with NVRTC, cached on disk; <= 18 joints),
+ * "jit-long" (19..32 joints: rnea / crba / fwd_kin / jac compiled at load time, the rest run-time-n), "generic-7",
  * "generic-n" (run-time constants).  $RIGIDBODY_B200_VARIANT forces one, $RIGIDBODY_B200_JIT=0 disables the JIT,
  * $RIGIDBODY_B200_CACHE moves the cache directory (default ~/.cache/rigidbody_b200; empty string = no cache). */
 const char* multibody_gpu_kernel_variant(const RbGpu* g);

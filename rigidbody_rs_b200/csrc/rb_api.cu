@@ -212,6 +212,24 @@ int pick_ops(RbGpu* g) {
     } else if (want == "jit-specialised") {
         return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-specialised needs a chain of at most 18 joints");
     }
+    // chains of 19..32 joints: rnea / crba / fwd_kin / jac specialised at load time ("jit-long"), forward dynamics and
+    // rollouts through the run-time-n family (lane-per-joint kernels)
+    if ((want == "jit-long" || (want == "auto" && jit_on && !is_c32)) && n > RB_JIT_MAX_N && n <= RB_JIT_LONG_MAX_N) {
+        RbJitImage img; std::string log;
+        int rc = rb_jit_compile(g->model, img, log);
+        if (rc == RB_OK) { std::string err; rc = rb_jit_load(img, n, g->jit, err); if (rc != RB_OK) log = err; }
+        if (rc == RB_OK) {
+            g->ops = rb_ops_jit_long();
+            g->param.assign(sizeof(RbJitParam), 0);
+            memcpy(g->param.data(), &g->jit, sizeof(RbJitParam));
+            g->family_note = img.from_cache ? "kernels from the disk cache" : "kernels compiled with NVRTC";
+            return setup_generic_n(g, flat, &g->ops2, &g->param2);
+        }
+        if (want == "jit-long") return fail(rc, "run-time specialisation failed: " + log);
+        g->family_note = "run-time specialisation unavailable (" + log.substr(0, 200) + "); using run-time-n kernels";
+    } else if (want == "jit-long") {
+        return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=jit-long serves chains of 19..32 joints");
+    }
     if ((want == "auto" || want == "generic-7") && n == 7) {
         g->ops = rb_ops_rt7();
         g->param.assign(g->ops->param_bytes, 0);
@@ -220,7 +238,7 @@ int pick_ops(RbGpu* g) {
         return RB_OK;
     }
     if (want == "generic-7") return fail(RB_ERR_UNSUPPORTED, "RIGIDBODY_B200_VARIANT=generic-7 needs a 7-joint chain");
-    if (want != "auto" && want != "generic-n" && want != "chain32-specialised" && want != "jit-specialised")
+    if (want != "auto" && want != "generic-n" && want != "chain32-specialised" && want != "jit-specialised" && want != "jit-long")
         return fail(RB_ERR_ARG, "unknown RIGIDBODY_B200_VARIANT '" + want + "'");
     if ((want == "auto" || want == "chain32-specialised") && is_c32) {
         g->ops = rb_ops_chain32();

@@ -81,6 +81,12 @@ const char* const kKernelExprs[RB_JIT_KERNELS] = {
     "rb_crba_kernel<CtModel<TabJit>>",        "rb_fwd_kin_kernel<CtModel<TabJit>>",
     "rb_jac_kernel<CtModel<TabJit>>",         "rb_rollout_kernel<CtModel<TabJit>>",
     "rb_rnea_kernel<CtModel<TabJit, float>, false>", "rb_fd_kernel<CtModel<TabJit, float>, false>"};
+// chains of RB_JIT_MAX_N+1 .. RB_JIT_LONG_MAX_N joints: the long-chain layouts of rb_kernels_long.cuh for rnea / crba
+// (no n x n array in the thread), the plain kernels for fwd_kin / jac, nothing else
+const char* const kLongExprs[RB_JIT_KERNELS] = {
+    "rb_long_rnea_kernel<CtModel<TabJit>>", nullptr, nullptr, nullptr,
+    "rb_long_crba_kernel<CtModel<TabJit>>", "rb_fwd_kin_kernel<CtModel<TabJit>>",
+    "rb_jac_kernel<CtModel<TabJit>>",       nullptr, nullptr, nullptr};
 const char* const kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DRB_DEVICE_ONLY=1"};
 
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -137,11 +143,18 @@ void cache_write(const std::string& file, const RbJitImage& img) {
 }  // namespace
 
 int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
-    if (m.n < 1 || m.n > RB_JIT_MAX_N) { log = "chain too long for register-resident kernels"; return RB_ERR_UNSUPPORTED; }
+    if (m.n < 1 || m.n > RB_JIT_LONG_MAX_N) { log = "chain too long for unrolled kernels"; return RB_ERR_UNSUPPORTED; }
+    // beyond RB_JIT_MAX_N joints the unrolled forward dynamics / rollout are no longer worth their compile time (nor
+    // faster than the lane-per-joint kernel): compile the O(n) and output-bound kernels only
+    const bool long_set = m.n > RB_JIT_MAX_N;
+    if (long_set && !m.serial) { log = "trees beyond 18 joints run on the run-time-n family"; return RB_ERR_UNSUPPORTED; }
+    const char* const* exprs = long_set ? kLongExprs : kKernelExprs;
+    auto wanted = [&](int k) { return exprs[k] != nullptr; };
     std::string err;
     const Nvrtc* nv = load_nvrtc(err);
     if (!nv) { log = err; return RB_ERR_UNSUPPORTED; }
-    const std::string main_src = std::string("#include \"rb_kernels.cuh\"\n") + rb_model_emit_header(m, "TabJit");
+    const std::string main_src = std::string(long_set ? "#include \"rb_kernels_long.cuh\"\n" : "#include \"rb_kernels.cuh\"\n") +
+                                 rb_model_emit_header(m, "TabJit");
 
     // cache key: everything that determines the cubin
     int vmaj = 0, vmin = 0;
@@ -170,7 +183,7 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     if (nv->CreateProgram(&prog, main_src.c_str(), "rb_jit_model.cu", rb_jit_src_count, rb_jit_src_texts, rb_jit_src_names) != 0) {
         log = "nvrtcCreateProgram failed"; return RB_ERR_CUDA;
     }
-    for (const char* e : kKernelExprs) nv->AddNameExpression(prog, e);
+    for (int k = 0; k < RB_JIT_KERNELS; ++k) if (wanted(k)) nv->AddNameExpression(prog, exprs[k]);
     std::vector<const char*> opts(kOptions, kOptions + sizeof kOptions / sizeof kOptions[0]);
     for (const std::string& o : extra) opts.push_back(o.c_str());
     const int rc = nv->CompileProgram(prog, (int)opts.size(), opts.data());
@@ -179,8 +192,10 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     if (ls > 1) { std::string l(ls, '\0'); nv->GetProgramLog(prog, &l[0]); log = l; }
     if (rc != 0) { nv->DestroyProgram(&prog); if (log.empty()) log = "nvrtcCompileProgram failed"; return RB_ERR_CUDA; }
     img.lowered.clear();
-    for (const char* e : kKernelExprs) {
+    for (int k = 0; k < RB_JIT_KERNELS; ++k) {
+        const char* e = exprs[k];
         const char* low = nullptr;
+        if (!wanted(k)) { img.lowered.push_back(std::string()); continue; }        // not part of this chain's kernel set
         if (nv->GetLoweredName(prog, e, &low) != 0 || !low) { nv->DestroyProgram(&prog); log = std::string("no lowered name for ") + e; return RB_ERR_CUDA; }
         img.lowered.push_back(low);
     }
@@ -202,6 +217,7 @@ int rb_jit_load(const RbJitImage& img, int n, RbJitParam& out, std::string& err)
     out.n = n;
     for (int k = 0; k < RB_JIT_KERNELS; ++k) {
         cudaKernel_t kern = nullptr;
+        if (img.lowered[k].empty()) { out.k[k] = nullptr; continue; }
         e = cudaLibraryGetKernel(&kern, lib, img.lowered[k].c_str());
         if (e != cudaSuccess) { err = std::string("cudaLibraryGetKernel(") + img.lowered[k] + "): " + cudaGetErrorString(e); cudaLibraryUnload(lib); out.lib = nullptr; return RB_ERR_CUDA; }
         out.k[k] = kern;
@@ -210,7 +226,7 @@ int rb_jit_load(const RbJitImage& img, int n, RbJitParam& out, std::string& err)
     const int aos_smem = 3 * RB_BLOCK * n * (int)sizeof(double);
     if (aos_smem > 48 * 1024)
         for (int k : {RB_JK_RNEA_AOS, RB_JK_FD_AOS})
-            cudaFuncSetAttribute((const void*)out.k[k], cudaFuncAttributeMaxDynamicSharedMemorySize, aos_smem);
+            if (out.k[k]) cudaFuncSetAttribute((const void*)out.k[k], cudaFuncAttributeMaxDynamicSharedMemorySize, aos_smem);
     return RB_OK;
 }
 
@@ -286,6 +302,12 @@ cudaError_t j_fd_f32(const void* param, const float* q, const float* dq, const f
     return cudaLaunchKernel((const void*)P->k[RB_JK_FD_F32], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
 }
 }  // namespace
+
+const RbOps* rb_ops_jit_long() {
+    static const RbOps ops = {"jit-long", 0, sizeof(RbJitParam), false, &j_rnea, nullptr, nullptr, nullptr,
+                              &j_crba, &j_fk, &j_jac, nullptr, nullptr, nullptr};
+    return &ops;
+}
 
 const RbOps* rb_ops_jit() {
     static const RbOps ops = {"jit-specialised", 0, sizeof(RbJitParam), false, &j_rnea, &j_fd, &j_rnea_aos, &j_fd_aos,

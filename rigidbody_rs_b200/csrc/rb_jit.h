@@ -5,6 +5,7 @@
 #include "rb_host_model.h"
 
 #define RB_JIT_MAX_N 18        // longest chain the register-resident unrolled kernels are compiled for (FD falls off a cliff at 20)
+#define RB_JIT_LONG_MAX_N 32   // 19..32 joints: only rnea / crba / fwd_kin / jac are compiled ("jit-long"); the rest falls through
 #define RB_JIT_KERNELS 10
 enum : int { RB_JK_RNEA = 0, RB_JK_RNEA_AOS, RB_JK_FD, RB_JK_FD_AOS, RB_JK_CRBA, RB_JK_FK, RB_JK_JAC, RB_JK_ROLLOUT,
              RB_JK_RNEA_F32, RB_JK_FD_F32 };
@@ -29,3 +30,4 @@ void rb_jit_unload(RbJitParam& p);
 
 struct RbOps;
 const RbOps* rb_ops_jit();
+const RbOps* rb_ops_jit_long();   // the partial table of chains of RB_JIT_MAX_N+1 .. RB_JIT_LONG_MAX_N joints

@@ -155,7 +155,7 @@ RB_DI void rb_aos_store(T* __restrict__ out, size_t B, T* buf, const T (&v)[N]) 
 }
 
 template <class M, bool AOS = false>
-__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_RNEA_RT : (M::N <= 8 ? RB_MINB_RNEA : (M::N <= 14 ? RB_MINB_RNEA_LONG : RB_MINB_RNEA_XLONG)))
+__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_RNEA_RT : (M::N <= 8 ? RB_MINB_RNEA : (M::N <= 14 ? RB_MINB_RNEA_LONG : (M::N <= 18 ? RB_MINB_RNEA_XLONG : 2))))
 rb_rnea_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
                const RB_R* __restrict__ ddq, RB_R* __restrict__ tau, size_t B, size_t ld) {
     constexpr int N = M::N;

@@ -11,7 +11,9 @@
 //     (rb_kernels_warp.cu, 0.218 G evals/s) serve it through the fallback table.
 #pragma once
 #include "rb_kernels.cuh"
+#ifndef RB_DEVICE_ONLY
 #include "rb_util.cuh"
+#endif
 
 #ifndef RB_MINB_LONG
 #define RB_MINB_LONG 2
@@ -52,6 +54,7 @@ rb_long_crba_kernel(const __grid_constant__ typename M::Param p, const double* _
     });
 }
 
+#ifndef RB_DEVICE_ONLY
 template <class M>
 struct RbLaunchLong {
     using MP = typename M::Param;
@@ -76,3 +79,4 @@ struct RbLaunchLong {
         return o;
     }
 };
+#endif  // RB_DEVICE_ONLY

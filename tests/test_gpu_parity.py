@@ -531,7 +531,9 @@ def test_long_random_chains(rb, n, seed):
     R, t, m, c, Ic = _random_chain(n, seed)
     t = t * (8.0 / n)                                    # keep the reach (and cond(H)) comparable across lengths
     mb = rb.Multibody.from_descriptor(R, t, m, c, Ic)
-    assert mb.kernel_variant == ("jit-specialised" if n <= 18 else "generic-n")     # 13: the longest unrolled kernels the tests compile
+    # <= 18 joints: every kernel specialised at load time; 19..32: rnea / crba / fwd_kin / jac specialised ("jit-long"), forward
+    # dynamics through the lane-per-joint kernel; beyond: loop-based kernels and the shared-memory tile solver
+    assert mb.kernel_variant == ("jit-specialised" if n <= 18 else ("jit-long" if n <= 32 else "generic-n"))
     ch = ChainNP.from_arrays(R, t, m, c, Ic)
     rng = np.random.default_rng(seed)
     B = 333

@@ -283,5 +283,9 @@ def test_jit_precompile_without_gpu(rb, tmp_path, monkeypatch):
     d.gravity[:] = [0.0, 0.0, 9.81]
     assert _lib.lib.multibody_jit_precompile(C.byref(d), None, log, 8192) == 0, (_lib.lib.multibody_last_error(), log.value)
     assert len(os.listdir(tmp_path / "cache")) == 2
-    # chains longer than the register-resident limit are refused, not miscompiled
-    assert _lib.lib.multibody_jit_precompile(None, CHAIN32.encode(), log, 8192) == _lib.RB_ERR_UNSUPPORTED
+    # chains beyond the unrolled kernels' limit (32 joints) are refused, not miscompiled
+    R, t, m, c, Ic = _random_chain(33, 12)
+    keep = [np.ascontiguousarray(x) for x in (R, t, m, c, Ic)]
+    d.n_joints = 33
+    d.parent_rot, d.parent_trans, d.mass, d.com, d.inertia_com = (dp(x) for x in keep)
+    assert _lib.lib.multibody_jit_precompile(C.byref(d), None, log, 8192) == _lib.RB_ERR_UNSUPPORTED
