@@ -11,6 +11,7 @@
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <type_traits>
 #else
 typedef unsigned int uint32_t;
@@ -481,15 +482,15 @@ struct RbLaunch {
     static unsigned grid(size_t B) { return (unsigned)((B + RB_BLOCK - 1) / RB_BLOCK); }
     // SM count of the current device (cached per device ordinal).
     static int sm_count() {
-        static int cache[64] = {0};
+        static std::atomic<int> cache[64];
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-        if (cache[dev] == 0) {
-            int v = 0;
+        int v = cache[dev].load(std::memory_order_relaxed);
+        if (v == 0) {
             if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-            cache[dev] = v;
+            cache[dev].store(v, std::memory_order_relaxed);
         }
-        return cache[dev];
+        return v;
     }
     // Full tiles go through the persistent TMA-fed kernel when rows are 16-byte aligned; the ragged tail
     // (and unaligned or tiny batches) through the one-tile-per-block kernel.
@@ -504,13 +505,13 @@ struct RbLaunch {
         if (!aligned || tiles < 2 * (size_t)cap || tiles > 0xFFFFFFF0u) return cudaSuccess;
         auto k = rb_stream_kernel<M, MINB, IS_FD>;
         constexpr size_t smem = (size_t)RB_STAGES * 3 * M::N * RB_BLOCK * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
+        static std::atomic<bool> configured{false};
+        if (!configured.load(std::memory_order_acquire)) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
-            configured = true;
+            configured.store(true, std::memory_order_release);
         }
         k<<<cap, RB_BLOCK, smem, st>>>(p, a, b, c, out, (unsigned)tiles, ld, status);
         *done = tiles * RB_BLOCK;

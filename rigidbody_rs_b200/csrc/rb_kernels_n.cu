@@ -3,6 +3,7 @@
 //
 // generic-n: persistent grid-stride kernels; the model rows sit in global memory (uniform loads, cached in
 // L1/constant path); per-thread per-link state goes to a strided scratch [slot][thread] in HBM.
+#include <atomic>
 #include "rb_kernels.cuh"
 #include "rb_dyn_n.cuh"
 #include "rb_util.cuh"
@@ -370,11 +371,13 @@ cudaError_t n_rnea(const void* param, const double* q, const double* dq, const d
 template <int TS>
 cudaError_t launch_tile(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld, int* status,
                         size_t smem, int dev, int sms, cudaStream_t st) {
-    static size_t configured[64] = {0};     // per device: largest dynamic shared-memory size opted into
-    if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+    // per device: largest dynamic shared-memory size opted into (atomic: handles may be created from several threads;
+    // setting the attribute twice is harmless, a torn read is not)
+    static std::atomic<size_t> configured[64];
+    if (dev >= 0 && dev < 64 && smem > configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(rbn_ldlt_tile_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[dev] = smem;
+        configured[dev].store(smem, std::memory_order_release);
     }
     const size_t tiles = (cnt + TS - 1) / TS;
     size_t per_sm = (size_t)(220 * 1024) / (smem + 1024);

@@ -22,6 +22,7 @@
 // Same result as  qdd = solve(sym(crba(q)), tau - rnea(q, dq, 0))   up to rounding: the world-frame
 // sums associate differently from the reference's link-frame recursion (measured 5e-14 relative on the 32-joint
 // chain, cond(H) ~ 1e4).
+#include <atomic>
 #include "rb_kernels.cuh"
 #include "rb_util.cuh"
 
@@ -737,20 +738,20 @@ cudaError_t rb_launch_warp_fd(const double* model, int n, const double* q, const
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     constexpr size_t smem = ((size_t)RBW_WARPS * RBW_PER_WARP + RBW_MODEL_DOUBLES) * sizeof(double);
-    static bool configured[64] = {false};
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
+    static std::atomic<bool> configured[64];                 // per device; setting the attribute twice is harmless
+    if (dev >= 0 && dev < 64 && !configured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(rbw_fd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[dev] = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     const size_t groups = (B + RBW_GROUP - 1) / RBW_GROUP;
 #if RBW_HALF
     constexpr size_t hsmem = ((size_t)RBW_HWARPS * RBH_PER_WARP + RBH_MODEL) * sizeof(double);
-    static bool hconfigured[64] = {false};
-    if (dev >= 0 && dev < 64 && !hconfigured[dev]) {
+    static std::atomic<bool> hconfigured[64];
+    if (dev >= 0 && dev < 64 && !hconfigured[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(rbh_fd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
         if (e != cudaSuccess) return e;
-        hconfigured[dev] = true;
+        hconfigured[dev].store(true, std::memory_order_release);
     }
     const size_t hwant = (groups + RBW_HWARPS - 1) / RBW_HWARPS;
     rbh_fd_kernel<<<(unsigned)(hwant < (size_t)sms ? hwant : (size_t)sms), 32 * RBW_HWARPS, hsmem, st>>>(model, n, q, dq, tau, qdd, B, ld, status);
