@@ -522,7 +522,7 @@ def test_inverse_dynamics_derivatives_chain32(rb, mb_chain32, oracle_chain32):
     assert np.abs(gv - Dv).max() < TOL * max(1.0, np.abs(Dv).max())
 
 
-@pytest.mark.parametrize("n,seed", [(13, 1), (18, 7), (19, 6), (24, 2), (32, 3), (33, 4), (64, 5)])
+@pytest.mark.parametrize("n,seed", [(13, 1), (15, 7), (19, 6), (24, 2), (32, 3), (33, 4), (64, 5)])
 def test_long_random_chains(rb, n, seed):
     """Chains beyond the register-resident limit: run-time-n kernels; forward dynamics by the warp-per-state kernel
     up to 32 joints (idle lanes padded) and by the shared-memory tile solver beyond."""
