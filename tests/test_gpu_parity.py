@@ -780,3 +780,12 @@ def test_full_size_properties_16M(mb_fr3, oracle_fr3):
     assert state_err(tau[:, idx].cpu().numpy(), oracle_fr3.rnea_batch(qs, dqs, ddqs), 0).max() < TOL
     want = oracle_fr3.fill(0x5EED0001, 0, lim["lower"], lim["upper"], 0, 8)
     np.testing.assert_array_equal(q[:, :8].cpu().numpy(), want)
+
+
+def test_cpp_example_runs(rb, tmp_path):
+    """examples/batch_demo.cpp through the C ABI from C++: single-state symbols, batched calls, one-call entry point."""
+    import subprocess
+    from test_host import _build_example
+    r = subprocess.run([_build_example(tmp_path), FR3], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "fr3-specialised" in r.stdout

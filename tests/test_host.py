@@ -289,3 +289,25 @@ def test_jit_precompile_without_gpu(rb, tmp_path, monkeypatch):
     d.n_joints = 33
     d.parent_rot, d.parent_trans, d.mass, d.com, d.inertia_com = (dp(x) for x in keep)
     assert _lib.lib.multibody_jit_precompile(C.byref(d), None, log, 8192) == _lib.RB_ERR_UNSUPPORTED
+
+
+def _build_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "batch_demo")
+    libdir = os.path.join(ROOT, "rigidbody_rs_b200")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "batch_demo.cpp"),
+                    "-L" + libdir, "-lrigidbody_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_example_builds_against_the_c_abi(rb, tmp_path):
+    """examples/batch_demo.cpp: a C++ program using only include/rigidbody.h links against the library; without a GPU
+    it reports the error instead of computing anything."""
+    import subprocess
+    import torch
+    exe = _build_example(tmp_path)
+    r = subprocess.run([exe, FR3], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stdout
