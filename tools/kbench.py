@@ -39,6 +39,12 @@ for op in a.ops.split(","):
         qc = q[:, :Bc].contiguous(); Hout = torch.empty((n * n, Bc), dtype=torch.float64, device=dev)
         fn = lambda: mb.crba(qc, out=Hout)
         units = Bc
+    elif op in ("fk", "jac"):
+        Bc = min(B, 1 << 23)
+        qc = q[:, :Bc].contiguous()
+        O = torch.empty((3 if op == "fk" else 6 * n, Bc), dtype=torch.float64, device=dev)
+        fn = (lambda: mb.fwd_kin(qc, out=O)) if op == "fk" else (lambda: mb.jac(qc, out=O))
+        units = Bc
     elif op in ("rnea_deriv", "fd_deriv"):
         Bc = min(B, 1 << 21)
         blocks = 2 if op == "rnea_deriv" else 3
