@@ -414,8 +414,11 @@ enum : int { RB_CW_QREF = 0, RB_CW_Q, RB_CW_DQ, RB_CW_TAU, RB_CW_QF, RB_CW_DQF, 
 #ifndef RB_RO_BLOCK
 #define RB_RO_BLOCK 128     // threads per rollout block (smaller blocks balance the single wave across 148 SMs)
 #endif
+#ifndef RB_RO_MINB
+#define RB_RO_MINB (RB_MINB_ROLLOUT * (RB_BLOCK / RB_RO_BLOCK))
+#endif
 template <class M>
-__global__ void __launch_bounds__(RB_RO_BLOCK, RB_MINB_ROLLOUT * (RB_BLOCK / RB_RO_BLOCK))
+__global__ void __launch_bounds__(RB_RO_BLOCK, RB_RO_MINB)
 rb_rollout_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q0, const RB_R* __restrict__ dq0,
                   const RB_R* __restrict__ tau, RB_R dt, int horizon, RB_R* __restrict__ q_traj,
                   RB_R* __restrict__ dq_traj, RB_R* __restrict__ q_fin, RB_R* __restrict__ dq_fin,
