@@ -67,6 +67,7 @@ struct RbGpu {
     size_t hpk_states = 0;
     RbJitParam jit{};                     // run-time compiled kernels (jit-specialised family); lib == nullptr if unused
     std::string family_note;              // why this family was chosen (e.g. the JIT fallback reason)
+    bool split_rnea_fd = false;           // $RIGIDBODY_B200_FUSED=0: multibody_rnea_fd_batch issues the two launches instead of the fused kernel
     double* d_model = nullptr;            // generic-n: model rows on the device
     DevBuf scratch;                       // generic-n: per-thread strided scratch
     DevBuf hpk;                           // generic-n: packed H of one chunk of states (forward dynamics)
@@ -285,6 +286,7 @@ int gpu_create(const RbHostModel& model, int device, RbGpu** out) {
     *g->h_status = 0;
     int rc = pick_ops(g);
     if (rc != RB_OK) return bail(rc);
+    if (const char* f = getenv("RIGIDBODY_B200_FUSED")) g->split_rnea_fd = std::string(f) == "0";
     *out = g;
     return RB_OK;
 }
@@ -617,6 +619,9 @@ extern "C" int multibody_rnea_fd_batch(RbGpu* g, const double* q, const double* 
     OpDesc op{4, {q, dq, ddq, tau_in}, {n, n, n, n}, out, 2 * n,
               [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
                   const int n = g->model.n;
+                  // one fused pass where the family has it (shared sin/cos, bias recursion and mass matrix)
+                  if (g->ops->rnea_fd && !g->split_rnea_fd)
+                      return g->ops->rnea_fd(g->param.data(), in[0], in[1], in[2], in[3], out, B, ld, g->d_status, st);
                   {
                       ScratchOrder so(g, RB_TABLE(g, rnea), st);
                       cudaError_t e = RB_TABLE(g, rnea)->rnea(RB_PARAM(g, rnea), in[0], in[1], in[2], out, B, ld, st);

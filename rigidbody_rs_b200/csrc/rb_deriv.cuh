@@ -243,37 +243,4 @@ RB_DI void rb_rnea_derivatives(const RbModelK<N>& p, const double* sn, const dou
     }
 }
 
-// LDL^T of the upper triangle in place (A(j,i) <- L(i,j) for i > j; the diagonal keeps d_j) and its application to
-// right-hand sides: the factor-once / solve-many split of rb_ldlt_solve (rb_dyn.cuh), same operation order.
-template <int N>
-RB_DI bool rb_ldlt_factor(double (&A)[N][N], double (&dinv)[N]) {
-    bool ok = true;
-    rb_for_up<0, N>([&](auto jc) {                           // compile-time indices: see rb_ldlt_solve_static
-        constexpr int J = decltype(jc)::value;
-        const double d = A[J][J];
-        ok = ok && (d > 0.0);
-        dinv[J] = rb_rcp_pos(d);
-        rb_for_up<J + 1, N>([&](auto ic) {
-            constexpr int I = decltype(ic)::value;
-            const double l = A[J][I] * dinv[J];
-            rb_for_up<I, N>([&](auto kc) {
-                constexpr int K = decltype(kc)::value;
-                A[I][K] = fma(-l, A[J][K], A[I][K]);
-            });
-            A[J][I] = l;
-        });
-    });
-    return ok;
-}
-template <int N>
-RB_DI void rb_ldlt_apply(const double (&A)[N][N], const double (&dinv)[N], double (&x)[N]) {
-    rb_for_up<0, N>([&](auto jc) {
-        constexpr int J = decltype(jc)::value;
-        rb_for_up<J + 1, N>([&](auto ic) { constexpr int I = decltype(ic)::value; x[I] = fma(-A[J][I], x[J], x[I]); });
-    });
-    rb_for_up<0, N>([&](auto jc) { constexpr int J = decltype(jc)::value; x[J] *= dinv[J]; });
-    rb_for_down<N - 1>([&](auto ic) {
-        constexpr int I = decltype(ic)::value;
-        rb_for_up<I + 1, N>([&](auto kc) { constexpr int K = decltype(kc)::value; x[I] = fma(-A[I][K], x[K], x[I]); });
-    });
-}
+// (the factor-once / solve-many split of the LDL^T, rb_ldlt_factor / rb_ldlt_apply, lives in rb_dyn.cuh)

@@ -480,6 +480,49 @@ RB_DI bool rb_ldlt_solve_static(T (&A)[N][N], T (&x)[N]) {
     return ok;
 }
 
+// The same LDL^T in two halves, for callers that factorise and solve in different places (the warp-specialised rollout
+// hands L and 1/d from one warp to another).  Operation for operation rb_ldlt_solve / rb_ldlt_solve_static: a
+// factorisation here followed by rb_ldlt_apply gives bit-identical results.
+template <int N, class T>
+RB_DI bool rb_ldlt_factor(T (&A)[N][N], T (&dinv)[N]) {
+    bool ok = true;
+    rb_for_up<0, N>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        const T d = A[J][J];
+        ok = ok && (d > T(0));
+        dinv[J] = rb_rcp_pos(d);
+        rb_for_up<J + 1, N>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            const T l = A[J][I] * dinv[J];
+            rb_for_up<I, N>([&](auto kc) {
+                constexpr int K = decltype(kc)::value;
+                A[I][K] = fma(-l, A[J][K], A[I][K]);
+            });
+            A[J][I] = l;
+        });
+    });
+    return ok;
+}
+// x <- (L D L^T)^-1 x with L(I, J) = getL(RbIC<J>, RbIC<I>) for J < I (the strict upper triangle rb_ldlt_factor leaves).
+template <int N, class T, class GetL>
+RB_DI void rb_ldlt_apply_fn(GetL&& getL, const T (&dinv)[N], T (&x)[N]) {
+    rb_for_up<0, N>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        rb_for_up<J + 1, N>([&](auto ic) { constexpr int I = decltype(ic)::value; x[I] = fma(-getL(RbIC<J>{}, RbIC<I>{}), x[J], x[I]); });
+    });
+    rb_for_up<0, N>([&](auto jc) { constexpr int J = decltype(jc)::value; x[J] *= dinv[J]; });
+    rb_for_down<N - 1>([&](auto ic) {
+        constexpr int I = decltype(ic)::value;
+        rb_for_up<I + 1, N>([&](auto kc) { constexpr int K = decltype(kc)::value; x[I] = fma(-getL(RbIC<I>{}, RbIC<K>{}), x[K], x[I]); });
+    });
+}
+
+// ... with L in the array rb_ldlt_factor left it in.
+template <int N, class T>
+RB_DI void rb_ldlt_apply(const T (&A)[N][N], const T (&dinv)[N], T (&x)[N]) {
+    rb_ldlt_apply_fn<N>([&](auto jc, auto ic) { return A[decltype(jc)::value][decltype(ic)::value]; }, dinv, x);
+}
+
 // ------------------------------------------------------------------ forward dynamics
 // qdd = solve(sym(crba(q)), tau - rnea(q, dq, 0)); sin/cos computed once and shared by both halves.
 template <class M>
@@ -494,6 +537,40 @@ RB_DI bool rb_forward_dynamics(const typename M::Param& p, const RB_R (&s)[M::N]
     }
     RB_R H[N][N];
     rb_crba<M>(p, s, c, H);
+    if constexpr (N > 7) return rb_ldlt_solve_static<N>(H, qdd);
+    else return rb_ldlt_solve<N>(H, qdd);
+}
+
+// ------------------------------------------------------------------ inverse + forward dynamics of ONE state, fused
+// What multibody_rnea_fd_batch asks for: tau = rnea(q, dq, ddq) (multibody.rs:111-153) and
+// qdd = solve(sym(crba(q)), tau_in - rnea(q, dq, 0)) (:155-174 + the solve) of the same (q, dq).  Everything the two
+// share is computed once: sin/cos, the bias recursion rnea(q, dq, 0) and the mass matrix.  The inverse-dynamics result
+// then comes from the identity the equations of motion are (and tests/test_oracle.py pins):
+//     rnea(q, dq, ddq) = sym(crba(q)) ddq + rnea(q, dq, 0),
+// accumulated entry by entry while CRBA produces H (49 FMAs for 7 joints instead of a second ~500-instruction
+// recursion).  Rounding differs from the recursion by a few ulp of sum_j |H_ij| |ddq_j| (measured <= 2e-14 relative on
+// the FR3, tests/test_gpu_parity.py::test_fused_rnea_fd*), far inside the 1e-10 bar.
+template <class M>
+RB_DI bool rb_rnea_fd_fused(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
+                            const RB_R (&dq)[M::N], const RB_R (&ddq)[M::N], const RB_R (&tau_in)[M::N],
+                            RB_R (&tau)[M::N], RB_R (&qdd)[M::N]) {
+    constexpr int N = M::N;
+    rb_rnea<M, false>(p, s, c, dq, dq /*unused*/, tau);            // bias
+#pragma unroll
+    for (int i = 0; i < N; ++i) qdd[i] = tau_in[i] - tau[i];
+    RB_R H[N][N];
+    if constexpr (M::kTree) {
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int k = 0; k < N; ++k) H[r][k] = RB_R(0);
+    }
+    rb_crba_put<M>(p, s, c, [&](auto jc, auto ic, RB_R v) {
+        constexpr int J = decltype(jc)::value, I = decltype(ic)::value;
+        H[J][I] = v;
+        tau[J] = fma(v, ddq[I], tau[J]);
+        if constexpr (J != I) tau[I] = fma(v, ddq[J], tau[I]);
+    });
     if constexpr (N > 7) return rb_ldlt_solve_static<N>(H, qdd);
     else return rb_ldlt_solve<N>(H, qdd);
 }

@@ -80,13 +80,14 @@ const char* const kKernelExprs[RB_JIT_KERNELS] = {
     "rb_fd_kernel<CtModel<TabJit>, false>",   "rb_fd_kernel<CtModel<TabJit>, true>",
     "rb_crba_kernel<CtModel<TabJit>>",        "rb_fwd_kin_kernel<CtModel<TabJit>>",
     "rb_jac_kernel<CtModel<TabJit>>",         "rb_rollout_kernel<CtModel<TabJit>>",
-    "rb_rnea_kernel<CtModel<TabJit, float>, false>", "rb_fd_kernel<CtModel<TabJit, float>, false>"};
+    "rb_rnea_kernel<CtModel<TabJit, float>, false>", "rb_fd_kernel<CtModel<TabJit, float>, false>",
+    "rb_rnea_fd_kernel<CtModel<TabJit>>",     "rb_rollout_ws_kernel<CtModel<TabJit>>"};
 // chains of RB_JIT_MAX_N+1 .. RB_JIT_LONG_MAX_N joints: the long-chain layouts of rb_kernels_long.cuh for rnea / crba
 // (no n x n array in the thread), the plain kernels for fwd_kin / jac, nothing else
 const char* const kLongExprs[RB_JIT_KERNELS] = {
     "rb_long_rnea_kernel<CtModel<TabJit>>", nullptr, nullptr, nullptr,
     "rb_long_crba_kernel<CtModel<TabJit>>", "rb_fwd_kin_kernel<CtModel<TabJit>>",
-    "rb_jac_kernel<CtModel<TabJit>>",       nullptr, nullptr, nullptr};
+    "rb_jac_kernel<CtModel<TabJit>>",       nullptr, nullptr, nullptr, nullptr, nullptr};
 const char* const kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DRB_DEVICE_ONLY=1"};
 
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -149,7 +150,7 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     const bool long_set = m.n > RB_JIT_MAX_N;
     if (long_set && !m.serial) { log = "trees beyond 18 joints run on the run-time-n family"; return RB_ERR_UNSUPPORTED; }
     const char* const* exprs = long_set ? kLongExprs : kKernelExprs;
-    auto wanted = [&](int k) { return exprs[k] != nullptr; };
+    auto wanted = [&](int k) { return exprs[k] != nullptr && !(k == RB_JK_ROLLOUT_WS && m.n > RB_RO2_MAX_N); };   // static shared memory of the two-warp rollout
     std::string err;
     const Nvrtc* nv = load_nvrtc(err);
     if (!nv) { log = err; return RB_ERR_UNSUPPORTED; }
@@ -285,6 +286,8 @@ cudaError_t j_rollout(const void* param, const double* q0, const double* dq0, co
     if (B == 0) return cudaSuccess;
     RbEmptyParam ep{0};
     void* args[] = {&ep, &q0, &dq0, &tau, &dt, &horizon, &q_traj, &dq_traj, &q_fin, &dq_fin, &B, &ld, &status, &cost_w, &cost};
+    if (P->n <= RB_RO2_MAX_N && P->k[RB_JK_ROLLOUT_WS] && rb_rollout_mode() != 1)
+        return cudaLaunchKernel((const void*)P->k[RB_JK_ROLLOUT_WS], dim3(jgrid(B, 32)), dim3(64), args, 0, st);
     return cudaLaunchKernel((const void*)P->k[RB_JK_ROLLOUT], dim3(jgrid(B, RB_RO_BLOCK)), dim3(RB_RO_BLOCK), args, 0, st);
 }
 cudaError_t j_rnea_f32(const void* param, const float* q, const float* dq, const float* ddq, float* tau, size_t B, size_t ld, cudaStream_t st) {
@@ -301,6 +304,14 @@ cudaError_t j_fd_f32(const void* param, const float* q, const float* dq, const f
     void* args[] = {&ep, &q, &dq, &tau, &qdd, &B, &ld, &status};
     return cudaLaunchKernel((const void*)P->k[RB_JK_FD_F32], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
 }
+cudaError_t j_rnea_fd(const void* param, const double* q, const double* dq, const double* ddq, const double* tau_in, double* out,
+                      size_t B, size_t ld, int* status, cudaStream_t st) {
+    const RbJitParam* P = (const RbJitParam*)param;
+    if (B == 0) return cudaSuccess;
+    RbEmptyParam ep{0};
+    void* args[] = {&ep, &q, &dq, &ddq, &tau_in, &out, &B, &ld, &status};
+    return cudaLaunchKernel((const void*)P->k[RB_JK_RNEA_FD], dim3(jgrid(B, RB_BLOCK)), dim3(RB_BLOCK), args, 0, st);
+}
 }  // namespace
 
 const RbOps* rb_ops_jit_long() {
@@ -311,6 +322,6 @@ const RbOps* rb_ops_jit_long() {
 
 const RbOps* rb_ops_jit() {
     static const RbOps ops = {"jit-specialised", 0, sizeof(RbJitParam), false, &j_rnea, &j_fd, &j_rnea_aos, &j_fd_aos,
-                              &j_crba, &j_fk, &j_jac, &j_rollout, &j_rnea_f32, &j_fd_f32};
+                              &j_crba, &j_fk, &j_jac, &j_rollout, &j_rnea_f32, &j_fd_f32, &j_rnea_fd};
     return &ops;
 }

@@ -19,7 +19,6 @@ typedef unsigned long long uint64_t;
 typedef unsigned long uintptr_t;
 #endif
 #include "rb_dyn.cuh"
-#include "rb_tma.cuh"
 
 #ifndef RB_BLOCK
 #define RB_BLOCK 128
@@ -49,7 +48,10 @@ typedef unsigned long uintptr_t;
 #define RB_MINB_FD_RT 2
 #endif
 #ifndef RB_STREAM
-#define RB_STREAM 0        // 1 = route full tiles through the persistent TMA-fed kernels (measured slower)
+#define RB_STREAM 0        // 1 = route full tiles through the persistent TMA-fed kernels (experiments/, measured slower)
+#endif
+#ifndef RB_PREFETCH
+#define RB_PREFETCH 0      // 1 = persistent kernels with register prefetch (experiments/, measured slower)
 #endif
 
 #ifndef RB_DEVICE_ONLY
@@ -79,8 +81,16 @@ struct RbOps {
                             size_t B, size_t ld, cudaStream_t st);
     cudaError_t (*fd_f32)(const void* param, const float* q, const float* dq, const float* tau, float* qdd,
                           size_t B, size_t ld, int* status, cudaStream_t st);
+    // optional: tau = rnea(q, dq, ddq) and qdd = fd(q, dq, tau_in) in ONE pass over SoA batches, out = [2n][ld]
+    // (null = the API issues the rnea and fd launches back to back).  Keep this entry last: the positional
+    // initialisers of the partial tables leave it null.
+    cudaError_t (*rnea_fd)(const void* param, const double* q, const double* dq, const double* ddq, const double* tau_in,
+                           double* out, size_t B, size_t ld, int* status, cudaStream_t st);
 };
 
+// $RIGIDBODY_B200_ROLLOUT: "thread" = 1 (one thread per trajectory, rb_rollout_kernel), anything else / unset = 0
+// (two warps per 32 trajectories, rb_rollout_ws_kernel).  Read at every launch.
+int rb_rollout_mode();
 const RbOps* rb_ops_fr3();        // compile-time FR3 model (rb_kernels_fr3.cu)
 const RbOps* rb_ops_rt7();        // any 7-joint chain, run-time constants (rb_kernels_rt.cu)
 const RbOps* rb_ops_generic_n();  // any chain length (rb_kernels_n.cu)
@@ -213,147 +223,39 @@ rb_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict
     }
 }
 
-// ------------------------------------------------------------------ persistent variants with register prefetch (experiment)
-// A thread walks states s, s + T, s + 2T, ... and issues the loads of its NEXT state before computing the current one,
-// so every warp always has arithmetic to overlap its own memory latency (the one-shot kernels rely on other warps).
-#ifndef RB_PREFETCH
-#define RB_PREFETCH 0
-#endif
-#if RB_PREFETCH
-#ifndef RB_PF_MINB_RNEA
-#define RB_PF_MINB_RNEA 3
-#endif
-#ifndef RB_PF_MINB_FD
-#define RB_PF_MINB_FD 3
+// Inverse + forward dynamics of the same states in one pass (multibody_rnea_fd_batch): 4n doubles in, 2n out
+// (336 B per FR3 state instead of the 448 B of two launches), shared sin/cos, bias recursion and mass matrix
+// (rb_rnea_fd_fused).  out holds tau in rows 0..n-1 and qdd in rows n..2n-1.
+#ifndef RB_MINB_FUSED
+#define RB_MINB_FUSED RB_MINB_FD
 #endif
 template <class M>
-__global__ void __launch_bounds__(RB_BLOCK, RB_PF_MINB_RNEA)
-rb_rnea_pf_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
-                  const double* __restrict__ ddq, double* __restrict__ tau, size_t B, size_t ld) {
+__global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_FD_RT : (M::N <= 11 ? RB_MINB_FUSED : RB_MINB_FD_LONG))
+rb_rnea_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q, const RB_R* __restrict__ dq,
+                  const RB_R* __restrict__ ddq, const RB_R* __restrict__ tau_in, RB_R* __restrict__ out,
+                  size_t B, size_t ld, int* __restrict__ status) {
     constexpr int N = M::N;
-    const size_t nthr = (size_t)gridDim.x * RB_BLOCK;
-    size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
+    const size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
     if (s >= B) return;
-    double a[N], b[N], c[N];
-    rb_load<N>(q, ld, s, a); rb_load<N>(dq, ld, s, b); rb_load<N>(ddq, ld, s, c);
-    while (true) {
-        const size_t s2 = s + nthr;
-        const bool more = s2 < B;
-        double a2[N], b2[N], c2[N];
-        if (more) { rb_load<N>(q, ld, s2, a2); rb_load<N>(dq, ld, s2, b2); rb_load<N>(ddq, ld, s2, c2); }
-        double sn[N], cs[N], t[N];
-        rb_sincos_all<N>(a, sn, cs);
-        rb_rnea<M, true>(p, sn, cs, b, c, t);
-        rb_store<N>(tau, ld, s, t);
-        if (!more) break;
+    RB_R a[N], b[N], c[N], d[N], sn[N], cs[N], t[N], x[N];
+    rb_load<N>(q, ld, s, a);
+    rb_load<N>(dq, ld, s, b);
+    rb_load<N>(ddq, ld, s, c);
+    rb_load<N>(tau_in, ld, s, d);
+    rb_sincos_all<N>(a, sn, cs);
+    const bool ok = rb_rnea_fd_fused<M>(p, sn, cs, b, c, d, t, x);
+    rb_store<N>(out, ld, s, t);
+    if (!ok) {
+        atomicOr(status, RB_STATUS_NOT_SPD);
 #pragma unroll
-        for (int i = 0; i < N; ++i) { a[i] = a2[i]; b[i] = b2[i]; c[i] = c2[i]; }
-        s = s2;
+        for (int i = 0; i < N; ++i) x[i] = rb_nan<RB_R>();
     }
+    rb_store<N>(out + (size_t)N * ld, ld, s, x);
 }
-template <class M>
-__global__ void __launch_bounds__(RB_BLOCK, RB_PF_MINB_FD)
-rb_fd_pf_kernel(const __grid_constant__ typename M::Param p, const double* __restrict__ q, const double* __restrict__ dq,
-                const double* __restrict__ tau, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
-    constexpr int N = M::N;
-    const size_t nthr = (size_t)gridDim.x * RB_BLOCK;
-    size_t s = (size_t)blockIdx.x * RB_BLOCK + threadIdx.x;
-    if (s >= B) return;
-    double a[N], b[N], c[N];
-    rb_load<N>(q, ld, s, a); rb_load<N>(dq, ld, s, b); rb_load<N>(tau, ld, s, c);
-    bool all_ok = true;
-    while (true) {
-        const size_t s2 = s + nthr;
-        const bool more = s2 < B;
-        double a2[N], b2[N], c2[N];
-        if (more) { rb_load<N>(q, ld, s2, a2); rb_load<N>(dq, ld, s2, b2); rb_load<N>(tau, ld, s2, c2); }
-        double sn[N], cs[N], x[N];
-        rb_sincos_all<N>(a, sn, cs);
-        const bool ok = rb_forward_dynamics<M>(p, sn, cs, b, c, x);
-        if (!ok) {
-            all_ok = false;
-#pragma unroll
-            for (int i = 0; i < N; ++i) x[i] = rb_nan<double>();
-        }
-        rb_store<N>(qdd, ld, s, x);
-        if (!more) break;
-#pragma unroll
-        for (int i = 0; i < N; ++i) { a[i] = a2[i]; b[i] = b2[i]; c[i] = c2[i]; }
-        s = s2;
-    }
-    if (!all_ok) atomicOr(status, RB_STATUS_NOT_SPD);
-}
-#endif
 
-// ------------------------------------------------------------------ streaming (persistent, TMA-fed) RNEA / FD
-// The one-tile-per-block kernels above leave each warp's 21 input loads exposed at the start of its life, so
-// HBM latency is hidden only by other resident warps -- and registers cap those at 16-20 per SM.  Here a
-// persistent block walks tiles of RB_BLOCK states; one elected thread asks the TMA unit to bulk-copy the
-// next tile's 3N input rows (RB_BLOCK*8 = 1 KiB contiguous each) into a 2-stage shared-memory ring while all
-// warps compute the current tile, and an mbarrier (transaction bytes) says when a stage has landed.  The
-// FP64 pipe then sees compute-phase warps only.  Requires 16-byte aligned rows (pointers % 16, ld % 2).
-#define RB_STAGES 2
-template <class M, int MINB, bool IS_FD>
-__global__ void __launch_bounds__(RB_BLOCK, MINB)
-rb_stream_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ in0, const RB_R* __restrict__ in1,
-                 const RB_R* __restrict__ in2, RB_R* __restrict__ out, unsigned num_tiles, size_t ld, int* __restrict__ status) {
-    constexpr int N = M::N, ROWS = 3 * N;
-    extern __shared__ __align__(128) double rb_stage[];      // [RB_STAGES][ROWS][RB_BLOCK]
-    __shared__ __align__(8) uint64_t bar[RB_STAGES];
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-#pragma unroll
-        for (int k = 0; k < RB_STAGES; ++k) rb_mbar_init(&bar[k], 1);
-        rb_fence_barrier_init();
-    }
-    __syncthreads();
-    auto issue = [&](unsigned tile, int st) {
-        const size_t s0 = (size_t)tile * RB_BLOCK;
-        RB_R* dst = rb_stage + (size_t)st * ROWS * RB_BLOCK;
-        rb_mbar_expect_tx(&bar[st], ROWS * RB_BLOCK * (uint32_t)sizeof(RB_R));
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const RB_R* src = (r < N ? in0 : (r < 2 * N ? in1 : in2)) + (size_t)(r % N) * ld + s0;
-            rb_bulk_g2s(dst + r * RB_BLOCK, src, RB_BLOCK * (uint32_t)sizeof(RB_R), &bar[st]);
-        }
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int k = 0; k < RB_STAGES; ++k) {
-            const unsigned t = blockIdx.x + k * gridDim.x;
-            if (t < num_tiles) issue(t, k);
-        }
-    }
-    bool ok = true;
-    unsigned it = 0;
-    for (unsigned tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int st = it % RB_STAGES;
-        rb_mbar_wait(&bar[st], (it / RB_STAGES) & 1);
-        const RB_R* src = rb_stage + (size_t)st * ROWS * RB_BLOCK + tid;
-        RB_R a[N], b[N], c[N], sn[N], cs[N], x[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            a[i] = src[i * RB_BLOCK]; b[i] = src[(N + i) * RB_BLOCK]; c[i] = src[(2 * N + i) * RB_BLOCK];
-        }
-        __syncthreads();                                     // every thread has drained this stage
-        if (tid == 0) {
-            const unsigned nxt = tile + RB_STAGES * gridDim.x;
-            if (nxt < num_tiles) issue(nxt, st);
-        }
-        rb_sincos_all<N>(a, sn, cs);
-        if constexpr (IS_FD) {
-            if (!rb_forward_dynamics<M>(p, sn, cs, b, c, x)) {
-                ok = false;
-#pragma unroll
-                for (int i = 0; i < N; ++i) x[i] = rb_nan<RB_R>();
-            }
-        } else {
-            rb_rnea<M, true>(p, sn, cs, b, c, x);
-        }
-        rb_store<N>(out, ld, (size_t)tile * RB_BLOCK + tid, x);
-    }
-    if constexpr (IS_FD) { if (!ok) atomicOr(status, RB_STATUS_NOT_SPD); }
-}
+#if RB_STREAM || RB_PREFETCH
+#include "experiments/rb_experiments.cuh"   // measured dead ends, not part of the default build
+#endif
 
 // H out: reference convention, n*n entries per state, entry k = r + n*c, upper filled, strict lower 0.
 template <class M>
@@ -477,6 +379,143 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const RB_R* __res
     if (!ok) atomicOr(status, RB_STATUS_NOT_SPD);
 }
 
+// ------------------------------------------------------------------ warp-specialised rollout
+// One trajectory's forward-dynamics step is a ~1900-instruction dependent chain; a thread per trajectory needs 255
+// registers (8 warps per SM) and, when the trajectories are split over several GPUs, leaves a lone warp per scheduler
+// that no amount of SM coverage speeds up (profiles/r1_kbench_rollout.jsonl: 8 192 and 16 384 trajectories both take
+// 0.16 ms).  Here TWO warps serve 32 trajectories, lane = trajectory in both:
+//   warp A ("bias"):   sin/cos of q, the bias recursion rnea(q, dq, 0), then -- once L arrives -- the two triangular
+//                      solves, the semi-implicit Euler update, the trajectory stores and the running cost;
+//   warp B ("matrix"): crba(q) from A's sin/cos and the LDL^T factorisation, which need neither dq nor tau.
+// The hand-over goes through shared memory ([value][lane]: conflict-free) with two named barriers per step.  The
+// dependent chain per step drops from ~1 130 to ~670 FP64 instructions, each role fits 128 registers (16 warps per SM,
+// blocks of 64 threads balance 2 048 groups over 148 SMs to 1 %), and the operations are those of rb_rollout_kernel in
+// the same order: results are bit-identical (tests/test_gpu_parity.py::test_rollout_kernels_agree_bitwise).
+#ifndef RB_RO2_MINB
+#define RB_RO2_MINB 8       // 64-thread blocks per SM -> 128 registers
+#endif
+#ifndef RB_RO2_PREFETCH
+#define RB_RO2_PREFETCH 1   // 1 = load the next step's torques one step ahead (7 more live registers)
+#endif
+#define RB_RO2_MAX_N 12     // static shared memory: (2n + n(n+1)/2) x 32 doubles per block
+RB_DI void rb_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <class M>
+__global__ void __launch_bounds__(64, M::kSpecialised && M::N <= 8 ? RB_RO2_MINB : 4)
+rb_rollout_ws_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q0, const RB_R* __restrict__ dq0,
+                     const RB_R* __restrict__ tau, RB_R dt, int horizon, RB_R* __restrict__ q_traj,
+                     RB_R* __restrict__ dq_traj, RB_R* __restrict__ q_fin, RB_R* __restrict__ dq_fin,
+                     size_t B, size_t ld, int* __restrict__ status, const RB_R* __restrict__ cost_w, RB_R* __restrict__ cost) {
+    constexpr int N = M::N, NL = N * (N - 1) / 2;
+    __shared__ RB_R sh_sc[2 * N][32];        // sin (rows 0..N-1) and cos (N..2N-1) of this step's q
+    __shared__ RB_R sh_ld[NL + N][32];       // L (strict upper of the factorised H, row-major) then 1/d
+    __shared__ int sh_ok[32];
+    const int lane = threadIdx.x & 31;
+    const size_t s = (size_t)blockIdx.x * 32 + lane;
+    const bool live = s < B;                 // padding lanes run the arithmetic on zeros and store nothing
+    const size_t step = (size_t)N * ld;
+    if ((threadIdx.x >> 5) == 0) {
+        // ---------------------------------------------------------------- warp A
+        RB_R q[N], dq[N], u[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { q[i] = RB_R(0); dq[i] = RB_R(0); u[i] = RB_R(0); }
+        if (live) { rb_load<N>(q0, ld, s, q); rb_load<N>(dq0, ld, s, dq); rb_load<N>(tau, ld, s, u); }
+        RB_R J = RB_R(0);
+        for (int t = 0; t < horizon; ++t) {
+            RB_R sn[N], cs[N], x[N];
+#if RB_RO2_PREFETCH
+            RB_R un[N];
+            if (live && t + 1 < horizon) rb_load<N>(tau + (size_t)(t + 1) * step, ld, s, un);
+#else
+            if (live && t > 0) rb_load<N>(tau + (size_t)t * step, ld, s, u);     // consumed after the bias recursion
+#endif
+            rb_sincos_all<N>(q, sn, cs);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { sh_sc[i][lane] = sn[i]; sh_sc[N + i][lane] = cs[i]; }
+            rb_bar_sync(1, 64);                                   // sin/cos published
+            {
+                RB_R bias[N];
+                rb_rnea<M, false>(p, sn, cs, dq, dq /*unused*/, bias);
+#pragma unroll
+                for (int i = 0; i < N; ++i) x[i] = u[i] - bias[i];
+            }
+            rb_bar_sync(2, 64);                                   // L and 1/d published by warp B
+            {
+                RB_R dinv[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) dinv[i] = sh_ld[NL + i][lane];
+                rb_ldlt_apply_fn<N>([&](auto jc, auto ic) {
+                    constexpr int Jr = decltype(jc)::value, Ic = decltype(ic)::value;       // row Jr < column Ic
+                    return sh_ld[Jr * N - Jr * (Jr + 1) / 2 + (Ic - Jr - 1)][lane];
+                }, dinv, x);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                dq[i] = fma(dt, x[i], dq[i]);
+                q[i] = fma(dt, dq[i], q[i]);
+            }
+            if (live) {
+                if (q_traj) rb_store<N>(q_traj + (size_t)t * step, ld, s, q);
+                if (dq_traj) rb_store<N>(dq_traj + (size_t)t * step, ld, s, dq);
+            }
+            if (cost) {
+                RB_R c = RB_R(0);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const RB_R e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
+                    c = fma(__ldg(cost_w + RB_CW_Q * RB_MAX_N + i) * e, e, c);
+                    c = fma(__ldg(cost_w + RB_CW_DQ * RB_MAX_N + i) * dq[i], dq[i], c);
+                    c = fma(__ldg(cost_w + RB_CW_TAU * RB_MAX_N + i) * u[i], u[i], c);
+                }
+                J = fma(dt, c, J);
+            }
+#if RB_RO2_PREFETCH
+            if (t + 1 < horizon) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) u[i] = un[i];
+            }
+#endif
+        }
+        rb_bar_sync(1, 64);                                       // warp B's verdict on positive definiteness
+        if (live) {
+            if (cost) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const RB_R e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
+                    J = fma(__ldg(cost_w + RB_CW_QF * RB_MAX_N + i) * e, e, J);
+                    J = fma(__ldg(cost_w + RB_CW_DQF * RB_MAX_N + i) * dq[i], dq[i], J);
+                }
+                __stcs(cost + s, sh_ok[lane] ? J : rb_nan<RB_R>());
+            }
+            if (q_fin) rb_store<N>(q_fin, ld, s, q);
+            if (dq_fin) rb_store<N>(dq_fin, ld, s, dq);
+        }
+    } else {
+        // ---------------------------------------------------------------- warp B
+        bool ok = true;
+        for (int t = 0; t < horizon; ++t) {
+            RB_R sn[N], cs[N], H[N][N], dinv[N];
+            rb_bar_sync(1, 64);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { sn[i] = sh_sc[i][lane]; cs[i] = sh_sc[N + i][lane]; }
+            rb_crba<M>(p, sn, cs, H);
+            ok = rb_ldlt_factor<N>(H, dinv) && ok;
+            rb_for_up<0, N>([&](auto jc) {
+                constexpr int Jr = decltype(jc)::value;
+                rb_for_up<Jr + 1, N>([&](auto ic) {
+                    constexpr int Ic = decltype(ic)::value;
+                    sh_ld[Jr * N - Jr * (Jr + 1) / 2 + (Ic - Jr - 1)][lane] = H[Jr][Ic];
+                });
+                sh_ld[NL + Jr][lane] = dinv[Jr];
+            });
+            rb_bar_sync(2, 64);
+        }
+        sh_ok[lane] = ok ? 1 : 0;
+        rb_bar_sync(1, 64);
+        if (!ok && live) atomicOr(status, RB_STATUS_NOT_SPD);
+    }
+}
+
 #ifndef RB_DEVICE_ONLY
 // ------------------------------------------------------------------ launchers for policy M
 template <class M>
@@ -495,47 +534,13 @@ struct RbLaunch {
         }
         return v;
     }
-    // Full tiles go through the persistent TMA-fed kernel when rows are 16-byte aligned; the ragged tail
-    // (and unaligned or tiny batches) through the one-tile-per-block kernel.
-    template <int MINB, bool IS_FD>
-    static cudaError_t stream3(const P& p, const double* a, const double* b, const double* c, double* out,
-                               size_t B, size_t ld, int* status, cudaStream_t st, size_t* done) {
-        *done = 0;
-#if RB_STREAM
-        const bool aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15u) == 0 && (ld & 1u) == 0;
-        const size_t tiles = B / RB_BLOCK;
-        const unsigned cap = (unsigned)sm_count() * MINB;
-        if (!aligned || tiles < 2 * (size_t)cap || tiles > 0xFFFFFFF0u) return cudaSuccess;
-        auto k = rb_stream_kernel<M, MINB, IS_FD>;
-        constexpr size_t smem = (size_t)RB_STAGES * 3 * M::N * RB_BLOCK * sizeof(double);
-        static std::atomic<bool> configured{false};
-        if (!configured.load(std::memory_order_acquire)) {
-            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-            configured.store(true, std::memory_order_release);
-        }
-        k<<<cap, RB_BLOCK, smem, st>>>(p, a, b, c, out, (unsigned)tiles, ld, status);
-        *done = tiles * RB_BLOCK;
-        return cudaGetLastError();
-#else
-        return cudaSuccess;
-#endif
-    }
     static cudaError_t rnea(const void* param, const double* q, const double* dq, const double* ddq, double* tau,
                             size_t B, size_t ld, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
         size_t done = 0;
-#if RB_PREFETCH
-        if constexpr (std::is_same<typename M::Real, double>::value) {
-            const size_t cap = (size_t)sm_count() * RB_PF_MINB_RNEA, want = (B + RB_BLOCK - 1) / RB_BLOCK;
-            rb_rnea_pf_kernel<M><<<(unsigned)(want < cap ? want : cap), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, ddq, tau, B, ld);
-            return cudaGetLastError();
-        }
+#if RB_STREAM || RB_PREFETCH
+        { cudaError_t e = RbExperimentLaunch<M>::rnea(*(const P*)param, q, dq, ddq, tau, B, ld, st, sm_count(), &done); if (e != cudaSuccess || done == B) return e; }
 #endif
-        cudaError_t e = stream3<RB_MINB_RNEA, false>(*(const P*)param, q, dq, ddq, tau, B, ld, nullptr, st, &done);
-        if (e != cudaSuccess || done == B) return e;
         rb_rnea_kernel<M><<<grid(B - done), RB_BLOCK, 0, st>>>(*(const P*)param, q + done, dq + done, ddq + done, tau + done, B - done, ld);
         return cudaGetLastError();
     }
@@ -543,16 +548,16 @@ struct RbLaunch {
                           size_t B, size_t ld, int* status, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
         size_t done = 0;
-#if RB_PREFETCH
-        if constexpr (std::is_same<typename M::Real, double>::value) {
-            const size_t cap = (size_t)sm_count() * RB_PF_MINB_FD, want = (B + RB_BLOCK - 1) / RB_BLOCK;
-            rb_fd_pf_kernel<M><<<(unsigned)(want < cap ? want : cap), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, tau, qdd, B, ld, status);
-            return cudaGetLastError();
-        }
+#if RB_STREAM || RB_PREFETCH
+        { cudaError_t e = RbExperimentLaunch<M>::fd(*(const P*)param, q, dq, tau, qdd, B, ld, status, st, sm_count(), &done); if (e != cudaSuccess || done == B) return e; }
 #endif
-        cudaError_t e = stream3<RB_MINB_FD, true>(*(const P*)param, q, dq, tau, qdd, B, ld, status, st, &done);
-        if (e != cudaSuccess || done == B) return e;
         rb_fd_kernel<M><<<grid(B - done), RB_BLOCK, 0, st>>>(*(const P*)param, q + done, dq + done, tau + done, qdd + done, B - done, ld, status);
+        return cudaGetLastError();
+    }
+    static cudaError_t rnea_fd(const void* param, const double* q, const double* dq, const double* ddq, const double* tau_in,
+                               double* out, size_t B, size_t ld, int* status, cudaStream_t st) {
+        if (B == 0) return cudaSuccess;
+        rb_rnea_fd_kernel<M><<<grid(B), RB_BLOCK, 0, st>>>(*(const P*)param, q, dq, ddq, tau_in, out, B, ld, status);
         return cudaGetLastError();
     }
     static constexpr size_t aos_smem = (size_t)3 * RB_BLOCK * M::N * sizeof(double);
@@ -587,6 +592,13 @@ struct RbLaunch {
                                int horizon, double* q_traj, double* dq_traj, double* q_fin, double* dq_fin,
                                size_t B, size_t ld, int* status, const double* cost_w, double* cost, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
+        if constexpr (M::N <= RB_RO2_MAX_N) {
+            if (rb_rollout_mode() != 1) {      // two warps per 32 trajectories (default)
+                rb_rollout_ws_kernel<M><<<(unsigned)((B + 31) / 32), 64, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
+                                                                                  q_fin, dq_fin, B, ld, status, cost_w, cost);
+                return cudaGetLastError();
+            }
+        }
         rb_rollout_kernel<M><<<(unsigned)((B + RB_RO_BLOCK - 1) / RB_RO_BLOCK), RB_RO_BLOCK, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
                                                           q_fin, dq_fin, B, ld, status, cost_w, cost);
         return cudaGetLastError();
@@ -608,11 +620,11 @@ struct RbLaunch {
     }
     template <class M32 = void>
     static RbOps ops(const char* name) {
-        RbOps o;
+        RbOps o{};
         o.name = name; o.n = M::N; o.param_bytes = sizeof(P); o.shared_scratch = false;
         o.rnea = &rnea; o.fd = &fd; o.rnea_aos = &rnea_aos; o.fd_aos = &fd_aos;
         o.crba = &crba; o.fwd_kin = &fwd_kin; o.jac = &jac; o.rollout = &rollout;
-        o.rnea_f32 = nullptr; o.fd_f32 = nullptr;
+        o.rnea_f32 = nullptr; o.fd_f32 = nullptr; o.rnea_fd = &rnea_fd;
         if constexpr (!std::is_void<M32>::value) { o.rnea_f32 = &rnea_f32<M32>; o.fd_f32 = &fd_f32<M32>; }
         return o;
     }

@@ -7,6 +7,13 @@
 #include "rb_kernels.cuh"
 #include "rb_dyn_n.cuh"
 #include "rb_util.cuh"
+#include <cstdlib>
+#include <cstring>
+
+int rb_rollout_mode() {
+    const char* e = getenv("RIGIDBODY_B200_ROLLOUT");      // read per launch (tests flip it inside one process)
+    return e && strcmp(e, "thread") == 0 ? 1 : 0;
+}
 
 __global__ void __launch_bounds__(RB_BLOCK)
 rbn_rnea_kernel(RbNParam P, const double* __restrict__ q, const double* __restrict__ dq, const double* __restrict__ ddq,

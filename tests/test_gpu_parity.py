@@ -123,24 +123,53 @@ def test_rnea_fd_host_batches(mb_fr3, oracle_fr3, B, layout):
 
 @pytest.mark.parametrize("layout", ["soa", "aos"])
 def test_rnea_fd_one_call_equals_two_calls(rb, mb_fr3, oracle_fr3, layout):
-    """multibody_rnea_fd_batch: same kernels, q and dq staged once; host and device, both layouts, chunked sizes."""
+    """multibody_rnea_fd_batch: q and dq staged once; host and device, both layouts, chunked sizes.  The fused kernel
+    (rb_rnea_fd_fused) shares sin/cos, the bias recursion and the mass matrix: qdd is bit-identical to the separate
+    forward-dynamics call, tau = bias + sym(H) ddq differs from the recursion by rounding only (held to 1e-12 here,
+    1e-10 against the oracle).  With RIGIDBODY_B200_FUSED=0 the call issues the two launches: everything bit-identical."""
     import torch
     B = 3000
     q, dq, ddq, tau = _states(oracle_fr3, B)
+    want_t, want_a = oracle_fr3.rnea_batch(q, dq, ddq), oracle_fr3.forward_dynamics_batch(q, dq, tau)
+    ax = 0
     if layout == "aos":
-        q, dq, ddq, tau = (np.ascontiguousarray(x.T) for x in (q, dq, ddq, tau))
-    both = mb_fr3.rnea_fd(q, dq, ddq, tau, layout=layout)
+        q, dq, ddq, tau, want_t, want_a = (np.ascontiguousarray(x.T) for x in (q, dq, ddq, tau, want_t, want_a))
+        ax = 1
+    n = 7
+    split = lambda x: (x[:n], x[n:]) if layout == "soa" else (x[:, :n], x[:, n:])
     t, a = mb_fr3.rnea(q, dq, ddq, layout=layout), mb_fr3.forward_dynamics(q, dq, tau, layout=layout)
-    want = np.concatenate([t, a], axis=0 if layout == "soa" else 1)
-    assert both.shape == want.shape and np.array_equal(both, want)
+    both = mb_fr3.rnea_fd(q, dq, ddq, tau, layout=layout)
+    bt, ba = split(both)
+    assert np.array_equal(ba, a)
+    assert state_err(bt, t, ax).max() < 1e-12
+    assert state_err(bt, want_t, ax).max() < TOL and state_err(ba, want_a, ax).max() < TOL
     dev = torch.device("cuda:0")
     tq, tdq, tddq, ttau = (torch.from_numpy(x).to(dev) for x in (q, dq, ddq, tau))
     got = mb_fr3.rnea_fd(tq, tdq, tddq, ttau, layout=layout)
     mb_fr3.sync()
-    assert np.array_equal(got.cpu().numpy(), want)
-    t1, a1 = mb_fr3.rnea_fd(q[0] if layout == "aos" else q[:, 0], dq[0] if layout == "aos" else dq[:, 0],
-                            ddq[0] if layout == "aos" else ddq[:, 0], tau[0] if layout == "aos" else tau[:, 0])
-    assert np.array_equal(t1, t[0] if layout == "aos" else t[:, 0]) and np.array_equal(a1, a[0] if layout == "aos" else a[:, 0])
+    assert np.array_equal(got.cpu().numpy(), both)
+    sl = (lambda x: x[0]) if layout == "aos" else (lambda x: x[:, 0])
+    t1, a1 = mb_fr3.rnea_fd(sl(q), sl(dq), sl(ddq), sl(tau))
+    assert np.array_equal(t1, sl(bt)) and np.array_equal(a1, sl(ba))
+    os.environ["RIGIDBODY_B200_FUSED"] = "0"
+    try:
+        two = rb.Multibody.from_urdf(FR3)
+    finally:
+        os.environ.pop("RIGIDBODY_B200_FUSED", None)
+    assert np.array_equal(two.rnea_fd(q, dq, ddq, tau, layout=layout), np.concatenate([t, a], axis=ax))
+
+
+def test_fused_rnea_fd_all_families(rb, oracle_fr3):
+    """The fused inverse + forward dynamics pass in every family that has it (ahead-of-time, run-time compiled,
+    run-time constants), ragged size; families without it (generic-n) issue the two launches."""
+    B = 1000
+    q, dq, ddq, tau = _states(oracle_fr3, B, seed=0x5EED0007)
+    want_t, want_a = oracle_fr3.rnea_batch(q, dq, ddq), oracle_fr3.forward_dynamics_batch(q, dq, tau)
+    for mb in _variants(rb, FR3):
+        both = mb.rnea_fd(q, dq, ddq, tau)
+        assert state_err(both[:7], want_t, 0).max() < TOL, mb.kernel_variant
+        assert state_err(both[7:], want_a, 0).max() < TOL, mb.kernel_variant
+        assert np.array_equal(both[7:], mb.forward_dynamics(q, dq, tau)), mb.kernel_variant
 
 
 def test_empty_batch_and_bad_shapes(mb_fr3):
@@ -282,6 +311,32 @@ def test_rollout_matches_oracle(rb, oracle_fr3):
         qa, dqa = mb.rollout(np.ascontiguousarray(q.T), np.ascontiguousarray(dq.T),
                              np.ascontiguousarray(tau.transpose(0, 2, 1)), dt, layout="aos")
         np.testing.assert_array_equal(qa.transpose(0, 2, 1), qt)
+
+
+@pytest.mark.parametrize("B", [1, 33, 100, 4096])
+def test_rollout_kernels_agree_bitwise(rb, oracle_fr3, B):
+    """rb_rollout_ws_kernel (two warps per 32 trajectories, default) performs the operations of rb_rollout_kernel (one
+    thread per trajectory, RIGIDBODY_B200_ROLLOUT=thread) in the same order: trajectories and costs are bit-identical,
+    ragged tails included."""
+    H, dt = 24, 1e-3
+    q, dq, _, _ = _states(oracle_fr3, B, seed=0x5EED0003)
+    lim = oracle_fr3.model
+    tau = np.stack([oracle_fr3.fill(0x5EED0003, 4 + t % 32, -lim.effort, lim.effort, t * B, B) for t in range(H)])
+    w = np.linspace(0.5, 2.0, 7)
+    for mb in _variants(rb, FR3):
+        if mb.kernel_variant == "generic-n":
+            continue
+        a = mb.rollout(q, dq, tau, dt, final=True)
+        ca = mb.rollout_cost(q, dq, tau, dt, w_q=w, w_dq=0.1 * w, w_tau=1e-3 * w, w_q_final=3 * w)
+        os.environ["RIGIDBODY_B200_ROLLOUT"] = "thread"
+        try:
+            b = mb.rollout(q, dq, tau, dt, final=True)
+            cb = mb.rollout_cost(q, dq, tau, dt, w_q=w, w_dq=0.1 * w, w_tau=1e-3 * w, w_q_final=3 * w)
+        finally:
+            os.environ.pop("RIGIDBODY_B200_ROLLOUT", None)
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y, err_msg=mb.kernel_variant)
+        np.testing.assert_array_equal(ca, cb, err_msg=mb.kernel_variant)
 
 
 def test_rollout_chain32(rb, mb_chain32, oracle_chain32):
@@ -674,6 +729,23 @@ def test_not_spd_is_reported(rb):
     z = np.zeros((2, 4))
     with pytest.raises(rb.NotPositiveDefinite):
         mb.forward_dynamics(z, z, z)
+    # the same through the fused inverse + forward dynamics pass and both rollout kernels (the two-warp kernel learns it
+    # from the matrix warp through shared memory)
+    with pytest.raises(rb.NotPositiveDefinite):
+        mb.rnea_fd(z, z, z, z)
+    tau = np.zeros((3, 2, 4))
+    for mode in (None, "thread"):
+        if mode:
+            os.environ["RIGIDBODY_B200_ROLLOUT"] = mode
+        try:
+            with pytest.raises(rb.NotPositiveDefinite):
+                mb.rollout(z, z, tau, 1e-3)
+            with pytest.raises(rb.NotPositiveDefinite):
+                mb.rollout_cost(z, z, tau, 1e-3, w_q=np.ones(2))
+            # a later, healthy call on the same engine is not blamed for it
+            assert mb.rnea(z, z, z).shape == (2, 4)
+        finally:
+            os.environ.pop("RIGIDBODY_B200_ROLLOUT", None)
 
 
 def test_nan_and_huge_angles_do_not_poison_neighbours(mb_fr3, oracle_fr3):

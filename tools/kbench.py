@@ -14,6 +14,7 @@ ap.add_argument("--urdf", default="assets/fr3.urdf")
 ap.add_argument("--ops", default="rnea,fd")
 ap.add_argument("--layout", default="soa", choices=["soa", "aos"])
 ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+ap.add_argument("--traj", type=int, default=65536, help="trajectories of the rollout op")
 a = ap.parse_args()
 mb = rb.Multibody.from_urdf(a.urdf)
 n, B = mb.n, a.states
@@ -27,13 +28,18 @@ H = 64
 for op in a.ops.split(","):
     units = B
     if op == "rollout":
-        Bt = min(B, 65536)
+        Bt = min(B, a.traj)
         tau = torch.empty((H, n, Bt), dtype=torch.float64, device=dev)
         for t in range(H):
             mb.fill(tau[t], 3, 4 + t % 32, -lim["effort"], lim["effort"], first_index=t * Bt)
         q0, dq0 = q[:, :Bt].contiguous(), dq[:, :Bt].contiguous()
         fn = lambda: mb.rollout(q0, dq0, tau, 1e-3)
         units = Bt * H
+    elif op == "rnea_fd":
+        tin = torch.empty_like(q); mb.fill(tin, 2, 3, -lim["effort"], lim["effort"])
+        out2 = torch.empty((2 * n, B), dtype=torch.float64, device=dev)
+        fn = lambda: mb.rnea_fd(q, dq, x3, tin, out=out2)
+        units = 2 * B
     elif op == "crba":
         Bc = min(B, 1 << 22)
         qc = q[:, :Bc].contiguous(); Hout = torch.empty((n * n, Bc), dtype=torch.float64, device=dev)
