@@ -31,9 +31,14 @@ STATES_PER_GPU = 1 << 24
 # algorithmic work per evaluation (SURVEY.md 8d / BASELINE.md section 2), N = 7
 RNEA_FLOPS, FD_FLOPS, BYTES_PER_EVAL = 2026.0, 4180.0, 224.0
 SEED_RNEA, SEED_FD = 0x5EED0001, 0x5EED0002
-# FP64-pipe SASS instructions one thread (= one state) executes in the fr3-specialised kernels: static count of
-# the straight-line kernels (tools/sass_count.sh; tests/test_host.py checks these against the built library).
-FP64_INSTR = {"rb_rnea_kernel": 635, "rb_fd_kernel": 1130}
+# FP64-pipe SASS instructions of the fr3-specialised kernels (tools/sass_count.sh; tests/test_host.py checks the static
+# totals against the built library).  The kernels are straight-line except for the out-of-range fallback of the batched
+# sin/cos (rb_sincos_batched: six per-joint CUDA sincos() calls, 21 FP64 instructions each, taken only when some
+# |q_i| >= 1e5): executed per state = static - fallback.  ncu's smsp__sass_thread_inst_executed_op_d{fma,add,mul}
+# counters in profiles/ agree.
+FP64_STATIC = {"rb_rnea_kernel": 804, "rb_fd_kernel": 1299}
+FP64_FALLBACK = {"rb_rnea_kernel": 126, "rb_fd_kernel": 126}
+FP64_INSTR = {k: FP64_STATIC[k] - FP64_FALLBACK[k] for k in FP64_STATIC}
 FP64_LANES_PER_SM = 64
 
 

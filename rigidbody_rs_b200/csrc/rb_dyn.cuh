@@ -10,6 +10,10 @@
 #include "rb_model.h"
 
 #define RB_DI __device__ __forceinline__
+#ifndef RB_BATCHED_SINCOS
+#define RB_BATCHED_SINCOS 2      // branch-free, interleavable sin/cos of all joints of a state (rb_sincos_batched): 0 = off, 2 = every kernel
+                                 // (RNEA +2.7 %, FD +4 %, rollout +6..14 % against per-joint sincos(): profiles/r2_kbench_rollout.jsonl)
+#endif
 // Scalar type of the model policy in scope (every function below is templated on a policy M or on a scalar T).
 #define RB_R typename M::Real
 
@@ -174,12 +178,63 @@ RB_DI void rb_inertia_mul(const typename M::Param& p, const RB_R (&al)[3], const
 // sin/cos of every joint angle (joint.rs:48-50 builds the same rotation as a quaternion).
 RB_DI void rb_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 RB_DI void rb_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+// One angle, |x| < RB_SINCOS_FAST_LIMIT, no branches: three-term Cody-Waite reduction by pi/2 with FMAs (the quotient
+// has at most 17 bits, every product is exact inside its FMA), then the fdlibm kernels on [-pi/4, pi/4] (S1..S6,
+// C1..C6; < 1 ulp) and the quadrant fix-up with selects.  Same cost as the fast path of CUDA's sincos() (23 FP64
+// instructions) but straight-line, so that rb_sincos_all can interleave the joints of a state: CUDA's version carries a
+// slow-path branch per call, which serialises them -- 7 dependent ~13-deep FMA chains per state, 38 % of a rollout step
+// when a lone warp runs it (profiles/r2_rollout_ws_stalls.txt).  tools/check_sincos.c pins the accuracy on the host.
+#define RB_SINCOS_FAST_LIMIT 1.0e5
+RB_DI void rb_sincos_fast(double x, double* sn, double* cs) {
+    const int k = __double2int_rn(x * 0.6366197723675814);
+    const double kd = (double)k;
+    double r = fma(-kd, 1.5707963267948966, x);
+    r = fma(-kd, 6.123233995736766e-17, r);
+    r = fma(-kd, -1.4973849048591698e-33, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s0 = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double hz = 0.5 * z, w = 1.0 - hz;
+    const double c0 = w + ((1.0 - w) - hz + z * (z * pc));
+    const double a = (k & 1) ? c0 : s0, b = (k & 1) ? s0 : c0;
+    *sn = (k & 2) ? -a : a;
+    *cs = ((k + 1) & 2) ? -b : b;
+}
+// sin/cos of all joints of a state: the branch-free path whenever every angle is in range (one test per state), the
+// per-joint library call otherwise (huge angles, NaN, Inf).
 template <int N, class T>
-RB_DI void rb_sincos_all(const T (&q)[N], T (&s)[N], T (&c)[N]) {
+RB_DI void rb_sincos_batched(const T (&q)[N], T (&s)[N], T (&c)[N]) {
+    if constexpr (sizeof(T) == 8) {
+        bool big = false;                         // also true for NaN / Inf
+#pragma unroll
+        for (int i = 0; i < N; ++i) big = big || !(fabs(q[i]) < RB_SINCOS_FAST_LIMIT);
+        if (!big) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) rb_sincos_fast(q[i], &s[i], &c[i]);
+            return;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) rb_sincos(q[i], &s[i], &c[i]);
 }
-
+template <int N, class T>
+RB_DI void rb_sincos_all(const T (&q)[N], T (&s)[N], T (&c)[N]) {
+#if RB_BATCHED_SINCOS >= 2
+    rb_sincos_batched<N>(q, s, c);
+#else
+#pragma unroll
+    for (int i = 0; i < N; ++i) rb_sincos(q[i], &s[i], &c[i]);
+#endif
+}
 // ------------------------------------------------------------------ RNEA  (multibody.rs:111-153)
 // tau = ID(q, dq, ddq).  HAS_DDQ = false is the bias-force call rnea(q, dq, 0) used by forward dynamics.
 //
@@ -311,10 +366,17 @@ RB_DI void rb_rnea(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R
 // the 10-parameter update below is the same map: with R = R_p Rz(q), u = R h + (m/2) t,
 //   h' = R h + m t,   I_o' = R I_o R^T - (t u^T + u t^T) + 2 (t.u) Id,   then add link i-1's own (h, I_o).
 // `put(RbIC<J>, RbIC<I>, value)` receives every entry H(J, I), J <= I, once.
-template <class M, class Put>
-RB_DI void rb_crba_put(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N], Put&& put) {
+// s, c: anything indexable by joint (arrays of sin/cos, or a view that reads them from shared memory on demand).
+template <class M, class SC, class Put>
+RB_DI void rb_crba_put(const typename M::Param& p, const SC& s, const SC& c, Put&& put) {
     constexpr int N = M::N;
-    if constexpr (M::kTree) { rb_crba_put_tree<M>(p, s, c, put); return; }
+    if constexpr (M::kTree) {
+        RB_R sa[N], ca[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { sa[i] = s[i]; ca[i] = c[i]; }
+        rb_crba_put_tree<M>(p, sa, ca, put);
+        return;
+    }
     RB_R h[3] = {KV(N - 1, RB_F_H, 0), KV(N - 1, RB_F_H, 1), KV(N - 1, RB_F_H, 2)};            // :157
     RB_R Ixx = KV(N - 1, RB_F_I, 0), Ixy = KV(N - 1, RB_F_I, 1), Ixz = KV(N - 1, RB_F_I, 2);
     RB_R Iyy = KV(N - 1, RB_F_I, 3), Iyz = KV(N - 1, RB_F_I, 4), Izz = KV(N - 1, RB_F_I, 5);
@@ -386,9 +448,8 @@ RB_DI void rb_crba_put(const typename M::Param& p, const RB_R (&s)[M::N], const 
     });
 }
 
-template <class M>
-RB_DI void rb_crba(const typename M::Param& p, const RB_R (&s)[M::N], const RB_R (&c)[M::N],
-                   RB_R (&H)[M::N][M::N]) {
+template <class M, class SC>
+RB_DI void rb_crba(const typename M::Param& p, const SC& s, const SC& c, RB_R (&H)[M::N][M::N]) {
     if constexpr (M::kTree) {                        // entries whose row joint does not support the column joint stay 0
 #pragma unroll
         for (int r = 0; r < M::N; ++r)

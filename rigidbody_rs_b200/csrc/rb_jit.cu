@@ -81,13 +81,13 @@ const char* const kKernelExprs[RB_JIT_KERNELS] = {
     "rb_crba_kernel<CtModel<TabJit>>",        "rb_fwd_kin_kernel<CtModel<TabJit>>",
     "rb_jac_kernel<CtModel<TabJit>>",         "rb_rollout_kernel<CtModel<TabJit>>",
     "rb_rnea_kernel<CtModel<TabJit, float>, false>", "rb_fd_kernel<CtModel<TabJit, float>, false>",
-    "rb_rnea_fd_kernel<CtModel<TabJit>>",     "rb_rollout_ws_kernel<CtModel<TabJit>>"};
+    "rb_rnea_fd_kernel<CtModel<TabJit>>"};
 // chains of RB_JIT_MAX_N+1 .. RB_JIT_LONG_MAX_N joints: the long-chain layouts of rb_kernels_long.cuh for rnea / crba
 // (no n x n array in the thread), the plain kernels for fwd_kin / jac, nothing else
 const char* const kLongExprs[RB_JIT_KERNELS] = {
     "rb_long_rnea_kernel<CtModel<TabJit>>", nullptr, nullptr, nullptr,
     "rb_long_crba_kernel<CtModel<TabJit>>", "rb_fwd_kin_kernel<CtModel<TabJit>>",
-    "rb_jac_kernel<CtModel<TabJit>>",       nullptr, nullptr, nullptr, nullptr, nullptr};
+    "rb_jac_kernel<CtModel<TabJit>>",       nullptr, nullptr, nullptr, nullptr};
 const char* const kOptions[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DRB_DEVICE_ONLY=1"};
 
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -150,7 +150,7 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     const bool long_set = m.n > RB_JIT_MAX_N;
     if (long_set && !m.serial) { log = "trees beyond 18 joints run on the run-time-n family"; return RB_ERR_UNSUPPORTED; }
     const char* const* exprs = long_set ? kLongExprs : kKernelExprs;
-    auto wanted = [&](int k) { return exprs[k] != nullptr && !(k == RB_JK_ROLLOUT_WS && m.n > RB_RO2_MAX_N); };   // static shared memory of the two-warp rollout
+    auto wanted = [&](int k) { return exprs[k] != nullptr; };
     std::string err;
     const Nvrtc* nv = load_nvrtc(err);
     if (!nv) { log = err; return RB_ERR_UNSUPPORTED; }
@@ -286,8 +286,6 @@ cudaError_t j_rollout(const void* param, const double* q0, const double* dq0, co
     if (B == 0) return cudaSuccess;
     RbEmptyParam ep{0};
     void* args[] = {&ep, &q0, &dq0, &tau, &dt, &horizon, &q_traj, &dq_traj, &q_fin, &dq_fin, &B, &ld, &status, &cost_w, &cost};
-    if (P->n <= RB_RO2_MAX_N && P->k[RB_JK_ROLLOUT_WS] && rb_rollout_mode() != 1)
-        return cudaLaunchKernel((const void*)P->k[RB_JK_ROLLOUT_WS], dim3(jgrid(B, 32)), dim3(64), args, 0, st);
     return cudaLaunchKernel((const void*)P->k[RB_JK_ROLLOUT], dim3(jgrid(B, RB_RO_BLOCK)), dim3(RB_RO_BLOCK), args, 0, st);
 }
 cudaError_t j_rnea_f32(const void* param, const float* q, const float* dq, const float* ddq, float* tau, size_t B, size_t ld, cudaStream_t st) {

@@ -88,8 +88,8 @@ struct RbOps {
                            double* out, size_t B, size_t ld, int* status, cudaStream_t st);
 };
 
-// $RIGIDBODY_B200_ROLLOUT: "thread" = 1 (one thread per trajectory, rb_rollout_kernel), anything else / unset = 0
-// (two warps per 32 trajectories, rb_rollout_ws_kernel).  Read at every launch.
+// $RIGIDBODY_B200_ROLLOUT, read at every launch: "ws" = 2 selects the two-warp kernel of experiments/rb_rollout_ws.cuh
+// in builds made with -DRB_ROLLOUT_WS=1; anything else = 0, the product kernel (rb_rollout_kernel).
 int rb_rollout_mode();
 const RbOps* rb_ops_fr3();        // compile-time FR3 model (rb_kernels_fr3.cu)
 const RbOps* rb_ops_rt7();        // any 7-joint chain, run-time constants (rb_kernels_rt.cu)
@@ -313,11 +313,15 @@ rb_jac_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restric
 #endif
 // Rows of the cost-weight block a rollout may carry: cost_w[row * RB_MAX_N + joint] (see RbQuadCost in rigidbody.h).
 enum : int { RB_CW_QREF = 0, RB_CW_Q, RB_CW_DQ, RB_CW_TAU, RB_CW_QF, RB_CW_DQF, RB_CW_ROWS };
+#ifndef RB_ROLLOUT_WS
+#define RB_ROLLOUT_WS 0
+#endif
 #ifndef RB_RO_BLOCK
-#define RB_RO_BLOCK 128     // threads per rollout block (smaller blocks balance the single wave across 148 SMs)
+#define RB_RO_BLOCK 32      // threads per rollout block: one warp (warps of small blocks are spread over the four SM
+                            // sub-partitions like those of large ones, profiles/r2_ubench_smsp_mapping.txt)
 #endif
 #ifndef RB_RO_MINB
-#define RB_RO_MINB (RB_MINB_ROLLOUT * (RB_BLOCK / RB_RO_BLOCK))
+#define RB_RO_MINB (RB_MINB_ROLLOUT * (128 / RB_RO_BLOCK))
 #endif
 template <class M>
 __global__ void __launch_bounds__(RB_RO_BLOCK, RB_RO_MINB)
@@ -341,7 +345,7 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const RB_R* __res
         // prefetch the next step's torques so the load latency hides behind this step's arithmetic
         if (t + 1 < horizon) rb_load<N>(tau + (size_t)(t + 1) * step, ld, s, un);
         rb_sincos_all<N>(q, sn, cs);
-        ok = rb_forward_dynamics<M>(p, sn, cs, dq, u, qdd) && ok;
+                ok = rb_forward_dynamics<M>(p, sn, cs, dq, u, qdd) && ok;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             dq[i] = fma(dt, qdd[i], dq[i]);
@@ -379,142 +383,9 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const RB_R* __res
     if (!ok) atomicOr(status, RB_STATUS_NOT_SPD);
 }
 
-// ------------------------------------------------------------------ warp-specialised rollout
-// One trajectory's forward-dynamics step is a ~1900-instruction dependent chain; a thread per trajectory needs 255
-// registers (8 warps per SM) and, when the trajectories are split over several GPUs, leaves a lone warp per scheduler
-// that no amount of SM coverage speeds up (profiles/r1_kbench_rollout.jsonl: 8 192 and 16 384 trajectories both take
-// 0.16 ms).  Here TWO warps serve 32 trajectories, lane = trajectory in both:
-//   warp A ("bias"):   sin/cos of q, the bias recursion rnea(q, dq, 0), then -- once L arrives -- the two triangular
-//                      solves, the semi-implicit Euler update, the trajectory stores and the running cost;
-//   warp B ("matrix"): crba(q) from A's sin/cos and the LDL^T factorisation, which need neither dq nor tau.
-// The hand-over goes through shared memory ([value][lane]: conflict-free) with two named barriers per step.  The
-// dependent chain per step drops from ~1 130 to ~670 FP64 instructions, each role fits 128 registers (16 warps per SM,
-// blocks of 64 threads balance 2 048 groups over 148 SMs to 1 %), and the operations are those of rb_rollout_kernel in
-// the same order: results are bit-identical (tests/test_gpu_parity.py::test_rollout_kernels_agree_bitwise).
-#ifndef RB_RO2_MINB
-#define RB_RO2_MINB 8       // 64-thread blocks per SM -> 128 registers
+#if RB_ROLLOUT_WS
+#include "experiments/rb_rollout_ws.cuh"      // two warps per 32 trajectories: measured slower, not part of the default build
 #endif
-#ifndef RB_RO2_PREFETCH
-#define RB_RO2_PREFETCH 1   // 1 = load the next step's torques one step ahead (7 more live registers)
-#endif
-#define RB_RO2_MAX_N 12     // static shared memory: (2n + n(n+1)/2) x 32 doubles per block
-RB_DI void rb_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-template <class M>
-__global__ void __launch_bounds__(64, M::kSpecialised && M::N <= 8 ? RB_RO2_MINB : 4)
-rb_rollout_ws_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict__ q0, const RB_R* __restrict__ dq0,
-                     const RB_R* __restrict__ tau, RB_R dt, int horizon, RB_R* __restrict__ q_traj,
-                     RB_R* __restrict__ dq_traj, RB_R* __restrict__ q_fin, RB_R* __restrict__ dq_fin,
-                     size_t B, size_t ld, int* __restrict__ status, const RB_R* __restrict__ cost_w, RB_R* __restrict__ cost) {
-    constexpr int N = M::N, NL = N * (N - 1) / 2;
-    __shared__ RB_R sh_sc[2 * N][32];        // sin (rows 0..N-1) and cos (N..2N-1) of this step's q
-    __shared__ RB_R sh_ld[NL + N][32];       // L (strict upper of the factorised H, row-major) then 1/d
-    __shared__ int sh_ok[32];
-    const int lane = threadIdx.x & 31;
-    const size_t s = (size_t)blockIdx.x * 32 + lane;
-    const bool live = s < B;                 // padding lanes run the arithmetic on zeros and store nothing
-    const size_t step = (size_t)N * ld;
-    if ((threadIdx.x >> 5) == 0) {
-        // ---------------------------------------------------------------- warp A
-        RB_R q[N], dq[N], u[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) { q[i] = RB_R(0); dq[i] = RB_R(0); u[i] = RB_R(0); }
-        if (live) { rb_load<N>(q0, ld, s, q); rb_load<N>(dq0, ld, s, dq); rb_load<N>(tau, ld, s, u); }
-        RB_R J = RB_R(0);
-        for (int t = 0; t < horizon; ++t) {
-            RB_R sn[N], cs[N], x[N];
-#if RB_RO2_PREFETCH
-            RB_R un[N];
-            if (live && t + 1 < horizon) rb_load<N>(tau + (size_t)(t + 1) * step, ld, s, un);
-#else
-            if (live && t > 0) rb_load<N>(tau + (size_t)t * step, ld, s, u);     // consumed after the bias recursion
-#endif
-            rb_sincos_all<N>(q, sn, cs);
-#pragma unroll
-            for (int i = 0; i < N; ++i) { sh_sc[i][lane] = sn[i]; sh_sc[N + i][lane] = cs[i]; }
-            rb_bar_sync(1, 64);                                   // sin/cos published
-            {
-                RB_R bias[N];
-                rb_rnea<M, false>(p, sn, cs, dq, dq /*unused*/, bias);
-#pragma unroll
-                for (int i = 0; i < N; ++i) x[i] = u[i] - bias[i];
-            }
-            rb_bar_sync(2, 64);                                   // L and 1/d published by warp B
-            {
-                RB_R dinv[N];
-#pragma unroll
-                for (int i = 0; i < N; ++i) dinv[i] = sh_ld[NL + i][lane];
-                rb_ldlt_apply_fn<N>([&](auto jc, auto ic) {
-                    constexpr int Jr = decltype(jc)::value, Ic = decltype(ic)::value;       // row Jr < column Ic
-                    return sh_ld[Jr * N - Jr * (Jr + 1) / 2 + (Ic - Jr - 1)][lane];
-                }, dinv, x);
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                dq[i] = fma(dt, x[i], dq[i]);
-                q[i] = fma(dt, dq[i], q[i]);
-            }
-            if (live) {
-                if (q_traj) rb_store<N>(q_traj + (size_t)t * step, ld, s, q);
-                if (dq_traj) rb_store<N>(dq_traj + (size_t)t * step, ld, s, dq);
-            }
-            if (cost) {
-                RB_R c = RB_R(0);
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const RB_R e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
-                    c = fma(__ldg(cost_w + RB_CW_Q * RB_MAX_N + i) * e, e, c);
-                    c = fma(__ldg(cost_w + RB_CW_DQ * RB_MAX_N + i) * dq[i], dq[i], c);
-                    c = fma(__ldg(cost_w + RB_CW_TAU * RB_MAX_N + i) * u[i], u[i], c);
-                }
-                J = fma(dt, c, J);
-            }
-#if RB_RO2_PREFETCH
-            if (t + 1 < horizon) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) u[i] = un[i];
-            }
-#endif
-        }
-        rb_bar_sync(1, 64);                                       // warp B's verdict on positive definiteness
-        if (live) {
-            if (cost) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const RB_R e = q[i] - __ldg(cost_w + RB_CW_QREF * RB_MAX_N + i);
-                    J = fma(__ldg(cost_w + RB_CW_QF * RB_MAX_N + i) * e, e, J);
-                    J = fma(__ldg(cost_w + RB_CW_DQF * RB_MAX_N + i) * dq[i], dq[i], J);
-                }
-                __stcs(cost + s, sh_ok[lane] ? J : rb_nan<RB_R>());
-            }
-            if (q_fin) rb_store<N>(q_fin, ld, s, q);
-            if (dq_fin) rb_store<N>(dq_fin, ld, s, dq);
-        }
-    } else {
-        // ---------------------------------------------------------------- warp B
-        bool ok = true;
-        for (int t = 0; t < horizon; ++t) {
-            RB_R sn[N], cs[N], H[N][N], dinv[N];
-            rb_bar_sync(1, 64);
-#pragma unroll
-            for (int i = 0; i < N; ++i) { sn[i] = sh_sc[i][lane]; cs[i] = sh_sc[N + i][lane]; }
-            rb_crba<M>(p, sn, cs, H);
-            ok = rb_ldlt_factor<N>(H, dinv) && ok;
-            rb_for_up<0, N>([&](auto jc) {
-                constexpr int Jr = decltype(jc)::value;
-                rb_for_up<Jr + 1, N>([&](auto ic) {
-                    constexpr int Ic = decltype(ic)::value;
-                    sh_ld[Jr * N - Jr * (Jr + 1) / 2 + (Ic - Jr - 1)][lane] = H[Jr][Ic];
-                });
-                sh_ld[NL + Jr][lane] = dinv[Jr];
-            });
-            rb_bar_sync(2, 64);
-        }
-        sh_ok[lane] = ok ? 1 : 0;
-        rb_bar_sync(1, 64);
-        if (!ok && live) atomicOr(status, RB_STATUS_NOT_SPD);
-    }
-}
 
 #ifndef RB_DEVICE_ONLY
 // ------------------------------------------------------------------ launchers for policy M
@@ -592,15 +463,17 @@ struct RbLaunch {
                                int horizon, double* q_traj, double* dq_traj, double* q_fin, double* dq_fin,
                                size_t B, size_t ld, int* status, const double* cost_w, double* cost, cudaStream_t st) {
         if (B == 0) return cudaSuccess;
+#if RB_ROLLOUT_WS
         if constexpr (M::N <= RB_RO2_MAX_N) {
-            if (rb_rollout_mode() != 1) {      // two warps per 32 trajectories (default)
-                rb_rollout_ws_kernel<M><<<(unsigned)((B + 31) / 32), 64, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
+            if (rb_rollout_mode() == 2) {
+                rb_rollout_ws_kernel<M><<<(unsigned)((B + 63) / 64), 128, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
                                                                                   q_fin, dq_fin, B, ld, status, cost_w, cost);
                 return cudaGetLastError();
             }
         }
-        rb_rollout_kernel<M><<<(unsigned)((B + RB_RO_BLOCK - 1) / RB_RO_BLOCK), RB_RO_BLOCK, 0, st>>>(*(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj,
-                                                          q_fin, dq_fin, B, ld, status, cost_w, cost);
+#endif
+        rb_rollout_kernel<M><<<(unsigned)((B + RB_RO_BLOCK - 1) / RB_RO_BLOCK), RB_RO_BLOCK, 0, st>>>(
+            *(const P*)param, q0, dq0, tau, dt, horizon, q_traj, dq_traj, q_fin, dq_fin, B, ld, status, cost_w, cost);
         return cudaGetLastError();
     }
     // M32 = the same policy with Real = float (fp32 mode)

@@ -12,7 +12,7 @@
 
 int rb_rollout_mode() {
     const char* e = getenv("RIGIDBODY_B200_ROLLOUT");      // read per launch (tests flip it inside one process)
-    return e && strcmp(e, "thread") == 0 ? 1 : 0;
+    return e && strcmp(e, "ws") == 0 ? 2 : 0;
 }
 
 __global__ void __launch_bounds__(RB_BLOCK)

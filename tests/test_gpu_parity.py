@@ -314,10 +314,9 @@ def test_rollout_matches_oracle(rb, oracle_fr3):
 
 
 @pytest.mark.parametrize("B", [1, 33, 100, 4096])
-def test_rollout_kernels_agree_bitwise(rb, oracle_fr3, B):
-    """rb_rollout_ws_kernel (two warps per 32 trajectories, default) performs the operations of rb_rollout_kernel (one
-    thread per trajectory, RIGIDBODY_B200_ROLLOUT=thread) in the same order: trajectories and costs are bit-identical,
-    ragged tails included."""
+def test_rollout_launch_modes_agree_bitwise(rb, oracle_fr3, B):
+    """$RIGIDBODY_B200_ROLLOUT=ws selects the two-warp kernel of experiments/rb_rollout_ws.cuh in builds that have it
+    (-DRB_ROLLOUT_WS=1; ignored otherwise): bit-identical trajectories and costs, ragged tails included."""
     H, dt = 24, 1e-3
     q, dq, _, _ = _states(oracle_fr3, B, seed=0x5EED0003)
     lim = oracle_fr3.model
@@ -328,15 +327,36 @@ def test_rollout_kernels_agree_bitwise(rb, oracle_fr3, B):
             continue
         a = mb.rollout(q, dq, tau, dt, final=True)
         ca = mb.rollout_cost(q, dq, tau, dt, w_q=w, w_dq=0.1 * w, w_tau=1e-3 * w, w_q_final=3 * w)
-        os.environ["RIGIDBODY_B200_ROLLOUT"] = "thread"
-        try:
-            b = mb.rollout(q, dq, tau, dt, final=True)
-            cb = mb.rollout_cost(q, dq, tau, dt, w_q=w, w_dq=0.1 * w, w_tau=1e-3 * w, w_q_final=3 * w)
-        finally:
-            os.environ.pop("RIGIDBODY_B200_ROLLOUT", None)
-        for x, y in zip(a, b):
-            np.testing.assert_array_equal(x, y, err_msg=mb.kernel_variant)
-        np.testing.assert_array_equal(ca, cb, err_msg=mb.kernel_variant)
+        for mode in ("ws",):
+            os.environ["RIGIDBODY_B200_ROLLOUT"] = mode
+            try:
+                b = mb.rollout(q, dq, tau, dt, final=True)
+                cb = mb.rollout_cost(q, dq, tau, dt, w_q=w, w_dq=0.1 * w, w_tau=1e-3 * w, w_q_final=3 * w)
+            finally:
+                os.environ.pop("RIGIDBODY_B200_ROLLOUT", None)
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(x, y, err_msg=mb.kernel_variant + " " + mode)
+            np.testing.assert_array_equal(ca, cb, err_msg=mb.kernel_variant + " " + mode)
+
+
+def test_rollout_is_forward_dynamics_plus_fma_euler_bitwise(mb_fr3, oracle_fr3):
+    """The rollout kernel performs the arithmetic of the forward-dynamics kernel: stepping with
+    multibody_forward_dynamics_batch and an exactly rounded fma-Euler update reproduces it bit for bit."""
+    import mpmath as mp
+    mp.mp.prec = 200
+    B, H, dt = 33, 5, 1e-3
+    q, dq, _, _ = _states(oracle_fr3, B, seed=0x5EED0003)
+    lim = oracle_fr3.model
+    tau = np.stack([oracle_fr3.fill(0x5EED0003, 4 + t % 32, -lim.effort, lim.effort, t * B, B) for t in range(H)])
+    qt, dqt = mb_fr3.rollout(q, dq, tau, dt)
+    fma = np.vectorize(lambda a, b, c: float(mp.mpf(a) * mp.mpf(b) + mp.mpf(c)))
+    qs, dqs = q.copy(), dq.copy()
+    for t in range(H):
+        qdd = mb_fr3.forward_dynamics(qs, dqs, tau[t])
+        dqs = fma(dt, qdd, dqs)
+        qs = fma(dt, dqs, qs)
+        np.testing.assert_array_equal(dqt[t], dqs)
+        np.testing.assert_array_equal(qt[t], qs)
 
 
 def test_rollout_chain32(rb, mb_chain32, oracle_chain32):
@@ -734,7 +754,7 @@ def test_not_spd_is_reported(rb):
     with pytest.raises(rb.NotPositiveDefinite):
         mb.rnea_fd(z, z, z, z)
     tau = np.zeros((3, 2, 4))
-    for mode in (None, "thread"):
+    for mode in (None, "ws"):
         if mode:
             os.environ["RIGIDBODY_B200_ROLLOUT"] = mode
         try:

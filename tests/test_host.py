@@ -162,7 +162,7 @@ def test_bench_fp64_instruction_counts_match_the_built_library(built):
                          capture_output=True, text=True, check=True).stdout
     spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
-    for kernel, want in bench.FP64_INSTR.items():
+    for kernel, want in bench.FP64_STATIC.items():
         line = [l for l in out.splitlines() if l.startswith(kernel + "I7CtModelI6TabFr3dELb0E")]    # fp64, SoA instantiation
         assert len(line) == 1, out
         got = int(line[0].split("FP64 total")[1].split()[0])
