@@ -49,5 +49,6 @@ int main(int argc, char** argv) {
     multibody_free_result(tau1);
     multibody_gpu_free(g);
     multibody_free(mb);
-    return (e_single == 0.0 && e_round < 1e-9 && e_onecall == 0.0) ? 0 : 1;
+    // the one-call entry point runs the fused kernel: tau = bias + H ddq agrees with the recursion to rounding
+    return (e_single == 0.0 && e_round < 1e-9 && e_onecall < 1e-11) ? 0 : 1;
 }

@@ -111,7 +111,8 @@ typedef struct RbJointLimits {
     double lower[RB_MAX_JOINTS], upper[RB_MAX_JOINTS], velocity[RB_MAX_JOINTS], effort[RB_MAX_JOINTS];
 } RbJointLimits;
 
-/* Opaque engine: one chain descriptor resident on one GPU, plus its streams and staging buffers. */
+/* Opaque engine: one chain descriptor resident on one GPU, plus its streams and staging buffers (or, from
+ * multibody_gpu_new_multi, one such engine per listed GPU behind a single handle). */
 typedef struct RbGpu RbGpu;
 
 /* ---- construction -------------------------------------------------------------------------- */
@@ -124,8 +125,28 @@ int multibody_gpu_new_from_urdf(const char* urdf_path, int device, RbGpu** out);
 /* Engine for an existing reference-style handle. */
 int multibody_gpu_from_multibody(const Multibody* mb, int device, RbGpu** out);
 void multibody_gpu_free(RbGpu* g);
-/* The Rust crate rust/rigidbody_gpu_bindings additionally exports, for callers holding the Rust Multibody*:
- *   int multibody_gpu_from_rust(const Multibody* mb, int device, RbGpu** out);    */
+#ifdef RIGIDBODY_HAVE_RUST_BRIDGE
+/* Exported by the Rust crate rust/rigidbody_gpu_bindings (not by librigidbody_b200.so), for callers that hold the
+ * reference crate's own `Multibody*` (rigidbody_bindings/src/lib.rs:8-12): flattens it with ChainArrays::from_multibody
+ * (multibody.rs:79-81, joint.rs:26-31, inertia.rs:12-17) and calls multibody_gpu_new.  See INTEGRATION.md. */
+int multibody_gpu_from_rust(const Multibody* mb, int device, RbGpu** out);
+#endif
+
+/* ---- one engine over several GPUs of the box ------------------------------------------------- */
+/* The one-call shape of the reference (rigidbody_bindings/src/lib.rs:15-30: one host batch in, one result out) over
+ * n_dev devices: the chain is uploaded to every device listed, and every RB_MEM_HOST batch call on the returned handle
+ * cuts its batch into n_dev contiguous slices (device i owns states [B*i/n_dev, B*(i+1)/n_dev)), each moved and computed
+ * by its own host thread, copy streams and staging buffers; the call returns when the last device has written its slice
+ * of `out`.  No collective and no peer traffic: results are those of a single-device engine, bit for bit.
+ * RB_MEM_DEVICE calls need pointers on ONE device: they return RB_ERR_UNSUPPORTED on this handle; use the per-device
+ * engines (multibody_gpu_peer) for device-resident slices.  n_dev = 1 returns an ordinary engine.  devices: distinct
+ * CUDA ordinals.  Free with multibody_gpu_free (frees the per-device engines too). */
+int multibody_gpu_new_multi(const RbChainDesc* desc, const int* devices, int n_dev, RbGpu** out);
+int multibody_gpu_new_multi_from_urdf(const char* urdf_path, const int* devices, int n_dev, RbGpu** out);
+/* Devices behind a handle (1 for an ordinary engine) and the single-device engine of device slot `index` (the handle
+ * itself for an ordinary engine and index 0); owned by the handle, never freed by the caller. */
+int multibody_gpu_n_devices(const RbGpu* g);
+RbGpu* multibody_gpu_peer(RbGpu* g, int index);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 int multibody_gpu_n_joints(const RbGpu* g);
@@ -156,8 +177,12 @@ const char* multibody_last_error(void);
  * RB_MEM_DEVICE calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the legacy default
  * stream, as in every CUDA library) and return after the launch; sync the stream (or call multibody_gpu_sync)
  * before reading.  `stream` is ignored by RB_MEM_HOST calls.
- * RB_MEM_HOST calls are synchronous: they stage through the engine's pinned buffers in chunks, overlapping
- * H2D, compute and D2H, and return when `out` is complete.
+ * RB_MEM_HOST calls are synchronous: the batch is cut into chunks that flow host -> device staging buffer -> kernel
+ * -> device staging buffer -> host on three streams (H2D, compute and D2H of different chunks overlap); copies read and
+ * write the CALLER's memory directly, there is no pinned bounce buffer.  Pinned caller memory (multibody_host_alloc, or
+ * cudaHostRegister on memory the caller already owns) makes those copies asynchronous DMA at PCIe rate; with pageable
+ * memory the CUDA runtime stages every copy itself, the overlap is lost and throughput drops (measured: see
+ * profiles/ and bench.py's e2e.pageable).  The call returns when `out` is complete.
  * With n_states = 1, AOS, HOST these are the reference's single-state calls minus the leak.
  */
 
@@ -257,6 +282,11 @@ uint64_t multibody_gpu_launch_count(const RbGpu* g);
 /* Pinned host allocations, so RB_MEM_HOST calls copy at full PCIe rate without a staging hop. */
 int multibody_host_alloc(void** out, size_t bytes);
 void multibody_host_free(void* p);
+/* Bare ceiling of the host<->device path RB_MEM_HOST calls use: h2d_bytes from pinned host memory to the device and,
+ * concurrently, d2h_bytes back (both split evenly over the devices of a multi-device engine, all devices at once), no
+ * kernel in between; best of `reps` passes by wall clock.  Returns GB/s per direction, summed over devices: what an
+ * end-to-end call moving the same bytes cannot beat (bench.py reports e2e as a fraction of it). */
+int multibody_gpu_measure_copy_peak(RbGpu* g, size_t h2d_bytes, size_t d2h_bytes, int reps, double* h2d_gbs, double* d2h_gbs);
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), measured with a register-only
  * dependent-chain kernel for `millis` ms: the FP64 roofline denominator bench.py reports against. */
 int multibody_gpu_measure_fp64_peak(RbGpu* g, int millis, double* tflops);

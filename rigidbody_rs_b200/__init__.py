@@ -86,10 +86,36 @@ class Multibody:
 
     # ---- construction (multibody.rs:65-77)
     @classmethod
-    def from_urdf(cls, path, device=0):
+    def from_urdf(cls, path, device=0, devices=None):
+        """`devices` (a list of CUDA ordinals) builds ONE engine over several GPUs (multibody_gpu_new_multi_from_urdf):
+        host batches are cut into contiguous slices, one per device; device tensors then go to `peer(i)`."""
         h = C.c_void_p()
-        check(lib.multibody_gpu_new_from_urdf(str(path).encode(), int(device), C.byref(h)))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            check(lib.multibody_gpu_new_multi_from_urdf(str(path).encode(), arr, len(devices), C.byref(h)))
+        else:
+            check(lib.multibody_gpu_new_from_urdf(str(path).encode(), int(device), C.byref(h)))
         return cls(h)
+
+    @property
+    def n_devices(self):
+        return lib.multibody_gpu_n_devices(self._h)
+
+    def peer(self, index):
+        """The single-device engine of device slot `index` of a multi-device engine (owned by this object)."""
+        h = lib.multibody_gpu_peer(self._h, int(index))
+        if not h:
+            check(_lib.RB_ERR_ARG)
+        m = Multibody(C.c_void_p(h), owns=False)
+        m._parent = self          # keeps the owner alive
+        return m
+
+    def copy_peak(self, h2d_bytes, d2h_bytes, reps=3):
+        """Bare pinned-copy ceiling of the host path (multibody_gpu_measure_copy_peak): (h2d GB/s, d2h GB/s), both
+        directions at once, summed over the devices of the engine."""
+        a, b = C.c_double(), C.c_double()
+        check(lib.multibody_gpu_measure_copy_peak(self._h, int(h2d_bytes), int(d2h_bytes), int(reps), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @classmethod
     def from_descriptor(cls, parent_rot, parent_trans, mass, com, inertia_com, gravity=(0.0, 0.0, 9.81),

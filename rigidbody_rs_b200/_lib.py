@@ -78,6 +78,11 @@ PROTOTYPES = {
     "multibody_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "multibody_host_free": (None, [_vp]),
     "multibody_gpu_measure_fp64_peak": (_i, [_vp, _i, _dp]),
+    "multibody_gpu_new_multi": (_i, [C.POINTER(RbChainDesc), C.POINTER(C.c_int), _i, C.POINTER(_vp)]),
+    "multibody_gpu_new_multi_from_urdf": (_i, [C.c_char_p, C.POINTER(C.c_int), _i, C.POINTER(_vp)]),
+    "multibody_gpu_n_devices": (_i, [_vp]),
+    "multibody_gpu_peer": (_vp, [_vp, _i]),
+    "multibody_gpu_measure_copy_peak": (_i, [_vp, _sz, _sz, _i, _dp, _dp]),
 }
 
 

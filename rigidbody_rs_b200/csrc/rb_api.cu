@@ -7,7 +7,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,7 +59,56 @@ struct DevBuf {
 
 }  // namespace
 
+// One host thread per device of a multi-device engine: runs the slice of a host batch that its device owns.
+struct RbWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = true, stop = false;
+    int rc = RB_OK;
+    std::string err;
+    void run_loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || stop; });
+            if (stop) return;
+            std::function<int()> j = std::move(job);
+            has_job = false;
+            lk.unlock();
+            int r = RB_ERR_ARG; std::string e;
+            try { r = j(); if (r != RB_OK) e = g_err; }
+            catch (const std::exception& ex) { r = RB_ERR_ARG; e = std::string("exception: ") + ex.what(); }
+            lk.lock();
+            rc = r; err = e; done = true;
+            cv.notify_all();
+        }
+    }
+    void start() { th = std::thread([this] { run_loop(); }); }
+    void submit(std::function<int()> j) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(j); has_job = true; done = false;
+        cv.notify_all();
+    }
+    int wait(std::string* e) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return done; });
+        if (rc != RB_OK && e) *e = err;
+        return rc;
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; cv.notify_all(); }
+        if (th.joinable()) th.join();
+    }
+};
+
 struct RbGpu {
+    // A multi-device engine (multibody_gpu_new_multi) is a dispatcher: `peers` holds one ordinary single-device engine
+    // per device and `workers` one host thread per peer; it owns no CUDA resources itself.  Host batches are cut into
+    // contiguous slices, one per device; empty for an ordinary engine.
+    std::vector<RbGpu*> peers;
+    std::vector<RbWorker*> workers;
+    std::mutex mu_multi;                  // one multi-device call at a time (the workers hold one job each)
     int device = 0;
     int sm_count = 0;
     RbHostModel model;
@@ -76,8 +129,13 @@ struct RbGpu {
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
     DevBuf in[kSlots], out[kSlots], tmp[kSlots];
+    // Device status words (RB_STATUS_* bits set by kernels with atomicOr) and their pinned host mirrors:
+    //   [0] accumulates over RB_MEM_DEVICE calls (any stream, any thread) until multibody_gpu_sync reads and clears it;
+    //   [1] belongs to the ONE host-batch call holding `mu`: cleared when the call starts, read before `mu` is released,
+    //       so a host call never reports (or swallows) a bit set by somebody else's states.
     int* d_status = nullptr;
-    int* h_status = nullptr;              // pinned
+    int* h_status = nullptr;              // pinned, 2 words
+    std::mutex mu_status;                 // serialises readers of word [0]
     int sticky = RB_OK;
     std::atomic<uint64_t> launches{0};
     cudaEvent_t ev_scratch = nullptr;     // orders users of the engine-owned scratch (run-time-n / long-chain families) across streams
@@ -261,8 +319,10 @@ int gpu_create(const RbHostModel& model, int device, RbGpu** out) {
     if (device < 0 || device >= count) return fail(RB_ERR_ARG, "device ordinal out of range");
     cudaDeviceProp prop;
     RB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(RB_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; kernels are built for sm_100a only");
+    // sm_100a code is architecture-specific: it runs on compute capability 10.0 and nothing else (not 10.3, not 12.x)
+    if (prop.major != 10 || prop.minor != 0)
+        return fail(RB_ERR_CUDA, std::string("device '") + prop.name + "' has compute capability " + std::to_string(prop.major) + "." +
+                                     std::to_string(prop.minor) + "; the kernels are built (and run-time compiled) for sm_100a = 10.0 only");
     DeviceGuard dg(device);
     if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
     RbGpu* g = new (std::nothrow) RbGpu();
@@ -280,10 +340,12 @@ int gpu_create(const RbHostModel& model, int device, RbGpu** out) {
         if ((e = cudaEventCreateWithFlags(&g->ev_d2h[k], cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
     }
     if ((e = cudaEventCreateWithFlags(&g->ev_scratch, cudaEventDisableTiming)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
-    if ((e = cudaMalloc((void**)&g->d_status, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(status)"));
-    if ((e = cudaMemset(g->d_status, 0, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset(status)"));
-    if ((e = cudaMallocHost((void**)&g->h_status, sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMallocHost(status)"));
-    *g->h_status = 0;
+    if ((e = cudaMalloc((void**)&g->d_status, 2 * sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(status)"));
+    if ((e = cudaMemset(g->d_status, 0, 2 * sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMemset(status)"));
+    if ((e = cudaMallocHost((void**)&g->h_status, 2 * sizeof(int))) != cudaSuccess) return bail(fail_cuda(e, "cudaMallocHost(status)"));
+    g->h_status[0] = g->h_status[1] = 0;
+    // cost weights of multibody_rollout_cost: allocated once, here (a lazy first-call allocation would race)
+    { int rcw = g->cost_w.ensure(sizeof(double) * RB_CW_ROWS * RB_MAX_N); if (rcw != RB_OK) return bail(rcw); }
     int rc = pick_ops(g);
     if (rc != RB_OK) return bail(rc);
     if (const char* f = getenv("RIGIDBODY_B200_FUSED")) g->split_rnea_fd = std::string(f) == "0";
@@ -291,16 +353,28 @@ int gpu_create(const RbHostModel& model, int device, RbGpu** out) {
     return RB_OK;
 }
 
-// Reads and clears the device status word; maps it to an RbStatus.  Stream must be idle.
-int fetch_status(RbGpu* g) {
-    RB_CUDA(cudaMemcpyAsync(g->h_status, g->d_status, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
-    RB_CUDA(cudaMemsetAsync(g->d_status, 0, sizeof(int), g->stream));
+// Reads and clears status word `which` (see RbGpu::d_status); maps it to an RbStatus.  Caller holds the lock that owns
+// the word (mu for [1], mu_status for [0]) and g->stream has nothing of the caller's in flight but this.
+int fetch_status(RbGpu* g, int which) {
+    RB_CUDA(cudaMemcpyAsync(g->h_status + which, g->d_status + which, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    RB_CUDA(cudaMemsetAsync(g->d_status + which, 0, sizeof(int), g->stream));
     RB_CUDA(cudaStreamSynchronize(g->stream));
-    if (*g->h_status & RB_STATUS_NOT_SPD) {
-        *g->h_status = 0;
+    const int bits = g->h_status[which];
+    g->h_status[which] = 0;
+    if (bits & RB_STATUS_NOT_SPD)
         return fail(RB_ERR_NOT_SPD, "forward dynamics: mass matrix not positive definite for at least one state (its qdd is NaN)");
-    }
     return RB_OK;
+}
+
+// A host-batch call that fails half-way must not return while copies it queued still read or write the caller's
+// buffers, nor leave its staging slots and status word mid-flight for the next call.
+void drain_host_pipeline(RbGpu* g) {
+    cudaStreamSynchronize(g->s_h2d);
+    cudaStreamSynchronize(g->stream);
+    cudaStreamSynchronize(g->s_d2h);
+    cudaMemsetAsync(g->d_status + 1, 0, sizeof(int), g->stream);
+    cudaStreamSynchronize(g->stream);
+    cudaGetLastError();
 }
 
 // ---- a batched op, described once, run from device or host memory ----
@@ -311,9 +385,9 @@ struct OpDesc {
     double* out;
     int out_per;                 // doubles per state of the output
     // launch on SoA device buffers with leading dimension ld
-    cudaError_t (*launch)(RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st);
+    cudaError_t (*launch)(RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status);
     // optional: launch directly on AoS device buffers (kernel stages through shared memory); null = transpose around `launch`
-    cudaError_t (*launch_aos)(RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) = nullptr;
+    cudaError_t (*launch_aos)(RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st, int* status) = nullptr;
     bool (*has_aos)(RbGpu* g) = nullptr;
 };
 
@@ -333,13 +407,13 @@ int check_common(RbGpu* g, const OpDesc& op, size_t n_states, size_t& ld, RbLayo
 
 int run_device(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout, cudaStream_t st) {
     if (layout == RB_LAYOUT_SOA) {
-        cudaError_t e = op.launch(g, op.in, op.out, B, ld, st);
+        cudaError_t e = op.launch(g, op.in, op.out, B, ld, st, g->d_status);
         g->launches += 1;
         if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
         return RB_OK;
     }
     if (op.launch_aos && op.has_aos(g)) {
-        cudaError_t e = op.launch_aos(g, op.in, op.out, B, st);
+        cudaError_t e = op.launch_aos(g, op.in, op.out, B, st, g->d_status);
         g->launches += 1;
         if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
         return RB_OK;
@@ -358,7 +432,7 @@ int run_device(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout,
         if (e != cudaSuccess) return fail_cuda(e, "aos_to_soa launch");
         soa_in[k] = dst; off += (size_t)op.in_per[k];
     }
-    cudaError_t e = op.launch(g, soa_in, g->out[0].p, B, B, st);
+    cudaError_t e = op.launch(g, soa_in, g->out[0].p, B, B, st, g->d_status);
     g->launches += 1;
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     e = rb_launch_soa_to_aos(g->out[0].p, op.out, op.out_per, B, B, st);
@@ -369,9 +443,8 @@ int run_device(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout,
     return RB_OK;
 }
 
-// Host batch: chunks flow H2D -> compute -> D2H on three streams through kSlots staging slots.
-int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
-    std::lock_guard<std::mutex> lk(g->mu);
+// Host batch: chunks flow H2D -> compute -> D2H on three streams through kSlots staging slots.  Caller holds g->mu.
+int run_host_pipeline(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
     size_t in_d = 0;
     for (int k = 0; k < op.n_in; ++k) in_d += (size_t)op.in_per[k];
     const size_t per_state = (in_d + (size_t)op.out_per) * sizeof(double);
@@ -413,7 +486,7 @@ int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
             // inputs landed in tmp[s] as AoS; the kernel reads them there and writes AoS output into out[s]
             const double* aos_in[4]; off = 0;
             for (int k = 0; k < op.n_in; ++k) { aos_in[k] = g->tmp[s].p + off * chunk; off += (size_t)op.in_per[k]; }
-            cudaError_t e = op.launch_aos(g, aos_in, g->out[s].p, cnt, g->stream);
+            cudaError_t e = op.launch_aos(g, aos_in, g->out[s].p, cnt, g->stream, g->d_status + 1);
             g->launches += 1;
             if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
             RB_CUDA(cudaEventRecord(g->ev_comp[s], g->stream));
@@ -435,7 +508,7 @@ int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
             off = 0;
             for (int k = 0; k < op.n_in; ++k) { soa_in[k] = g->in[s].p + off * chunk; off += (size_t)op.in_per[k]; }
         }
-        cudaError_t e = op.launch(g, soa_in, g->out[s].p, cnt, cnt, g->stream);
+        cudaError_t e = op.launch(g, soa_in, g->out[s].p, cnt, cnt, g->stream, g->d_status + 1);
         g->launches += 1;
         if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
         if (aos) {
@@ -459,16 +532,64 @@ int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout) {
     return RB_OK;
 }
 
+int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout, bool has_status) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    int rc = RB_OK;
+    if (has_status) {       // this call's own status word starts clean
+        cudaError_t e = cudaMemsetAsync(g->d_status + 1, 0, sizeof(int), g->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(status)");
+    }
+    rc = run_host_pipeline(g, op, B, ld, layout);
+    if (rc != RB_OK) { const std::string keep = g_err; drain_host_pipeline(g); g_err = keep; return rc; }
+    return has_status ? fetch_status(g, 1) : RB_OK;     // still under g->mu
+}
+
+// Contiguous slice of a batch owned by device `i` of `n`.
+inline void slice_bounds(size_t B, size_t n, size_t i, size_t* lo, size_t* hi) { *lo = B * i / n; *hi = B * (i + 1) / n; }
+
+const char* kMultiDeviceOnly = "a multi-device engine serves RB_MEM_HOST batches; for device pointers call the per-device engine (multibody_gpu_peer)";
+
+// Runs job(i) for every peer on that peer's worker thread, waits for all of them; first hard error wins, otherwise
+// RB_ERR_NOT_SPD if any slice reported it.
+int run_on_peers(RbGpu* g, const std::function<int(size_t)>& job) {
+    std::lock_guard<std::mutex> lk(g->mu_multi);
+    const size_t n = g->peers.size();
+    for (size_t i = 0; i < n; ++i) g->workers[i]->submit([&job, i] { return job(i); });
+    int rc = RB_OK; std::string err;
+    for (size_t i = 0; i < n; ++i) {
+        std::string e;
+        const int r = g->workers[i]->wait(&e);
+        if (r != RB_OK && (rc == RB_OK || (rc == RB_ERR_NOT_SPD && r != RB_ERR_NOT_SPD))) { rc = r; err = "device " + std::to_string(g->peers[i]->device) + ": " + e; }
+    }
+    if (rc != RB_OK) g_err = err;
+    return rc;
+}
+
+int run_host(RbGpu* g, const OpDesc& op, size_t B, size_t ld, RbLayout layout, bool has_status);
+
 int run_op(RbGpu* g, OpDesc& op, size_t n_states, size_t ld, RbLayout layout, RbMem mem, void* stream, bool has_status) {
     int rc = check_common(g, op, n_states, ld, layout, mem);
     if (rc != RB_OK || n_states == 0) return rc;
+    if (!g->peers.empty()) {
+        if (mem != RB_MEM_HOST) return fail(RB_ERR_UNSUPPORTED, kMultiDeviceOnly);
+        const bool aos = layout == RB_LAYOUT_AOS;
+        return run_on_peers(g, [&](size_t i) -> int {
+            size_t lo, hi; slice_bounds(n_states, g->peers.size(), i, &lo, &hi);
+            if (hi == lo) return RB_OK;
+            RbGpu* pg = g->peers[i];
+            OpDesc sub = op;            // same launchers, pointers advanced to the slice (SoA: column lo of every row)
+            for (int k = 0; k < op.n_in; ++k) sub.in[k] = op.in[k] + lo * (aos ? (size_t)op.in_per[k] : 1);
+            sub.out = op.out + lo * (aos ? (size_t)op.out_per : 1);
+            DeviceGuard dg(pg->device);
+            if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
+            return run_host(pg, sub, hi - lo, ld, layout, has_status);
+        });
+    }
     DeviceGuard dg(g->device);
     if (!dg.ok) return fail(RB_ERR_CUDA, "cudaSetDevice failed");
     if (mem == RB_MEM_DEVICE)
         return run_device(g, op, n_states, ld, layout, (cudaStream_t)stream);
-    rc = run_host(g, op, n_states, ld, layout);
-    if (rc != RB_OK) return rc;
-    return has_status ? fetch_status(g) : RB_OK;
+    return run_host(g, op, n_states, ld, layout, has_status);
 }
 
 }  // namespace
@@ -492,6 +613,84 @@ extern "C" int multibody_gpu_new_from_urdf(const char* urdf_path, int device, Rb
     } catch (const std::exception& e) { return fail(RB_ERR_ARG, std::string("exception: ") + e.what()); }
 }
 
+namespace {
+// n_dev single-device engines behind one dispatcher handle (n_dev == 1: just the engine).
+int gpu_create_multi(const RbHostModel& model, const int* devices, int n_dev, RbGpu** out) {
+    if (!out) return fail(RB_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    if (!devices) return fail(RB_ERR_NULL, "devices is NULL");
+    if (n_dev < 1 || n_dev > 64) return fail(RB_ERR_ARG, "n_dev must be 1..64");
+    for (int i = 0; i < n_dev; ++i)
+        for (int k = 0; k < i; ++k)
+            if (devices[i] == devices[k]) return fail(RB_ERR_ARG, "device listed twice");
+    if (n_dev == 1) return gpu_create(model, devices[0], out);
+    RbGpu* g = new (std::nothrow) RbGpu();
+    if (!g) return fail(RB_ERR_CUDA, "out of host memory");
+    g->device = devices[0];
+    g->model = model;
+    // the per-device engines are built concurrently (each may run the run-time compiler or read its disk cache)
+    g->peers.assign((size_t)n_dev, nullptr);
+    std::vector<int> rcs((size_t)n_dev, RB_OK);
+    std::vector<std::string> errs((size_t)n_dev);
+    {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_dev; ++i)
+            th.emplace_back([&, i] {
+                try { rcs[i] = gpu_create(model, devices[i], &g->peers[i]); if (rcs[i] != RB_OK) errs[i] = g_err; }
+                catch (const std::exception& e) { rcs[i] = RB_ERR_ARG; errs[i] = std::string("exception: ") + e.what(); }
+            });
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < n_dev; ++i)
+        if (rcs[i] != RB_OK) {
+            const int rc = rcs[i]; const std::string msg = "device " + std::to_string(devices[i]) + ": " + errs[i];
+            multibody_gpu_free(g);
+            return fail(rc, msg);
+        }
+    g->sm_count = g->peers[0]->sm_count;
+    g->ops = g->peers[0]->ops;
+    g->family_note = g->peers[0]->family_note;
+    for (int i = 0; i < n_dev; ++i) {
+        RbWorker* w = new (std::nothrow) RbWorker();
+        if (!w) { multibody_gpu_free(g); return fail(RB_ERR_CUDA, "out of host memory"); }
+        g->workers.push_back(w);
+        w->start();
+    }
+    *out = g;
+    return RB_OK;
+}
+}  // namespace
+
+extern "C" int multibody_gpu_new_multi(const RbChainDesc* desc, const int* devices, int n_dev, RbGpu** out) {
+    try {
+        RbHostModel m; std::string err;
+        int rc = rb_model_from_desc(desc, m, err);
+        if (rc != RB_OK) { if (out) *out = nullptr; return fail(rc, err); }
+        return gpu_create_multi(m, devices, n_dev, out);
+    } catch (const std::exception& e) { return fail(RB_ERR_ARG, std::string("exception: ") + e.what()); }
+}
+
+extern "C" int multibody_gpu_new_multi_from_urdf(const char* urdf_path, const int* devices, int n_dev, RbGpu** out) {
+    try {
+        RbHostModel m; std::string err;
+        int rc = rb_model_from_urdf(urdf_path, m, err);
+        if (rc != RB_OK) { if (out) *out = nullptr; return fail(rc, err); }
+        return gpu_create_multi(m, devices, n_dev, out);
+    } catch (const std::exception& e) { return fail(RB_ERR_ARG, std::string("exception: ") + e.what()); }
+}
+
+extern "C" int multibody_gpu_n_devices(const RbGpu* g) {
+    if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    return g->peers.empty() ? 1 : (int)g->peers.size();
+}
+
+extern "C" RbGpu* multibody_gpu_peer(RbGpu* g, int index) {
+    if (!g) { fail(RB_ERR_NULL, "engine handle is NULL"); return nullptr; }
+    if (g->peers.empty()) return index == 0 ? g : (fail(RB_ERR_ARG, "peer index out of range"), (RbGpu*)nullptr);
+    if (index < 0 || index >= (int)g->peers.size()) { fail(RB_ERR_ARG, "peer index out of range"); return nullptr; }
+    return g->peers[(size_t)index];
+}
+
 extern "C" int multibody_gpu_from_multibody(const Multibody* mb, int device, RbGpu** out) {
     if (!mb) return fail(RB_ERR_NULL, "Multibody handle is NULL");
     try { return gpu_create(mb->model, device, out); }
@@ -500,6 +699,12 @@ extern "C" int multibody_gpu_from_multibody(const Multibody* mb, int device, RbG
 
 extern "C" void multibody_gpu_free(RbGpu* g) {
     if (!g) return;
+    if (!g->peers.empty() || !g->workers.empty()) {      // dispatcher of a multi-device engine: no CUDA resources of its own
+        for (RbWorker* w : g->workers) { w->shutdown(); delete w; }
+        for (RbGpu* pg : g->peers) multibody_gpu_free(pg);
+        delete g;
+        return;
+    }
     DeviceGuard dg(g->device);
     cudaDeviceSynchronize();              // device calls may still be running on caller streams and use our scratch
     if (g->ev_scratch) cudaEventDestroy(g->ev_scratch);
@@ -542,7 +747,12 @@ extern "C" int multibody_gpu_n_joints(const RbGpu* g) { return g ? g->model.n : 
 extern "C" int multibody_gpu_device(const RbGpu* g) { return g ? g->device : fail(RB_ERR_NULL, "engine handle is NULL"); }
 extern "C" const char* multibody_gpu_kernel_variant(const RbGpu* g) { return g && g->ops ? g->ops->name : ""; }
 extern "C" const char* multibody_last_error(void) { return g_err.c_str(); }
-extern "C" uint64_t multibody_gpu_launch_count(const RbGpu* g) { return g ? g->launches.load() : (uint64_t)0; }
+extern "C" uint64_t multibody_gpu_launch_count(const RbGpu* g) {
+    if (!g) return 0;
+    uint64_t total = g->launches.load();
+    for (const RbGpu* pg : g->peers) total += pg->launches.load();
+    return total;
+}
 
 static void copy_model(const RbHostModel& m, double* parent_rot, double* parent_trans, double* mass, double* h,
                        double* inertia_origin) {
@@ -584,11 +794,11 @@ extern "C" int multibody_rnea_batch(RbGpu* g, const double* q, const double* dq,
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
     OpDesc op{3, {q, dq, ddq}, {n, n, n}, tau, n,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
                   ScratchOrder so(g, RB_TABLE(g, rnea), st);
                   return RB_TABLE(g, rnea)->rnea(RB_PARAM(g, rnea), in[0], in[1], in[2], out, B, ld, st);
               },
-              [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st, int* status) {
                   return g->ops->rnea_aos(g->param.data(), in[0], in[1], in[2], out, B, st);
               },
               [](RbGpu* g) { return g->ops->rnea_aos != nullptr; }};
@@ -600,12 +810,12 @@ extern "C" int multibody_forward_dynamics_batch(RbGpu* g, const double* q, const
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
     OpDesc op{3, {q, dq, tau}, {n, n, n}, qdd, n,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
                   ScratchOrder so(g, RB_TABLE(g, fd), st);
-                  return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[2], out, B, ld, g->d_status, st);
+                  return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[2], out, B, ld, status, st);
               },
-              [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st) {
-                  return g->ops->fd_aos(g->param.data(), in[0], in[1], in[2], out, B, g->d_status, st);
+              [](RbGpu* g, const double* const* in, double* out, size_t B, cudaStream_t st, int* status) {
+                  return g->ops->fd_aos(g->param.data(), in[0], in[1], in[2], out, B, status, st);
               },
               [](RbGpu* g) { return g->ops->fd_aos != nullptr; }};
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
@@ -617,11 +827,11 @@ extern "C" int multibody_rnea_fd_batch(RbGpu* g, const double* q, const double* 
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
     OpDesc op{4, {q, dq, ddq, tau_in}, {n, n, n, n}, out, 2 * n,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
                   const int n = g->model.n;
                   // one fused pass where the family has it (shared sin/cos, bias recursion and mass matrix)
                   if (g->ops->rnea_fd && !g->split_rnea_fd)
-                      return g->ops->rnea_fd(g->param.data(), in[0], in[1], in[2], in[3], out, B, ld, g->d_status, st);
+                      return g->ops->rnea_fd(g->param.data(), in[0], in[1], in[2], in[3], out, B, ld, status, st);
                   {
                       ScratchOrder so(g, RB_TABLE(g, rnea), st);
                       cudaError_t e = RB_TABLE(g, rnea)->rnea(RB_PARAM(g, rnea), in[0], in[1], in[2], out, B, ld, st);
@@ -629,7 +839,7 @@ extern "C" int multibody_rnea_fd_batch(RbGpu* g, const double* q, const double* 
                   }
                   g->launches += 1;
                   ScratchOrder so(g, RB_TABLE(g, fd), st);
-                  return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[3], out + (size_t)n * ld, B, ld, g->d_status, st);
+                  return RB_TABLE(g, fd)->fd(RB_PARAM(g, fd), in[0], in[1], in[3], out + (size_t)n * ld, B, ld, status, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }
@@ -642,7 +852,7 @@ extern "C" int multibody_rnea_derivatives_batch(RbGpu* g, const double* q, const
     if (n > RB_RNEA_DERIV_MAX_N || !g->model.serial)
         return fail(RB_ERR_UNSUPPORTED, "inverse-dynamics derivative kernels serve serial chains of at most 32 joints");
     OpDesc op{3, {q, dq, ddq}, {n, n, n}, out, 2 * n * n,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
                   return rb_launch_rnea_deriv(g->model.n, g->flat.data(), in[0], in[1], in[2], out, B, ld, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, false);
@@ -655,8 +865,8 @@ extern "C" int multibody_fd_derivatives_batch(RbGpu* g, const double* q, const d
     if (n > RB_DERIV_MAX_N || !g->model.serial)
         return fail(RB_ERR_UNSUPPORTED, "forward-dynamics derivative kernels serve serial chains of at most 12 joints");
     OpDesc op{3, {q, dq, tau}, {n, n, n}, out, 3 * n * n,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
-                  return rb_launch_fd_deriv(g->model.n, g->flat.data(), in[0], in[1], in[2], out, B, ld, g->d_status, st);
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
+                  return rb_launch_fd_deriv(g->model.n, g->flat.data(), in[0], in[1], in[2], out, B, ld, status, st);
               }};
     return run_op(g, op, n_states, ld, layout, mem, stream, true);
 }
@@ -677,6 +887,7 @@ extern "C" int multibody_rnea_batch_f32(RbGpu* g, const float* q, const float* d
                                         size_t n_states, size_t ld, void* stream) {
     int rc = f32_common(g, q, dq, ddq, tau, n_states, ld);
     if (rc != RB_OK || n_states == 0) return rc;
+    if (!g->peers.empty()) return fail(RB_ERR_UNSUPPORTED, kMultiDeviceOnly);
     if (!g->ops->rnea_f32) return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no fp32 kernels");
     DeviceGuard dg(g->device);
     cudaError_t e = g->ops->rnea_f32(g->param.data(), q, dq, ddq, tau, n_states, ld, (cudaStream_t)stream);
@@ -689,6 +900,7 @@ extern "C" int multibody_forward_dynamics_batch_f32(RbGpu* g, const float* q, co
                                                     size_t n_states, size_t ld, void* stream) {
     int rc = f32_common(g, q, dq, tau, qdd, n_states, ld);
     if (rc != RB_OK || n_states == 0) return rc;
+    if (!g->peers.empty()) return fail(RB_ERR_UNSUPPORTED, kMultiDeviceOnly);
     if (!g->ops->fd_f32) return fail(RB_ERR_UNSUPPORTED, std::string("kernel family '") + g->ops->name + "' has no fp32 kernels");
     DeviceGuard dg(g->device);
     cudaError_t e = g->ops->fd_f32(g->param.data(), q, dq, tau, qdd, n_states, ld, g->d_status, (cudaStream_t)stream);
@@ -702,7 +914,7 @@ extern "C" int multibody_crba_batch(RbGpu* g, const double* q, double* H, size_t
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, H, n * n,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
                   ScratchOrder so(g, RB_TABLE(g, crba), st);
                   return RB_TABLE(g, crba)->crba(RB_PARAM(g, crba), in[0], out, B, ld, st);
               }};
@@ -714,7 +926,7 @@ extern "C" int multibody_fwd_kin_batch(RbGpu* g, const double* q, double* xyz, s
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, xyz, 3,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
                   ScratchOrder so(g, RB_TABLE(g, fwd_kin), st);
                   return RB_TABLE(g, fwd_kin)->fwd_kin(RB_PARAM(g, fwd_kin), in[0], out, B, ld, st);
               }};
@@ -726,7 +938,7 @@ extern "C" int multibody_jac_batch(RbGpu* g, const double* q, double* J, size_t 
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
     const int n = g->model.n;
     OpDesc op{1, {q, nullptr, nullptr}, {n, 0, 0}, J, 6 * n,
-              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st) {
+              [](RbGpu* g, const double* const* in, double* out, size_t B, size_t ld, cudaStream_t st, int* status) {
                   ScratchOrder so(g, RB_TABLE(g, jac), st);
                   return RB_TABLE(g, jac)->jac(RB_PARAM(g, jac), in[0], out, B, ld, st);
               }};
@@ -734,16 +946,37 @@ extern "C" int multibody_jac_batch(RbGpu* g, const double* q, double* J, size_t 
 }
 
 namespace {
+// `aos_stride`: elements between consecutive steps of the AoS arrays tau / q_traj / dq_traj (0 = n_traj * n, a dense
+// [H][n_traj][n] array; a multi-device engine passes the stride of the whole batch when it hands out slices).
 int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* tau, double dt, int horizon,
                  double* q_traj, double* dq_traj, double* q_final, double* dq_final, const RbQuadCost* w, double* cost,
-                 size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream) {
+                 size_t n_traj, size_t ld, RbLayout layout, RbMem mem, void* stream, size_t aos_stride = 0) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    if (!g->peers.empty()) {
+        if (layout != RB_LAYOUT_SOA && layout != RB_LAYOUT_AOS) return fail(RB_ERR_ARG, "bad layout");
+        if (mem != RB_MEM_HOST) return fail(mem == RB_MEM_DEVICE ? RB_ERR_UNSUPPORTED : RB_ERR_ARG, mem == RB_MEM_DEVICE ? kMultiDeviceOnly : "bad mem");
+        if (n_traj == 0) return RB_OK;
+        const bool aos = layout == RB_LAYOUT_AOS;
+        const size_t n = (size_t)g->model.n;
+        if (!aos) { if (ld == 0) ld = n_traj; if (ld < n_traj) return fail(RB_ERR_ARG, "ld < n_traj"); }
+        return run_on_peers(g, [&](size_t i) -> int {
+            size_t lo, hi; slice_bounds(n_traj, g->peers.size(), i, &lo, &hi);
+            if (hi == lo) return RB_OK;
+            const size_t o = lo * (aos ? n : 1);              // offset of trajectory lo inside one state array
+            auto at = [&](const double* p) { return p ? p + o : nullptr; };
+            auto atw = [&](double* p) { return p ? p + o : nullptr; };
+            return rollout_impl(g->peers[i], at(q0), at(dq0), at(tau), dt, horizon, atw(q_traj), atw(dq_traj), atw(q_final), atw(dq_final),
+                                w, cost ? cost + lo : nullptr, hi - lo, ld, layout, mem, nullptr, aos ? n_traj * n : 0);
+        });
+    }
     if (layout != RB_LAYOUT_SOA && layout != RB_LAYOUT_AOS) return fail(RB_ERR_ARG, "bad layout");
     if (mem != RB_MEM_HOST && mem != RB_MEM_DEVICE) return fail(RB_ERR_ARG, "bad mem");
     if (horizon < 0) return fail(RB_ERR_ARG, "horizon < 0");
     if (!std::isfinite(dt)) return fail(RB_ERR_ARG, "dt must be finite");
-    if (n_traj == 0 || horizon == 0) return RB_OK;
-    if (!q0 || !dq0 || !tau) return fail(RB_ERR_NULL, "input pointer is NULL");
+    if (n_traj == 0) return RB_OK;
+    // horizon == 0 is a rollout of no steps: q_final = q0, dq_final = dq0, cost = the terminal cost; tau is not read
+    if (horizon == 0 && !q_final && !dq_final && !cost) return RB_OK;
+    if (!q0 || !dq0 || (!tau && horizon > 0)) return fail(RB_ERR_NULL, "input pointer is NULL");
     if (layout == RB_LAYOUT_SOA) { if (ld == 0) ld = n_traj; if (ld < n_traj) return fail(RB_ERR_ARG, "ld < n_traj"); }
     const int n = g->model.n;
     if (cost && !w) return fail(RB_ERR_NULL, "cost weights are NULL");
@@ -760,7 +993,6 @@ int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* ta
                 if (!std::isfinite(rows[r][i]) || (r != RB_CW_QREF && rows[r][i] < 0.0)) return fail(RB_ERR_ARG, "cost weights must be finite and non-negative");
                 cw[r * RB_MAX_N + i] = rows[r][i];
             }
-        int rcw = g->cost_w.ensure(sizeof cw); if (rcw) return rcw;
     }
     const bool shared = cost != nullptr || RB_TABLE(g, rollout)->shared_scratch;
     if (mem == RB_MEM_DEVICE && layout == RB_LAYOUT_SOA) {
@@ -774,8 +1006,12 @@ int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* ta
     }
     // Host pointers and/or AoS: stage everything on the device as SoA with ld = n_traj, run once, bring results back.
     std::lock_guard<std::mutex> lk(g->mu);
+    int* const d_stat = g->d_status + (mem == RB_MEM_HOST ? 1 : 0);
+    if (mem == RB_MEM_HOST) RB_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(int), st));
+    auto staged = [&]() -> int {
     const size_t B = n_traj, one = (size_t)n * B, H = (size_t)horizon;
     const bool aos = layout == RB_LAYOUT_AOS, host = mem == RB_MEM_HOST;
+    const size_t src_step = aos ? (aos_stride ? aos_stride : one) : (size_t)n * ld;    // caller's distance between steps
     // in[0]: q0 | dq0 | tau[H]      out[0]: q_traj[H] | dq_traj[H] | q_fin | dq_fin      tmp[0]: AoS landing zone
     int rc = g->in[0].ensure((2 + H) * one * sizeof(double)); if (rc) return rc;
     rc = g->out[0].ensure(((2 * H + 2) * one + B) * sizeof(double)); if (rc) return rc;      // ... | cost[B]
@@ -784,7 +1020,7 @@ int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* ta
     auto bring_in = [&](const double* src, double* dst, size_t arrays) -> int {
         // `arrays` consecutive state arrays
         for (size_t a = 0; a < arrays; ++a) {
-            const double* s_a = src + a * (aos ? one : (size_t)n * ld);
+            const double* s_a = src + a * src_step;
             double* d_a = dst + a * one;
             if (!aos) {
                 RB_CUDA(cudaMemcpy2DAsync(d_a, B * sizeof(double), s_a, ld * sizeof(double), B * sizeof(double), (size_t)n,
@@ -814,7 +1050,7 @@ int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* ta
         if (cost) RB_CUDA(cudaMemcpyAsync(g->cost_w.p, cw, sizeof cw, cudaMemcpyHostToDevice, st));
         e = RB_TABLE(g, rollout)->rollout(RB_PARAM(g, rollout), d_in, d_in + one, d_in + 2 * one, dt, horizon,
                                     q_traj ? d_qt : nullptr, dq_traj ? d_dqt : nullptr, q_final ? d_qf : nullptr,
-                                    dq_final ? d_dqf : nullptr, B, B, g->d_status, cost ? g->cost_w.p : nullptr,
+                                    dq_final ? d_dqf : nullptr, B, B, d_stat, cost ? g->cost_w.p : nullptr,
                                     cost ? d_cost : nullptr, st);
     }
     g->launches += 1;
@@ -823,7 +1059,7 @@ int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* ta
         if (!dst) return RB_OK;
         for (size_t a = 0; a < arrays; ++a) {
             const double* s_a = src + a * one;
-            double* d_a = dst + a * (aos ? one : (size_t)n * ld);
+            double* d_a = dst + a * src_step;
             if (!aos) {
                 RB_CUDA(cudaMemcpy2DAsync(d_a, ld * sizeof(double), s_a, B * sizeof(double), B * sizeof(double), (size_t)n,
                                           host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
@@ -848,7 +1084,17 @@ int rollout_impl(RbGpu* g, const double* q0, const double* dq0, const double* ta
     if (cost) RB_CUDA(cudaMemcpyAsync(cost, d_cost, B * sizeof(double), host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
     // everything above went through engine-owned staging: drain before another call may reuse it
     RB_CUDA(cudaStreamSynchronize(st));
-    return host ? fetch_status(g) : RB_OK;
+    return RB_OK;
+    };
+    const int rc_staged = staged();
+    if (rc_staged != RB_OK) {       // copies already queued must not outlive the call
+        const std::string keep = g_err;
+        cudaStreamSynchronize(st);
+        if (mem == RB_MEM_HOST) drain_host_pipeline(g);
+        g_err = keep;
+        return rc_staged;
+    }
+    return mem == RB_MEM_HOST ? fetch_status(g, 1) : RB_OK;     // still under g->mu
 }
 }  // namespace
 
@@ -869,6 +1115,7 @@ extern "C" int multibody_rollout_cost(RbGpu* g, const double* q0, const double* 
 extern "C" int multibody_gpu_fill(RbGpu* g, double* dev_out, uint64_t seed, uint32_t field, const double* lo, const double* hi,
                                   size_t first_index, size_t count, size_t ld, void* stream) {
     if (!g || !dev_out || !lo || !hi) return fail(RB_ERR_NULL, "NULL argument");
+    if (!g->peers.empty()) return fail(RB_ERR_UNSUPPORTED, kMultiDeviceOnly);
     if (ld == 0) ld = count;
     if (ld < count) return fail(RB_ERR_ARG, "ld < count");
     if (field >= 64) return fail(RB_ERR_ARG, "field must be < 64");
@@ -883,9 +1130,19 @@ extern "C" int multibody_gpu_fill(RbGpu* g, double* dev_out, uint64_t seed, uint
 
 extern "C" int multibody_gpu_sync(RbGpu* g) {
     if (!g) return fail(RB_ERR_NULL, "engine handle is NULL");
+    if (!g->peers.empty()) {
+        int rc = RB_OK; std::string err;
+        for (RbGpu* pg : g->peers) {
+            const int r = multibody_gpu_sync(pg);
+            if (r != RB_OK && (rc == RB_OK || rc == RB_ERR_NOT_SPD)) { rc = r; err = g_err; }
+        }
+        if (rc != RB_OK) g_err = err;
+        return rc;
+    }
     DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu_status);
     RB_CUDA(cudaDeviceSynchronize());      // device calls run on caller streams: wait for all of them
-    return fetch_status(g);
+    return fetch_status(g, 0);
 }
 
 extern "C" int multibody_gpu_status(RbGpu* g) { return multibody_gpu_sync(g); }
@@ -898,8 +1155,71 @@ extern "C" int multibody_host_alloc(void** out, size_t bytes) {
 }
 extern "C" void multibody_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+// Bare transfer ceiling of the path RB_MEM_HOST calls use (include/rigidbody.h).
+extern "C" int multibody_gpu_measure_copy_peak(RbGpu* g, size_t h2d_bytes, size_t d2h_bytes, int reps,
+                                               double* h2d_gbs, double* d2h_gbs) {
+    if (!g || !h2d_gbs || !d2h_gbs) return fail(RB_ERR_NULL, "NULL argument");
+    if (reps < 1) return fail(RB_ERR_ARG, "reps < 1");
+    std::vector<RbGpu*> devs = g->peers.empty() ? std::vector<RbGpu*>{g} : g->peers;
+    const size_t nd = devs.size();
+    const size_t cap = (size_t)256 << 20;                         // staged through buffers of at most 256 MiB per direction
+    struct Side { void* h = nullptr; void* d = nullptr; size_t buf = 0; };
+    std::vector<Side> up(nd), down(nd);
+    std::vector<int> rcs(nd, RB_OK); std::vector<std::string> errs(nd);
+    auto cleanup = [&] {
+        for (size_t i = 0; i < nd; ++i) {
+            DeviceGuard dg(devs[i]->device);
+            for (Side* sd : {&up[i], &down[i]}) { if (sd->h) cudaFreeHost(sd->h); if (sd->d) cudaFree(sd->d); }
+        }
+    };
+    for (size_t i = 0; i < nd; ++i) {
+        DeviceGuard dg(devs[i]->device);
+        const size_t per_up = h2d_bytes / nd, per_down = d2h_bytes / nd;
+        up[i].buf = std::max<size_t>(1, std::min(cap, per_up)); down[i].buf = std::max<size_t>(1, std::min(cap, per_down));
+        cudaError_t e = cudaMallocHost(&up[i].h, up[i].buf);
+        if (e == cudaSuccess) e = cudaMalloc(&up[i].d, up[i].buf);
+        if (e == cudaSuccess) e = cudaMallocHost(&down[i].h, down[i].buf);
+        if (e == cudaSuccess) e = cudaMalloc(&down[i].d, down[i].buf);
+        if (e != cudaSuccess) { cleanup(); return fail_cuda(e, "copy probe allocation"); }
+        memset(up[i].h, 1, up[i].buf);
+    }
+    auto pass = [&](size_t i) -> int {           // one device: both directions at once, as the pipeline runs them
+        RbGpu* pg = devs[i];
+        DeviceGuard dg(pg->device);
+        const size_t per_up = h2d_bytes / nd, per_down = d2h_bytes / nd;
+        for (size_t off = 0; off < per_up; off += up[i].buf)
+            RB_CUDA(cudaMemcpyAsync(up[i].d, up[i].h, std::min(up[i].buf, per_up - off), cudaMemcpyHostToDevice, pg->s_h2d));
+        for (size_t off = 0; off < per_down; off += down[i].buf)
+            RB_CUDA(cudaMemcpyAsync(down[i].h, down[i].d, std::min(down[i].buf, per_down - off), cudaMemcpyDeviceToHost, pg->s_d2h));
+        RB_CUDA(cudaStreamSynchronize(pg->s_h2d));
+        RB_CUDA(cudaStreamSynchronize(pg->s_d2h));
+        return RB_OK;
+    };
+    auto all = [&]() -> int {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < nd; ++i) th.emplace_back([&, i] { rcs[i] = pass(i); if (rcs[i] != RB_OK) errs[i] = g_err; });
+        for (auto& t : th) t.join();
+        for (size_t i = 0; i < nd; ++i) if (rcs[i] != RB_OK) return fail(rcs[i], errs[i]);
+        return RB_OK;
+    };
+    int rc = all();                               // warm-up
+    double best = 1e30;
+    for (int r = 0; r < reps && rc == RB_OK; ++r) {
+        const auto t0 = std::chrono::steady_clock::now();
+        rc = all();
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        best = std::min(best, sec);
+    }
+    cleanup();
+    if (rc != RB_OK) return rc;
+    *h2d_gbs = (double)(h2d_bytes / nd * nd) / best / 1e9;
+    *d2h_gbs = (double)(d2h_bytes / nd * nd) / best / 1e9;
+    return RB_OK;
+}
+
 extern "C" int multibody_gpu_measure_fp64_peak(RbGpu* g, int millis, double* tflops) {
     if (!g || !tflops) return fail(RB_ERR_NULL, "NULL argument");
+    if (!g->peers.empty()) g = g->peers[0];
     DeviceGuard dg(g->device);
     double* d_out = nullptr;
     RB_CUDA(cudaMalloc((void**)&d_out, sizeof(double)));

@@ -9,6 +9,7 @@
 // libnvrtc is dlopen'ed: if it is absent the engine falls back to the run-time-constant families.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -96,24 +97,41 @@ uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
     return h;
 }
 
+// Where compiled kernels are cached: $RIGIDBODY_B200_CACHE, else $HOME/.cache/rigidbody_b200.  No HOME -> no cache (a
+// predictable path under /tmp could be pre-planted by another user of the host).
 std::string cache_dir() {
     if (const char* e = getenv("RIGIDBODY_B200_CACHE")) return e;
     const char* home = getenv("HOME");
-    return std::string(home ? home : "/tmp") + "/.cache/rigidbody_b200";
+    return home && *home ? std::string(home) + "/.cache/rigidbody_b200" : std::string();
 }
 
-void mkdirs(const std::string& path) {
+// Creates the directory (0700) if needed and says whether it can be trusted: it must be a directory owned by this user
+// that neither group nor others can write to -- anything they could write here we would later load and launch.
+bool cache_dir_usable(const std::string& path) {
+    if (path.empty()) return false;
     for (size_t i = 1; i <= path.size(); ++i)
-        if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0755);
+        if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0700);
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return false;
+    return st.st_uid == geteuid() && (st.st_mode & (S_IWGRP | S_IWOTH)) == 0;
 }
 
-// Cache file: "RBJ1" | n_names | (len, bytes)* | cubin_len | cubin
-bool cache_read(const std::string& file, RbJitImage& img) {
+// Cache file: "RBJ2" | key_len u64 | key bytes | n_names u32 | (len u32, bytes)* | cubin_len u64 | cubin | fnv1a64(cubin).
+// `key` is the FULL key material (model table, options, kernel expressions, compiler version, a hash of the kernel
+// sources): the file name is only a 64-bit hash of it, so a read compares every byte of the key and the checksum of
+// the image and treats any mismatch (collision, stale file, bit rot, foreign file) as a miss.
+bool cache_read(const std::string& file, const std::string& key, RbJitImage& img) {
+    struct stat st;
+    if (stat(file.c_str(), &st) != 0 || !S_ISREG(st.st_mode) || st.st_uid != geteuid() || (st.st_mode & (S_IWGRP | S_IWOTH))) return false;
     std::ifstream f(file, std::ios::binary);
     if (!f) return false;
-    char magic[4]; uint32_t cnt = 0;
-    f.read(magic, 4); f.read((char*)&cnt, 4);
-    if (!f || memcmp(magic, "RBJ1", 4) != 0 || cnt != RB_JIT_KERNELS) return false;
+    char magic[4]; uint64_t klen = 0; uint32_t cnt = 0;
+    f.read(magic, 4); f.read((char*)&klen, 8);
+    if (!f || memcmp(magic, "RBJ2", 4) != 0 || klen != key.size()) return false;
+    std::string stored(klen, '\0'); f.read(&stored[0], (std::streamsize)klen);
+    if (!f || stored != key) return false;
+    f.read((char*)&cnt, 4);
+    if (!f || cnt != RB_JIT_KERNELS) return false;
     img.lowered.clear();
     for (uint32_t k = 0; k < cnt; ++k) {
         uint32_t len = 0; f.read((char*)&len, 4);
@@ -121,21 +139,30 @@ bool cache_read(const std::string& file, RbJitImage& img) {
         std::string s(len, '\0'); f.read(&s[0], len);
         img.lowered.push_back(s);
     }
-    uint64_t clen = 0; f.read((char*)&clen, 8);
+    uint64_t clen = 0, sum = 0; f.read((char*)&clen, 8);
     if (!f || clen == 0 || clen > (64u << 20)) return false;
     img.cubin.resize(clen); f.read(img.cubin.data(), (std::streamsize)clen);
-    return (bool)f;
+    f.read((char*)&sum, 8);
+    if (!f) return false;
+    return sum == fnv1a(0xcbf29ce484222325ULL, img.cubin.data(), img.cubin.size());
 }
 
-void cache_write(const std::string& file, const RbJitImage& img) {
+void cache_write(const std::string& file, const std::string& key, const RbJitImage& img) {
     const std::string tmp = file + ".tmp" + std::to_string((long)getpid());
     {
-        std::ofstream f(tmp, std::ios::binary);
-        if (!f) return;
+        const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+        if (fd < 0) return;
+        close(fd);
+        std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+        if (!f) { remove(tmp.c_str()); return; }
+        uint64_t klen = key.size();
         uint32_t cnt = (uint32_t)img.lowered.size();
-        f.write("RBJ1", 4); f.write((const char*)&cnt, 4);
+        f.write("RBJ2", 4); f.write((const char*)&klen, 8); f.write(key.data(), (std::streamsize)klen);
+        f.write((const char*)&cnt, 4);
         for (const auto& s : img.lowered) { uint32_t len = (uint32_t)s.size(); f.write((const char*)&len, 4); f.write(s.data(), len); }
         uint64_t clen = img.cubin.size(); f.write((const char*)&clen, 8); f.write(img.cubin.data(), (std::streamsize)clen);
+        const uint64_t sum = fnv1a(0xcbf29ce484222325ULL, img.cubin.data(), img.cubin.size());
+        f.write((const char*)&sum, 8);
         if (!f) { remove(tmp.c_str()); return; }
     }
     rename(tmp.c_str(), file.c_str());      // atomic publish: concurrent processes never see a partial file
@@ -160,10 +187,6 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     // cache key: everything that determines the cubin
     int vmaj = 0, vmin = 0;
     nv->Version(&vmaj, &vmin);
-    uint64_t h = 0xcbf29ce484222325ULL;
-    h = fnv1a(h, main_src.data(), main_src.size());
-    for (int k = 0; k < rb_jit_src_count; ++k) h = fnv1a(h, rb_jit_src_texts[k], strlen(rb_jit_src_texts[k]));
-    for (const char* o : kOptions) h = fnv1a(h, o, strlen(o));
     // tuning knob: extra whitespace-separated compiler options (e.g. "-DRB_MINB_FD=2"), part of the cache key
     std::vector<std::string> extra;
     if (const char* e = getenv("RIGIDBODY_B200_JIT_FLAGS")) {
@@ -173,12 +196,24 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
             else cur += *c;
         }
     }
-    for (const std::string& o : extra) h = fnv1a(h, o.data(), o.size());
-    h = fnv1a(h, &vmaj, sizeof vmaj); h = fnv1a(h, &vmin, sizeof vmin);
+    uint64_t hs = 0xcbf29ce484222325ULL, hs2 = 0x84222325cbf29ce4ULL;       // the embedded kernel sources, two independent hashes
+    for (int k = 0; k < rb_jit_src_count; ++k) {
+        hs = fnv1a(hs, rb_jit_src_texts[k], strlen(rb_jit_src_texts[k]));
+        hs2 = fnv1a(hs2 ^ (uint64_t)k, rb_jit_src_texts[k], strlen(rb_jit_src_texts[k]));
+    }
+    char num[96];
+    snprintf(num, sizeof num, "nvrtc %d.%d kernels %d sources %016llx%016llx\n", vmaj, vmin, RB_JIT_KERNELS,
+             (unsigned long long)hs, (unsigned long long)hs2);
+    std::string key = num;
+    for (const char* o : kOptions) { key += o; key += '\n'; }
+    for (const std::string& o : extra) { key += o; key += '\n'; }
+    for (int k = 0; k < RB_JIT_KERNELS; ++k) { key += exprs[k] ? exprs[k] : "-"; key += '\n'; }
+    key += main_src;                                                        // includes the model table, digit for digit
+    const uint64_t h = fnv1a(0xcbf29ce484222325ULL, key.data(), key.size());
     char keybuf[32]; snprintf(keybuf, sizeof keybuf, "%016llx", (unsigned long long)h);
     const std::string dir = cache_dir(), file = dir + "/" + keybuf + ".rbjit";
-    const bool use_cache = !(getenv("RIGIDBODY_B200_CACHE") && std::string(getenv("RIGIDBODY_B200_CACHE")).empty());
-    if (use_cache && cache_read(file, img)) { img.from_cache = true; log = "cache hit " + file; return RB_OK; }
+    const bool use_cache = cache_dir_usable(dir);      // empty $RIGIDBODY_B200_CACHE, no $HOME or an untrusted directory: no cache
+    if (use_cache && cache_read(file, key, img)) { img.from_cache = true; log = "cache hit " + file; return RB_OK; }
 
     nvrtcProgram prog = nullptr;
     if (nv->CreateProgram(&prog, main_src.c_str(), "rb_jit_model.cu", rb_jit_src_count, rb_jit_src_texts, rb_jit_src_names) != 0) {
@@ -206,7 +241,7 @@ int rb_jit_compile(const RbHostModel& m, RbJitImage& img, std::string& log) {
     nv->GetCUBIN(prog, img.cubin.data());
     nv->DestroyProgram(&prog);
     img.from_cache = false;
-    if (use_cache) { mkdirs(dir); cache_write(file, img); }
+    if (use_cache) cache_write(file, key, img);
     return RB_OK;
 }
 

@@ -339,7 +339,7 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const RB_R* __res
     RB_R J = RB_R(0);                                // running quadratic cost (sampling-based MPC), see RbQuadCost
     const size_t step = (size_t)N * ld;
     RB_R u[N];
-    rb_load<N>(tau, ld, s, u);
+    if (horizon > 0) rb_load<N>(tau, ld, s, u);            // horizon == 0: no step, tau is not read (may be NULL)
     for (int t = 0; t < horizon; ++t) {
         RB_R sn[N], cs[N], qdd[N], un[N];
         // prefetch the next step's torques so the load latency hides behind this step's arithmetic

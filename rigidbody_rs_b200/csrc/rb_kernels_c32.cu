@@ -10,14 +10,16 @@ const RbOps* rb_ops_chain32() {
 }
 
 const double* rb_chain32_table() {
-    static double flat[RB_MODEL_DOUBLES(32)];
-    static bool init = false;
-    if (!init) {
-        for (int i = 0; i < 32; ++i)
-            for (int k = 0; k < 24; ++k) flat[i * 24 + k] = TabChain32::T[i][k];
-        for (int k = 0; k < 3; ++k) flat[32 * 24 + k] = TabChain32::G[k];
-        for (int k = 0; k < 9; ++k) flat[32 * 24 + 3 + k] = TabChain32::TIP[k];
-        init = true;
-    }
-    return flat;
+    // filled once, thread-safely (function-local static initialisation): engines may be created from several threads
+    struct Flat {
+        double v[RB_MODEL_DOUBLES(32)];
+        Flat() {
+            for (int i = 0; i < 32; ++i)
+                for (int k = 0; k < 24; ++k) v[i * 24 + k] = TabChain32::T[i][k];
+            for (int k = 0; k < 3; ++k) v[32 * 24 + k] = TabChain32::G[k];
+            for (int k = 0; k < 9; ++k) v[32 * 24 + 3 + k] = TabChain32::TIP[k];
+        }
+    };
+    static const Flat flat;
+    return flat.v;
 }

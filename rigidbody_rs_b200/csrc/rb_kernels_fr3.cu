@@ -11,14 +11,16 @@ const RbOps* rb_ops_fr3() {
 }
 
 const double* rb_fr3_table() {
-    static double flat[RB_MODEL_DOUBLES(7)];
-    static bool init = false;
-    if (!init) {
-        for (int i = 0; i < 7; ++i)
-            for (int k = 0; k < 24; ++k) flat[i * 24 + k] = TabFr3::T[i][k];
-        for (int k = 0; k < 3; ++k) flat[7 * 24 + k] = TabFr3::G[k];
-        for (int k = 0; k < 9; ++k) flat[7 * 24 + 3 + k] = TabFr3::TIP[k];
-        init = true;
-    }
-    return flat;
+    // filled once, thread-safely (function-local static initialisation): engines may be created from several threads
+    struct Flat {
+        double v[RB_MODEL_DOUBLES(7)];
+        Flat() {
+            for (int i = 0; i < 7; ++i)
+                for (int k = 0; k < 24; ++k) v[i * 24 + k] = TabFr3::T[i][k];
+            for (int k = 0; k < 3; ++k) v[7 * 24 + k] = TabFr3::G[k];
+            for (int k = 0; k < 9; ++k) v[7 * 24 + 3 + k] = TabFr3::TIP[k];
+        }
+    };
+    static const Flat flat;
+    return flat.v;
 }

@@ -881,3 +881,111 @@ def test_cpp_example_runs(rb, tmp_path):
     r = subprocess.run([_build_example(tmp_path), FR3], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "fr3-specialised" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ multi-device engine
+def _two_devices():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_multi_device_host_batch_equals_single_device_bitwise(rb, mb_fr3, oracle_fr3, layout):
+    """multibody_gpu_new_multi: ONE handle, ONE RB_MEM_HOST call, the batch cut into contiguous slices over 2 devices
+    (the one-call shape of rigidbody_bindings/src/lib.rs:15-30).  Every result equals the single-device
+    engine's bit for bit; ragged sizes, padded leading dimension, sizes below the device count."""
+    _two_devices()
+    mm = rb.Multibody.from_urdf(FR3, devices=[0, 1])
+    assert mm.n_devices == 2 and mm.kernel_variant == "fr3-specialised" and mm.peer(1).device == 1
+    ax = 0 if layout == "soa" else 1
+    for B in (1, 2, 3, 1001, 70001):
+        q, dq, ddq, tau = _states(oracle_fr3, B, seed=0x5EED0011)
+        if layout == "aos":
+            q, dq, ddq, tau = (np.ascontiguousarray(x.T) for x in (q, dq, ddq, tau))
+        for name, args in (("rnea", (q, dq, ddq)), ("forward_dynamics", (q, dq, tau)), ("rnea_fd", (q, dq, ddq, tau)),
+                           ("crba", (q,)), ("jac", (q,)), ("fwd_kin", (q,)), ("rnea_derivatives", (q, dq, ddq)),
+                           ("fd_derivatives", (q, dq, tau))):
+            a = getattr(mm, name)(*args, layout=layout)
+            b = getattr(mb_fr3, name)(*args, layout=layout)
+            if B == 1 and isinstance(a, tuple):
+                for x, y in zip(a, b):
+                    np.testing.assert_array_equal(x, y, err_msg=f"{name} B={B}")
+            else:
+                np.testing.assert_array_equal(a, b, err_msg=f"{name} B={B}")
+    # against the oracle, once
+    q, dq, ddq, tau = _states(oracle_fr3, 4097, seed=0x5EED0012)
+    assert state_err(mm.rnea(q, dq, ddq), oracle_fr3.rnea_batch(q, dq, ddq), 0).max() < TOL
+    # a padded leading dimension through the raw C ABI: rows of 5000 doubles, 4097 states
+    from rigidbody_rs_b200 import _lib
+    ld = 5000
+    bufs = [np.full((7, ld), np.nan) for _ in range(4)]
+    for b_, x in zip(bufs, (q, dq, ddq)):
+        b_[:, :4097] = x
+    rc = _lib.lib.multibody_rnea_batch(mm._h, *[C.c_void_p(b_.ctypes.data) for b_ in bufs], 4097, ld, 0, 0, None)
+    assert rc == 0, _lib.lib.multibody_last_error()
+    np.testing.assert_array_equal(bufs[3][:, :4097], mb_fr3.rnea(q, dq, ddq))
+    assert np.isnan(bufs[3][:, 4097:]).all()
+    mm.close()
+
+
+def test_multi_device_rollout_and_status(rb, mb_fr3, oracle_fr3):
+    """Rollouts (SoA and AoS: the AoS trajectory arrays are strided per slice) and the fused cost over 2 devices equal
+    the single-device results bit for bit; device pointers are refused with RB_ERR_UNSUPPORTED; a non-SPD state in ONE
+    device's slice is reported by the call; launch counts add up."""
+    import torch
+    _two_devices()
+    mm = rb.Multibody.from_urdf(FR3, devices=[0, 1])
+    B, H, dt = 301, 12, 1e-3
+    q, dq, _, _ = _states(oracle_fr3, B, seed=0x5EED0003)
+    lim = oracle_fr3.model
+    tau = np.stack([oracle_fr3.fill(0x5EED0003, 4 + t % 32, -lim.effort, lim.effort, t * B, B) for t in range(H)])
+    w = np.linspace(0.5, 2.0, 7)
+    l0 = mm.launch_count
+    for x, y in zip(mm.rollout(q, dq, tau, dt, final=True), mb_fr3.rollout(q, dq, tau, dt, final=True)):
+        np.testing.assert_array_equal(x, y)
+    assert mm.launch_count - l0 == 2
+    qa, dqa, ta = np.ascontiguousarray(q.T), np.ascontiguousarray(dq.T), np.ascontiguousarray(tau.transpose(0, 2, 1))
+    for x, y in zip(mm.rollout(qa, dqa, ta, dt, layout="aos", final=True), mb_fr3.rollout(qa, dqa, ta, dt, layout="aos", final=True)):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(mm.rollout_cost(q, dq, tau, dt, w_q=w, w_tau=1e-3 * w, w_q_final=3 * w),
+                                  mb_fr3.rollout_cost(q, dq, tau, dt, w_q=w, w_tau=1e-3 * w, w_q_final=3 * w))
+    with pytest.raises(rb.RigidBodyError) as ei:
+        mm.rnea(*(torch.zeros((7, 8), dtype=torch.float64, device="cuda:0") for _ in range(3)))
+    assert ei.value.code == -6
+    mm.close()
+    # a chain whose mass matrix is indefinite: the error raised on a worker thread reaches the caller, and the next call is clean
+    n = 2
+    R = np.tile(np.eye(3), (n, 1, 1)); t = np.zeros((n, 3)); t[1] = [0.1, 0, 0]
+    d = rb._lib.RbChainDesc()
+    keep = [np.ascontiguousarray(x) for x in (R, t, np.ones(n), np.zeros((n, 3)), np.tile(np.diag([0.1, 0.1, -5.0]), (n, 1, 1)))]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    d.n_joints = n
+    d.parent_rot, d.parent_trans, d.mass, d.com, d.inertia_com = (dp(x) for x in keep)
+    d.gravity[:] = [0.0, 0.0, 9.81]
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 1)
+    assert rb._lib.lib.multibody_gpu_new_multi(C.byref(d), devs, 2, C.byref(h)) == 0, rb._lib.lib.multibody_last_error()
+    bad = rb.Multibody(h)
+    z = np.zeros((2, 64))
+    with pytest.raises(rb.NotPositiveDefinite):
+        bad.forward_dynamics(z, z, z)
+    assert bad.rnea(z, z, z).shape == (2, 64)
+    bad.close()
+
+
+def test_multi_device_argument_checks(rb):
+    from rigidbody_rs_b200 import _lib
+    h = C.c_void_p()
+    one = (C.c_int * 1)(0)
+    assert _lib.lib.multibody_gpu_new_multi_from_urdf(FR3.encode(), one, 1, C.byref(h)) == 0
+    g = rb.Multibody(h)
+    assert g.n_devices == 1 and g.peer(0).device == 0            # n_dev = 1 is an ordinary engine
+    g.close()
+    twice = (C.c_int * 2)(0, 0)
+    assert _lib.lib.multibody_gpu_new_multi_from_urdf(FR3.encode(), twice, 2, C.byref(h)) == _lib.RB_ERR_ARG
+    assert _lib.lib.multibody_gpu_new_multi_from_urdf(FR3.encode(), None, 2, C.byref(h)) == _lib.RB_ERR_NULL
+    far = (C.c_int * 2)(0, 63)
+    assert _lib.lib.multibody_gpu_new_multi_from_urdf(FR3.encode(), far, 2, C.byref(h)) == _lib.RB_ERR_ARG
+    up, down = rb.Multibody.from_urdf(FR3).copy_peak(64 << 20, 32 << 20)
+    assert up > 1.0 and down > 0.5

@@ -18,6 +18,8 @@ HEADER = os.path.join(ROOT, "include", "rigidbody.h")
 def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    # declarations the Rust bridge crate provides (not this library): #ifdef RIGIDBODY_HAVE_RUST_BRIDGE ... #endif
+    src = re.sub(r"#ifdef RIGIDBODY_HAVE_RUST_BRIDGE.*?#endif", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(multibody_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -31,7 +33,8 @@ def test_library_exports_every_header_symbol(rb):
 
 
 def test_header_is_valid_c_and_cpp(tmp_path):
-    (tmp_path / "t.c").write_text('#include "rigidbody.h"\nint main(void){ RbChainDesc d; (void)d; return RB_OK; }\n')
+    # with and without the Rust bridge declaration
+    (tmp_path / "t.c").write_text('#define RIGIDBODY_HAVE_RUST_BRIDGE 1\n#include "rigidbody.h"\nint main(void){ RbChainDesc d; (void)d; (void)multibody_gpu_from_rust; return RB_OK; }\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
                     "-c", str(tmp_path / "t.c"), "-o", str(tmp_path / "t.o")], check=True)
     (tmp_path / "t.cpp").write_text('#include "rigidbody.h"\nint main(){ RbChainDesc d{}; (void)d; return RB_OK; }\n')
@@ -263,6 +266,57 @@ def test_axis_rebasing_on_the_host(rb, tmp_path):
     _, Rz_, tz_, *_ = _host_model(_lib.lib, path)
     np.testing.assert_allclose(Rz_, zz.Rp, rtol=0, atol=1e-15)
     np.testing.assert_array_equal(tz_, t)
+
+
+def test_jit_cache_is_verified_not_trusted(rb, tmp_path, monkeypatch):
+    """The on-disk kernel cache: a file is used only if its stored key material equals the request byte for byte and the
+    image checksum holds; a flipped bit, a truncated file or a file planted under another chain's name is a miss (and is
+    recompiled); a cache directory that group/others can write to is not used at all; no $HOME means no cache."""
+    from rigidbody_rs_b200 import _lib
+    cache = tmp_path / "cache"
+    monkeypatch.setenv("RIGIDBODY_B200_CACHE", str(cache))
+    log = C.create_string_buffer(8192)
+    def desc(seed):
+        keep = [np.ascontiguousarray(x) for x in _random_chain(2, seed)]
+        d = _lib.RbChainDesc()
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        d.n_joints = 2
+        d.parent_rot, d.parent_trans, d.mass, d.com, d.inertia_com = (dp(x) for x in keep)
+        d.gravity[:] = [0.0, 0.0, 9.81]
+        return d, keep
+    d, keep = desc(11)
+    pre = lambda: _lib.lib.multibody_jit_precompile(C.byref(d), None, log, 8192)
+    assert pre() == 0 and b"cache hit" not in log.value
+    assert (os.stat(cache).st_mode & 0o777) == 0o700
+    (name,) = os.listdir(cache)
+    path = cache / name
+    assert (os.stat(path).st_mode & 0o777) == 0o600
+    assert pre() == 0 and b"cache hit" in log.value
+    good = path.read_bytes()
+    # 1. bit rot inside the image
+    bad = bytearray(good); bad[len(bad) // 2] ^= 0x10
+    path.write_bytes(bytes(bad))
+    assert pre() == 0 and b"cache hit" not in log.value          # detected, recompiled, rewritten
+    assert path.read_bytes() == good
+    # 2. truncation
+    path.write_bytes(good[: len(good) - 100])
+    assert pre() == 0 and b"cache hit" not in log.value
+    # 3. another chain's (valid) file under this chain's name: the stored key material differs
+    d2, keep2 = desc(12)
+    assert _lib.lib.multibody_jit_precompile(C.byref(d2), None, log, 8192) == 0
+    other = [n for n in os.listdir(cache) if n != name][0]
+    path.write_bytes((cache / other).read_bytes())
+    assert pre() == 0 and b"cache hit" not in log.value
+    assert pre() == 0 and b"cache hit" in log.value
+    # 4. a directory others can write to is not trusted: nothing is read from it or written to it
+    loose = tmp_path / "loose"; loose.mkdir(); os.chmod(loose, 0o777)
+    monkeypatch.setenv("RIGIDBODY_B200_CACHE", str(loose))
+    assert pre() == 0 and b"cache hit" not in log.value
+    assert os.listdir(loose) == []
+    # 5. no cache directory configured and no HOME: compile every time, write nowhere
+    monkeypatch.delenv("RIGIDBODY_B200_CACHE")
+    monkeypatch.delenv("HOME", raising=False)
+    assert pre() == 0 and b"cache hit" not in log.value
 
 
 def test_jit_precompile_without_gpu(rb, tmp_path, monkeypatch):
