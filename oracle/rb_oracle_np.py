@@ -260,6 +260,37 @@ class ChainNP:
 def rnea_mp(model, q, dq, ddq, dps=40):
     """mpmath evaluation of the matrix-form RNEA for ONE state at `dps` digits (error bound for the fp64 paths).
     URDF decimal strings are taken at their fp64 values, as the reference does."""
+    return np.array([float(x) for x in _rnea_mp(model, q, dq, ddq, dps)])
+
+
+def fd_mp(model, q, dq, tau, dps=40, return_cond=False):
+    """mpmath evaluation of forward dynamics for ONE state: the composition SURVEY.md 3.3 defines,
+    qdd = H(q)^-1 (tau - rnea(q, dq, 0)), with H built column by column from the same `dps`-digit recursion
+    (H e_j = rnea(q, 0, e_j) - rnea(q, 0, 0), multibody.rs:111-153) and the system solved at `dps` digits: the value every
+    fp64 path (oracle LL^T, CUDA LDL^T, half-warp elimination) is an approximation OF.  With return_cond also the
+    2-norm condition number of H (fp64 is plenty for that)."""
+    import mpmath as mp
+    mp.mp.dps = dps
+    n = model.n
+    zero = np.zeros(n)
+    g = _rnea_mp(model, q, zero, zero, dps)
+    H = mp.matrix(n, n)
+    for j in range(n):
+        e = np.zeros(n); e[j] = 1.0
+        col = _rnea_mp(model, q, zero, e, dps)
+        for i in range(n):
+            H[i, j] = col[i] - g[i]
+    bias = _rnea_mp(model, q, dq, zero, dps)
+    b = mp.matrix([mp.mpf(float(tau[i])) - bias[i] for i in range(n)])
+    x = mp.lu_solve(H, b)
+    out = np.array([float(v) for v in x])
+    if return_cond:
+        Hf = np.array([[float(H[i, j]) for j in range(n)] for i in range(n)])
+        return out, float(np.linalg.cond(0.5 * (Hf + Hf.T)))
+    return out
+
+
+def _rnea_mp(model, q, dq, ddq, dps=40):
     import mpmath as mp
     mp.mp.dps = dps
     n = model.n
@@ -314,4 +345,4 @@ def rnea_mp(model, q, dq, ddq, dps=40):
             Rl = R[i] * fl[i]
             fl[i - 1] = fl[i - 1] + Rl
             fr[i - 1] = fr[i - 1] + R[i] * fr[i] + cross(t[i], Rl)
-    return np.array([float(x) for x in tau])
+    return tau

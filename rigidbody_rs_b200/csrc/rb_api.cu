@@ -620,9 +620,13 @@ int gpu_create_multi(const RbHostModel& model, const int* devices, int n_dev, Rb
     *out = nullptr;
     if (!devices) return fail(RB_ERR_NULL, "devices is NULL");
     if (n_dev < 1 || n_dev > 64) return fail(RB_ERR_ARG, "n_dev must be 1..64");
-    for (int i = 0; i < n_dev; ++i)
-        for (int k = 0; k < i; ++k)
-            if (devices[i] == devices[k]) return fail(RB_ERR_ARG, "device listed twice");
+    // test hook: RIGIDBODY_B200_ALLOW_DUPLICATE_DEVICES=1 lets a one-GPU box exercise the slicing / worker-thread path
+    // (two engines on the same device); pointless in production, hence refused by default
+    const char* dup = getenv("RIGIDBODY_B200_ALLOW_DUPLICATE_DEVICES");
+    if (!(dup && dup[0] == '1'))
+        for (int i = 0; i < n_dev; ++i)
+            for (int k = 0; k < i; ++k)
+                if (devices[i] == devices[k]) return fail(RB_ERR_ARG, "device listed twice");
     if (n_dev == 1) return gpu_create(model, devices[0], out);
     RbGpu* g = new (std::nothrow) RbGpu();
     if (!g) return fail(RB_ERR_CUDA, "out of host memory");

@@ -111,6 +111,28 @@ def test_mpmath_bounds_rounding_error(oracle_fr3, np_fr3):
         assert np.abs(np_fr3.rnea(q, dq, ddq)[0] - t).max() / s < 1e-12
 
 
+def test_mpmath_forward_dynamics_truth(oracle_fr3, oracle_chain32, np_fr3):
+    """The forward-dynamics truth (fd_mp: H column by column from the 40-digit recursion, 40-digit solve) against both
+    fp64 restatements: the C oracle's LL^T and the twin's numpy solve sit within 8 cond(H) eps of it (the bar of
+    conftest.fd_bound), and the truth itself satisfies rnea(q, dq, qdd) = tau to 1e-25."""
+    from conftest import fd_bound
+    from oracle.rb_oracle_np import _rnea_mp, fd_mp
+    rng = np.random.default_rng(5)
+    for o, K, lim in ((oracle_fr3, 4, 80.0), (oracle_chain32, 1, 50.0)):
+        n = o.model.n
+        for _ in range(K):
+            q, dq, tau = rng.uniform(-np.pi, np.pi, n), rng.uniform(-2, 2, n), rng.uniform(-lim, lim, n)
+            x, cond = fd_mp(o.model, q, dq, tau, return_cond=True)
+            err = np.abs(o.forward_dynamics(q, dq, tau) - x).max() / max(1.0, np.abs(x).max())
+            assert err <= fd_bound(cond) and err < 1e-11, (n, err, cond)
+            if n == 7:
+                errn = np.abs(np_fr3.forward_dynamics(q, dq, tau)[0] - x).max() / max(1.0, np.abs(x).max())
+                assert errn <= fd_bound(cond), (errn, cond)
+            back = _rnea_mp(o.model, q, dq, x, 40)          # residual of the (fp64-rounded) truth: rounding of x only
+            res = max(abs(float(back[i]) - tau[i]) for i in range(n))
+            assert res < 1e-9 * max(1.0, np.abs(tau).max())
+
+
 def test_reference_convention_tests_restated(oracle_fr3):
     """rigidbody/src/spatial.rs:283-382 restated against the oracle's building blocks, with the reference's own
     epsilons and the same asserts it leaves enabled."""
