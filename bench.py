@@ -9,6 +9,11 @@
 One step = one batched RNEA pass (BASELINE.json configs[1]) + one batched forward-dynamics pass (configs[2]) over
 2^24 synthetic FR3 states per GPU, device-resident SoA, sampled on the device by the counter-based generator of
 SURVEY.md 8d.  Each GPU owns its own 2^24 states (weak scaling, no data-path collective).  Prints ONE JSON line.
+
+The same line carries, under `configs`, short legs of the other BASELINE.json configurations so that every run the
+driver makes (1, 2, 4, 8 GPUs) records them: `fused_rnea_fd` (the one-pass kernel behind multibody_rnea_fd_batch),
+`rollout` (configs[3]: 65 536 trajectories x 64 steps split over the ranks, strong scaling) and `chain32` (configs[4]:
+2^26 states of the 32-joint chain split over the ranks, strong scaling), each with its own roofline object.
 """
 from __future__ import annotations
 
@@ -42,21 +47,30 @@ FP64_INSTR = {k: FP64_STATIC[k] - FP64_FALLBACK[k] for k in FP64_STATIC}
 FP64_LANES_PER_SM = 64
 
 
-def profiled_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture."""
+def profiled(kernel):
+    """What the committed `ncu --set full` capture of `kernel` says about ONE launch: DRAM bytes moved and (captures of
+    round 2 on) executed FP64 instructions by opcode.  The last match wins: the capture named *final* if there is one."""
     best = None
     pdir = os.path.join(ROOT, "profiles")
     names = sorted(os.listdir(pdir), key=lambda nm: ("final" in nm, nm)) if os.path.isdir(pdir) else []
-    for name in names:                                   # the last match wins: the capture named *final* if there is one
+
+    def num(v):
+        x, unit = (v.split() + [""])[:2]
+        return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "inst": 1.0, "": 1.0}.get(unit, 1.0)
+
+    for name in names:
         if not name.endswith("ncu_full_summary.json"):
             continue
         with open(os.path.join(pdir, name)) as f:
             for row in json.load(f):
                 if kernel in row.get("kernel", "") and "dram__bytes_read.sum" in row:
-                    def gb(v):
-                        num, unit = v.split()[:2]
-                        return float(num) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
-                    best = {"bytes": gb(row["dram__bytes_read.sum"]) + gb(row["dram__bytes_write.sum"]), "source": "profiles/" + name}
+                    d = {"bytes": num(row["dram__bytes_read.sum"]) + num(row["dram__bytes_write.sum"]), "source": "profiles/" + name,
+                         "grid": num(row.get("launch__grid_size", "0")), "block": num(row.get("launch__block_size", "0"))}
+                    ops = [row.get(f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum") for o in ("dfma", "dadd", "dmul")]
+                    if all(ops):
+                        d["fp64_thread_instr"] = sum(num(o) for o in ops)
+                        d["fp64_thread_flops"] = 2 * num(ops[0]) + num(ops[1]) + num(ops[2])
+                    best = d
     return best
 
 
@@ -134,14 +148,34 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle; test infrastructure)
-def cpu_arm(sample_states, steps, warmup):
+def host_threads():
+    # torchrun exports OMP_NUM_THREADS=1: size the team from the CPUs this process may run on instead
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_single_state(orc, calls=1_000_000):
+    """BASELINE.json configs[0]: the single-state RNEA of the reference path on ONE host core, at the reference's two
+    inputs -- q = dq = ddq = 0 (`bench_rnea`, multibody.rs:204-209) and the state of rigidbody_bindings/main.cpp:103-105 --
+    `calls` evaluations each after a 10 % warm-up (one C loop over a batch of identical states: no Python per call)."""
+    states = {"zero_state": (np.zeros(7), np.zeros(7), np.zeros(7)),
+              "main_cpp_state": (np.array([0, 0, 1, 0, 1, 0, 0.0]), np.array([0, 0, 0, 0, 1, 0, 0.0]), np.array([1, 0, 0, 0, 0, 1, 0.0]))}
+    out = {"calls": calls}
+    for name, (q, dq, ddq) in states.items():
+        Q, DQ, DDQ = (np.ascontiguousarray(np.repeat(x[:, None], calls, 1)) for x in (q, dq, ddq))
+        orc.rnea_batch(Q[:, : calls // 10], DQ[:, : calls // 10], DDQ[:, : calls // 10], threads=1)
+        t0 = time.perf_counter()
+        orc.rnea_batch(Q, DQ, DDQ, threads=1)
+        out[name + "_ns"] = (time.perf_counter() - t0) / calls * 1e9
+    return out
+
+
+def cpu_arm(sample_states, steps, warmup, single_calls=1_000_000):
     """Times oracle/rb_oracle.c (reference-shaped C restatement; the Rust crate cannot be built in this image),
     OpenMP static chunks over all host threads: RNEA + FD over `sample_states` states per step."""
     from oracle.rb_oracle import Oracle
     orc = Oracle.from_urdf(os.path.join(ROOT, "assets", "fr3.urdf"), fast=True)   # rebuilt -march=native on this host
     m = orc.model
-    # torchrun exports OMP_NUM_THREADS=1: size the team from the CPUs this process may run on instead
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = host_threads()
     if sample_states is None:       # calibrate to ~4 s of wall time per step
         S0 = 1 << 14
         q = orc.fill(SEED_RNEA, 0, m.lower, m.upper, 0, S0); dq = orc.fill(SEED_RNEA, 1, -m.velocity, m.velocity, 0, S0)
@@ -162,13 +196,9 @@ def cpu_arm(sample_states, steps, warmup):
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    # BASELINE.json configs[0]: one state, one core (the reference's bench_rnea input, multibody.rs:204-209)
-    z = np.zeros((7, 1)); reps = 20000
-    t0 = time.perf_counter()
-    for _ in range(3):
-        orc.rnea_batch(np.repeat(z, reps, 1), np.repeat(z, reps, 1), np.repeat(z, reps, 1), threads=1)
-    single_ns = (time.perf_counter() - t0) / (3 * reps) * 1e9
-    return {"value": 2.0 * S / sec, "unit": UNIT, "cores": threads, "kind": "port", "single_state_rnea_ns_one_core": single_ns,
+    single = cpu_single_state(orc, single_calls)
+    return {"value": 2.0 * S / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "single_state_rnea_ns_one_core": single["zero_state_ns"], "single_state": single,
             "sample": f"{S} FR3 states per step (RNEA + FD each), {steps} timed steps, OpenMP static over {threads} threads, "
                       f"oracle/rb_oracle.c -O3 -march=native"}, sec, S
 
@@ -181,7 +211,7 @@ def run_reference(args, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "fr3_rnea+fd", "states_per_step": S, "layout": "soa",
-                       "note": "CPU port of the reference path (oracle/); the Rust crate cannot be built here"},
+                       "note": "CPU port of the reference path (oracle/); the Rust crate cannot be built here (no cargo; probed)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -189,11 +219,34 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def fp64_roofline(kernel, ms, units, instr_per_unit, flops_executed_per_unit, alg_flops_per_unit, bytes_per_unit,
+                  fp64_peak, peak_note, hbm_peak, hbm_src, traffic=None, traffic_src=None, instr_src="static SASS count"):
+    """The roofline object of one FP64-pipe-bound kernel.  `frac` is the share of the FP64 pipe's issue slots the launch
+    used: every FP64 instruction (DFMA, DADD, DMUL, DSETP...) occupies the pipe like a DFMA, so executed instructions x 2
+    (FMA-equivalent flops) per second over the DFMA rate measured on this GPU in this run.  The SURVEY 8d flop count of
+    the general algorithm is kept as `algorithmic_frac` (> the executed figure where compile-time constants delete
+    work) and the HBM side sits beside it."""
+    sec = ms * 1e-3
+    fma_eq = 2.0 * instr_per_unit * units / sec / 1e12
+    d = {"kernel": kernel, "bound": "fp64", "achieved": fma_eq, "peak": fp64_peak, "unit": "TFLOP/s (FMA-equivalent: 2 x FP64 instructions executed)",
+         "frac": fma_eq / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
+         "fp64_instr_per_unit": instr_per_unit, "fp64_instr_source": instr_src,
+         "executed_tflops": flops_executed_per_unit * units / sec / 1e12 if flops_executed_per_unit else None,
+         "algorithmic_flops_per_unit": alg_flops_per_unit, "algorithmic_tflops": alg_flops_per_unit * units / sec / 1e12,
+         "algorithmic_frac": alg_flops_per_unit * units / sec / 1e12 / fp64_peak,
+         "units_per_s": units / sec, "ms": ms, "peak_source": peak_note}
+    if bytes_per_unit:
+        gbs = bytes_per_unit * units / sec / 1e9
+        d["hbm"] = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "bytes_per_unit": bytes_per_unit,
+                    "peak_source": hbm_src}
+    return d
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import rigidbody_rs_b200 as rb
-    from rigidbody_rs_b200.shard import max_over_ranks, sum_over_ranks
+    from rigidbody_rs_b200.shard import max_over_ranks, shard_bounds, sum_over_ranks
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -215,12 +268,23 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    def timed(fn, steps, warmup):
+        """max-over-ranks device time per call of fn (CUDA events on the launching stream, barrier on both sides)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+
+    # ------------------------------------------------------------------ headline: RNEA launch + FD launch, K steps
+    for _ in range(args.warmup):
         mb.rnea(q, dq, ddq, out=tau)
         mb.forward_dynamics(q, dq, tau_in, out=qdd)
-
-    for _ in range(args.warmup):
-        step()
     K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     sampler = ClockSampler(local_rank); sampler.start()
@@ -243,15 +307,43 @@ def run_ours(args, rank, local_rank, world):
     # FP64 roofline denominator: DFMA probe on the same GPU in the same run, run for about as long as the timed
     # region (a burst of a few ms keeps 1965 MHz; seconds of FP64 work pull ~1 kW and settle near 1.7 GHz under
     # sw_power_cap), so burst numbers are divided by a burst peak and sustained numbers by a sustained peak
-    probe_ms = int(min(2000.0, max(100.0, total_ms)))
+    probe_ms = int(min(2000.0, max(10.0, total_ms)))
     fp64_peak = mb.fp64_peak_tflops(probe_ms)
+    peak_note = f"DFMA probe (multibody_gpu_measure_fp64_peak) on this GPU in this run, {probe_ms} ms; nominal 148 x 64 x 2 x 1.965 GHz = 37.2"
     ms_step = max_over_ranks(total_ms / K, dev)
     ms_rnea = max_over_ranks(sum(e[0].elapsed_time(e[1]) for e in ev) / K, dev)
     ms_fd = max_over_ranks(sum(e[1].elapsed_time(e[2]) for e in ev) / K, dev)
     units = sum_over_ranks(2.0 * B, dev)               # evaluations all ranks processed per step
     value = units / (ms_step * 1e-3)
+    hbm_peak, hbm_src = measured_peaks()
+    fr3 = mb.kernel_variant == "fr3-specialised"
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    def roof(kernel, alg_flops, ms):
+        pr = profiled(kernel)
+        full = B == STATES_PER_GPU and pr is not None
+        instr, src, fl = FP64_INSTR[kernel], "static SASS count minus the out-of-range sin/cos fallback (tools/sass_count.sh)", None
+        if full and "fp64_thread_instr" in pr:
+            instr, src, fl = pr["fp64_thread_instr"] / B, "ncu smsp__sass_thread_inst_executed_op_d{fma,add,mul} (" + pr["source"] + ")", pr["fp64_thread_flops"] / B
+        return fp64_roofline(kernel, ms, float(B), instr if fr3 else float("nan"), fl, alg_flops, BYTES_PER_EVAL, fp64_peak, peak_note,
+                             hbm_peak, hbm_src, pr["bytes"] if full else None, pr["source"] if full else None, src)
+
+    # ------------------------------------------------------------------ configs.fused_rnea_fd: one pass, both results
+    both = torch.empty((2 * n, B), dtype=torch.float64, device=dev)
+    ms_fused = timed(lambda: mb.rnea_fd(q, dq, ddq, tau_in, out=both), K, args.warmup)
+    fused_ok = bool(torch.equal(both[n:, :65536], qdd[:, :65536])) and \
+        float(((both[:n, :65536] - tau[:, :65536]).abs().amax(0) / tau[:, :65536].abs().amax(0).clamp_min(1.0)).max()) < 1e-12
+    pr = profiled("rb_rnea_fd_kernel")
+    fused_instr = pr["fp64_thread_instr"] / STATES_PER_GPU if pr and "fp64_thread_instr" in pr else 1348.0 - 126.0
+    cfg_fused = {"value": units / (ms_fused * 1e-3), "unit": UNIT, "ms_per_step": ms_fused, "scaling": "weak",
+                 "step": "1 rb_rnea_fd_kernel launch: tau = rnea(q, dq, ddq) AND qdd = fd(q, dq, tau_in) of the same 2^24 states "
+                         "(shared sin/cos, bias recursion and mass matrix; tau = bias + H ddq)",
+                 "matches_separate_kernels": fused_ok,
+                 "roofline": fp64_roofline("rb_rnea_fd_kernel", ms_fused, float(B), fused_instr, pr.get("fp64_thread_flops", 0) / STATES_PER_GPU if pr else None,
+                                           RNEA_FLOPS + FD_FLOPS, 336.0, fp64_peak, peak_note, hbm_peak, hbm_src,
+                                           pr["bytes"] if pr and B == STATES_PER_GPU else None, pr["source"] if pr else None)}
+    del both
+
+    # ------------------------------------------------------------------ end to end through the C ABI with HOST buffers
     Be = args.e2e_states
     hq, hdq, hddq, htau_in = (rb.host_empty((n, Be)) for _ in range(4))
     htau, hqdd = rb.host_empty((n, Be)), rb.host_empty((n, Be))
@@ -266,8 +358,8 @@ def run_ours(args, rank, local_rank, world):
         mb.forward_dynamics(hq, hdq, htau_in, out=hqdd)
     torch.cuda.synchronize()
     sep_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, dev)
-    # the same step through the one-call entry point (multibody_rnea_fd_batch): identical kernels and results, but q and
-    # dq cross PCIe once instead of twice (4 input arrays instead of 6) -- the bus is what bounds this number
+    # the same step through the one-call entry point (multibody_rnea_fd_batch): q and dq cross PCIe once instead of
+    # twice (4 input arrays instead of 6) and the fused kernel serves every chunk -- the bus is what bounds this number
     hout = rb.host_empty((2 * n, Be))
     mb.rnea_fd(hq, hdq, hddq, htau_in, out=hout)
     barrier()
@@ -277,9 +369,60 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, dev)
     e2e_units = sum_over_ranks(2.0 * Be, dev)
-    # the host results equal the device-resident ones bit for bit (same kernels, same inputs)
-    same = bool(np.array_equal(htau[:, :4096], tau[:, :4096].cpu().numpy())) and bool(np.array_equal(hout[:n], htau)) \
-        and bool(np.array_equal(hout[n:], hqdd))
+    up_b, down_b = 4 * n * Be * 8, 2 * n * Be * 8
+    # the host results equal the device-resident ones: qdd bit for bit, tau to rounding (fused kernel)
+    same = bool(np.array_equal(htau[:, :4096], tau[:, :4096].cpu().numpy())) and bool(np.array_equal(hout[n:], hqdd)) \
+        and float(np.abs(hout[:n] - htau).max() / max(1.0, np.abs(htau).max())) < 1e-12
+    # the ceiling: the same bytes, both directions at once, pinned memory, no kernel -- every rank at the same time
+    barrier()
+    cu, cd = mb.copy_peak(up_b, down_b, 2)
+    barrier()
+    ceil_ms = max_over_ranks(up_b / cu / 1e6, dev)
+    e2e = {"value": e2e_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": up_b, "d2h_bytes_per_step": down_b,
+           "states_per_gpu": Be, "steps": e2e_steps, "ms_per_step": e2e_ms,
+           "h2d_GBs": world * up_b / e2e_ms / 1e6, "d2h_GBs": world * down_b / e2e_ms / 1e6,
+           "copy_ceiling": {"h2d_GBs": world * up_b / ceil_ms / 1e6, "d2h_GBs": world * down_b / ceil_ms / 1e6, "ms_per_step": ceil_ms,
+                            "evals_per_s": e2e_units / (ceil_ms * 1e-3),
+                            "how": "multibody_gpu_measure_copy_peak: the same bytes per direction from/to pinned host memory, both directions at "
+                                   "once, no kernel, all ranks at the same time (max over ranks)"},
+           "frac_of_copy_ceiling": ceil_ms / e2e_ms,
+           "api": "Multibody.rnea_fd on pinned numpy arrays -> multibody_rnea_fd_batch(RB_MEM_HOST), one process per GPU: q, dq, ddq, tau_in up, tau and qdd down",
+           "matches_device_path": same,
+           "separate_calls": {"value": e2e_units / (sep_ms * 1e-3), "ms_per_step": sep_ms, "h2d_bytes_per_step": 6 * n * Be * 8,
+                              "api": "Multibody.rnea + Multibody.forward_dynamics -> multibody_{rnea,forward_dynamics}_batch(RB_MEM_HOST)"}}
+    for h in (hq, hdq, hddq, htau_in, htau, hqdd, hout):
+        rb.host_free(h)
+    del hq, hdq, hddq, htau_in, htau, hqdd, hout
+
+    # one process, one handle, all N GPUs: multibody_gpu_new_multi cuts ONE host batch into N contiguous slices (rank 0
+    # drives it while the other ranks wait at the barrier); its own bare-copy ceiling beside it
+    if world > 1:
+        barrier()
+        if rank == 0:
+            Bm = (1 << 22) * world
+            mm = rb.Multibody.from_urdf(os.path.join(ROOT, "assets", "fr3.urdf"), devices=list(range(world)))
+            mq, mdq, mddq, mtin = (rb.host_empty((n, Bm)) for _ in range(4))
+            mout = rb.host_empty((2 * n, Bm))
+            rng = np.random.default_rng(0)
+            for h, (lo_, hi_) in zip((mq, mdq, mddq, mtin), ((lim["lower"], lim["upper"]), (-lim["velocity"], lim["velocity"]), (-10.0, 10.0), (-lim["effort"], lim["effort"]))):
+                h[...] = (np.broadcast_to(lo_, (n,))[:, None] + (np.broadcast_to(hi_, (n,)) - np.broadcast_to(lo_, (n,)))[:, None] * rng.random((1, Bm)))
+            mm.rnea_fd(mq, mdq, mddq, mtin, out=mout)
+            ts = []
+            for _ in range(e2e_steps):
+                t0 = time.perf_counter(); mm.rnea_fd(mq, mdq, mddq, mtin, out=mout); ts.append(time.perf_counter() - t0)
+            msec = sum(ts) / len(ts)
+            mu, md = mm.copy_peak(4 * n * Bm * 8, 2 * n * Bm * 8, 2)
+            e2e["single_process_multi_device"] = {
+                "value": 2.0 * Bm / msec, "unit": UNIT, "ms_per_step": msec * 1e3, "states": Bm, "devices": world,
+                "h2d_GBs": 4 * n * Bm * 8 / msec / 1e9, "d2h_GBs": 2 * n * Bm * 8 / msec / 1e9,
+                "copy_ceiling": {"h2d_GBs": mu, "d2h_GBs": md, "evals_per_s": 2.0 * Bm / (4 * n * Bm * 8 / mu / 1e9)},
+                "frac_of_copy_ceiling": (4 * n * Bm * 8 / mu / 1e9) / msec,
+                "api": "multibody_gpu_new_multi over all GPUs, ONE multibody_rnea_fd_batch(RB_MEM_HOST) call on one pinned host batch; "
+                       "the other ranks idle"}
+            for h in (mq, mdq, mddq, mtin, mout):
+                rb.host_free(h)
+            mm.close()
+        barrier()
 
     # optional assembly of the sharded result on every rank: ONE NCCL all-gather of tau, outside the timed
     # region and reported separately -- the compute path itself exchanges nothing
@@ -300,25 +443,70 @@ def run_ours(args, rank, local_rank, world):
         ok_g = bool(torch.equal(full[rank], part))
         gather = {"collective": "ncclAllGather(tau)", "ms": gms, "bytes_per_rank": int(part.numel() * 8),
                   "recv_GB_per_s_per_rank": (world - 1) * part.numel() * 8 / (gms * 1e-3) / 1e9, "own_slice_intact": ok_g}
+        del full, part
 
-    hbm_peak, hbm_src = measured_peaks()
-    rnea_s, fd_s = ms_rnea * 1e-3, ms_fd * 1e-3
+    # ------------------------------------------------------------------ configs.rollout: BASELINE configs[3], strong scaling
+    Ht, dt = 64, 1e-3
+    lo, hi = shard_bounds(65536, world, rank)
+    Bt = hi - lo
+    q0, dq0 = torch.empty((n, Bt), dtype=torch.float64, device=dev), torch.empty((n, Bt), dtype=torch.float64, device=dev)
+    mb.fill(q0, 0x5EED0003, 0, lim["lower"], lim["upper"], lo)
+    mb.fill(dq0, 0x5EED0003, 1, -lim["velocity"], lim["velocity"], lo)
+    taus = torch.empty((Ht, n, Bt), dtype=torch.float64, device=dev)
+    for t in range(Ht):
+        mb.fill(taus[t], 0x5EED0003, 4 + t % 32, -lim["effort"], lim["effort"], t * 65536 + lo)
+    l0 = mb.launch_count
+    ms_ro = timed(lambda: mb.rollout(q0, dq0, taus, dt), max(3, min(K, 10)), 3)
+    ro_launches = mb.launch_count - l0
+    ro_units = sum_over_ranks(float(Bt * Ht), dev)
+    pr = profiled("rb_rollout_kernel")
+    ro_instr = pr["fp64_thread_instr"] / (65536 * Ht) if pr and "fp64_thread_instr" in pr else FP64_INSTR["rb_fd_kernel"] + 14.0
+    cfg_rollout = {"metric": "FR3 MPC rollout FD steps/sec (fp64)", "value": ro_units / (ms_ro * 1e-3), "unit": "steps/s", "ms_per_step": ms_ro,
+                   "scaling": "strong", "trajectories": 65536, "trajectories_per_gpu": Bt, "horizon": Ht, "dt": dt,
+                   "step": "1 rb_rollout_kernel launch: semi-implicit Euler through forward dynamics, (q, dq) written after every step",
+                   "roofline": fp64_roofline("rb_rollout_kernel", ms_ro, float(Bt * Ht), ro_instr, pr.get("fp64_thread_flops", 0) / (65536 * Ht) if pr else None,
+                                             FD_FLOPS + 28.0, 168.0, fp64_peak, peak_note, hbm_peak, hbm_src,
+                                             pr["bytes"] if pr and world == 1 else None, pr["source"] if pr else None,
+                                             "ncu op counters" if pr and "fp64_thread_instr" in pr else "FD kernel count + 14 (Euler update)")}
+    del q0, dq0, taus
 
-    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-
-    def roof(kernel, flops, sec):
-        tf = flops * B / sec / 1e12
-        gbs = BYTES_PER_EVAL * B / sec / 1e9
-        tr = profiled_traffic(kernel) if B == STATES_PER_GPU else None
-        pipe = FP64_INSTR[kernel] * B / sec / (FP64_LANES_PER_SM * sm_count * sm_hz) if mb.kernel_variant == "fr3-specialised" else None
-        return {"kernel": kernel, "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": tf / fp64_peak, "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
-                "fp64_pipe_util": pipe, "fp64_instr_per_eval": FP64_INSTR[kernel],
-                "evals_per_s": B / sec, "ms": sec * 1e3,
-                "peak_source": f"DFMA probe (multibody_gpu_measure_fp64_peak) on this GPU in this run, {probe_ms} ms; nominal 37.2",
-                "flops_per_eval": flops, "bytes_per_eval": BYTES_PER_EVAL,
-                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}}
+    # ------------------------------------------------------------------ configs.chain32: BASELINE configs[4], strong scaling
+    cfg_chain32 = None
+    if not args.no_chain32:
+        del q, dq, ddq, tau_in, tau, qdd
+        torch.cuda.empty_cache()
+        mc = rb.Multibody.from_urdf(os.path.join(ROOT, "assets", "chain32.urdf"), device=local_rank)
+        lo, hi = shard_bounds(args.chain32_states, world, rank)
+        Bc, nc = hi - lo, mc.n
+        pi = np.full(nc, np.pi)
+        cq = torch.empty((nc, Bc), dtype=torch.float64, device=dev)
+        cdq, cx, cin, co1, co2 = (torch.empty_like(cq) for _ in range(5))
+        mc.fill(cq, 0x5EED0005, 0, -pi, pi, lo)
+        mc.fill(cdq, 0x5EED0005, 1, -2.0, 2.0, lo)
+        mc.fill(cx, 0x5EED0005, 2, -10.0, 10.0, lo)
+        mc.fill(cin, 0x5EED0005, 3, -50.0, 50.0, lo)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        mc.rnea(cq, cdq, cx, out=co1); mc.forward_dynamics(cq, cdq, cin, out=co2)
+        barrier()
+        ksteps = 2
+        tr = tf = 0.0
+        for _ in range(ksteps):
+            e[0].record(); mc.rnea(cq, cdq, cx, out=co1); e[1].record(); mc.forward_dynamics(cq, cdq, cin, out=co2); e[2].record()
+            torch.cuda.synchronize()
+            tr += e[0].elapsed_time(e[1]); tf += e[1].elapsed_time(e[2])
+        barrier()
+        ms_cr, ms_cf = max_over_ranks(tr / ksteps, dev), max_over_ranks(tf / ksteps, dev)
+        c_units = sum_over_ranks(2.0 * Bc, dev)
+        prf, prr = profiled("rbh_fd_kernel"), profiled("rb_long_rnea_kernel")
+        cfg_chain32 = {"metric": "chain32 RNEA+FD evals/sec (fp64)", "value": c_units / ((ms_cr + ms_cf) * 1e-3), "unit": UNIT,
+                       "ms_per_step": ms_cr + ms_cf, "scaling": "strong", "states": args.chain32_states, "states_per_gpu": Bc, "n_joints": nc,
+                       "kernel_variant": mc.kernel_variant, "step": "1 rb_long_rnea_kernel launch + 1 rbh_fd_kernel launch over all states",
+                       "roofline": fp64_roofline("rbh_fd_kernel", ms_cf, float(Bc), prf["fp64_thread_instr"] / (1 << 20) if prf and "fp64_thread_instr" in prf else 1130.0 * 16,
+                                                 None, 53800.0, 1024.0, fp64_peak, peak_note, hbm_peak, hbm_src, None, prf["source"] if prf else None,
+                                                 "FP64 instructions per state over the 16 lanes that own it (1130 warp instructions per state, ncu)"),
+                       "roofline_rnea": fp64_roofline("rb_long_rnea_kernel", ms_cr, float(Bc), prr["fp64_thread_instr"] / (1 << 20) if prr and "fp64_thread_instr" in prr else 3626.0,
+                                                      None, 9476.0, 1024.0, fp64_peak, peak_note, hbm_peak, hbm_src, None, prr["source"] if prr else None)}
+        del cq, cdq, cx, cin, co1, co2
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -327,16 +515,13 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": "fr3_rnea+fd_16M", "states_per_gpu": B, "n_joints": n, "layout": "soa",
                    "kernel_variant": mb.kernel_variant, "cache": "inputs larger than L2 (2.8 GB read per kernel)",
                    "step": "1 RNEA launch + 1 forward-dynamics launch over all states", "parallelism": f"dp{world}"},
-        "roofline": roof("rb_fd_kernel", FD_FLOPS, fd_s),
-        "roofline_rnea": roof("rb_rnea_kernel", RNEA_FLOPS, rnea_s),
-        "e2e": {"value": e2e_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * n * Be * 8,
-                "d2h_bytes_per_step": 2 * n * Be * 8, "states_per_gpu": Be, "steps": e2e_steps, "ms_per_step": e2e_ms,
-                "api": "Multibody.rnea_fd on pinned numpy arrays -> multibody_rnea_fd_batch(RB_MEM_HOST): q, dq, ddq, tau_in up, tau and qdd down",
-                "matches_device_path": same,
-                "separate_calls": {"value": e2e_units / (sep_ms * 1e-3), "ms_per_step": sep_ms, "h2d_bytes_per_step": 6 * n * Be * 8,
-                                   "api": "Multibody.rnea + Multibody.forward_dynamics -> multibody_{rnea,forward_dynamics}_batch(RB_MEM_HOST)"}},
+        "roofline": roof("rb_fd_kernel", FD_FLOPS, ms_fd),
+        "roofline_rnea": roof("rb_rnea_kernel", RNEA_FLOPS, ms_rnea),
+        "configs": {"fused_rnea_fd": cfg_fused, "rollout": cfg_rollout, "chain32": cfg_chain32},
+        "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    line["configs"]["rollout"]["gpu_launches"] = int(ro_launches)
     if gather is not None:
         line["gather"] = gather
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -344,78 +529,6 @@ def run_ours(args, rank, local_rank, world):
         line["cpu_baseline"] = cb
     elif rank == 0:
         line["cpu_baseline"] = None
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-
-
-def run_other(args, rank, local_rank, world):
-    """BASELINE.json configs[3] (FR3 MPC rollout, 65 536 trajectories x 64 steps, strong scaling: the trajectories
-    are split across ranks) and configs[4] (32-joint chain RNEA + FD, weak scaling).  Same JSON shape, kernel-only."""
-    import torch
-    import torch.distributed as dist
-    import rigidbody_rs_b200 as rb
-    from rigidbody_rs_b200.shard import max_over_ranks, shard_bounds, sum_over_ranks
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    rollout = args.workload == "rollout"
-    mb = rb.Multibody.from_urdf(os.path.join(ROOT, "assets", "fr3.urdf" if rollout else "chain32.urdf"), device=local_rank)
-    n, lim = mb.n, mb.limits()
-    H = 64
-    if rollout:
-        lo, hi = shard_bounds(65536, world, rank)
-        B, first, seed = hi - lo, lo, 0x5EED0003
-    else:
-        B = args.states if args.states != STATES_PER_GPU else 1 << 22
-        first, seed = rank * B, 0x5EED0005
-    q = torch.empty((n, B), dtype=torch.float64, device=dev)
-    dq, x3, out, out2 = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
-    mb.fill(q, seed, 0, lim["lower"], lim["upper"], first)
-    mb.fill(dq, seed, 1, -lim["velocity"], lim["velocity"], first)
-    if rollout:
-        tau = torch.empty((H, n, B), dtype=torch.float64, device=dev)
-        for t in range(H):
-            mb.fill(tau[t], seed, 4 + t % 32, -lim["effort"], lim["effort"], t * 65536 + first)
-        step = lambda: mb.rollout(q, dq, tau, 1e-3)
-        units_rank, flops, label = float(B * H), 4208.0, "rb_rollout_kernel"
-    else:
-        mb.fill(x3, seed, 2, -10.0, 10.0, first)
-        tau_in = torch.empty_like(q)
-        mb.fill(tau_in, seed, 3, -lim["effort"], lim["effort"], first)
-        def step():
-            mb.rnea(q, dq, x3, out=out)
-            mb.forward_dynamics(q, dq, tau_in, out=out2)
-        units_rank, flops, label = 2.0 * B, (9476.0 + 53800.0) / 2, "rb_long_rnea_kernel + rbh_fd_kernel"
-    for _ in range(args.warmup):
-        step()
-    fp64_peak = mb.fp64_peak_tflops(100)
-    sampler = ClockSampler(local_rank); sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    l0 = mb.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
-    units = sum_over_ranks(units_rank, dev)
-    tf = flops * units / world / (ms * 1e-3) / 1e12
-    line = {"metric": "FR3 MPC rollout FD steps/sec (fp64)" if rollout else "chain32 RNEA+FD evals/sec (fp64)",
-            "value": units / (ms * 1e-3), "unit": "steps/s" if rollout else UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if rollout else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "fr3_rollout_65536x64" if rollout else "chain32_rnea+fd", "states_per_gpu": B, "n_joints": n,
-                       "horizon": H if rollout else None, "dt": 1e-3 if rollout else None, "kernel_variant": mb.kernel_variant,
-                       "parallelism": f"dp{world}"},
-            "roofline": {"kernel": label, "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
-                         "traffic": None, "flops_per_unit": flops},
-            "gpu_launches": int(mb.launch_count - l0), "clocks": clocks}
     if rank == 0:
         print(json.dumps(line), flush=True)
 
@@ -430,8 +543,8 @@ def main():
     ap.add_argument("--e2e-states", type=int, default=STATES_PER_GPU, help="states per GPU per end-to-end step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="fr3", choices=["fr3", "rollout", "chain32"],
-                    help="fr3 = the headline RNEA+FD line (BASELINE.json configs[1]+[2]); rollout = configs[3]; chain32 = configs[4]")
+    ap.add_argument("--no-chain32", action="store_true", help="skip the configs.chain32 leg")
+    ap.add_argument("--chain32-states", type=int, default=1 << 26, help="states of the chain32 leg, split over the GPUs (BASELINE configs[4]: 64M)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -448,7 +561,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        (run_ours if args.workload == "fr3" else run_other)(args, rank, local_rank, world)
+        run_ours(args, rank, local_rank, world)
     finally:
         if world > 1:
             dist.destroy_process_group()

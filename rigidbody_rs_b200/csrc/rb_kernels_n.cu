@@ -567,7 +567,7 @@ cudaError_t rb_launch_soa_to_aos(const double* soa, double* aos, int n, size_t B
     rb_soa_to_aos_kernel<<<(unsigned)((B + spb - 1) / spb), 256, (size_t)spb * n * sizeof(double), st>>>(soa, aos, n, B, ld, spb);
     return cudaGetLastError();
 }
-cudaError_t rb_launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t st) {
-    rb_fp64_peak_kernel<<<blocks, 256, 0, st>>>(out, iters, 0.999999, 1e-7);
+cudaError_t rb_launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t st) {
+    rb_fp64_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-7);
     return cudaGetLastError();
 }

@@ -12,7 +12,7 @@ cudaError_t rb_launch_fill(double* out, uint64_t seed, uint32_t field, int n, co
 // `per_state` doubles per state: [B][per_state] <-> [per_state][ld]
 cudaError_t rb_launch_aos_to_soa(const double* aos, double* soa, int per_state, size_t B, size_t ld, cudaStream_t st);
 cudaError_t rb_launch_soa_to_aos(const double* soa, double* aos, int per_state, size_t B, size_t ld, cudaStream_t st);
-cudaError_t rb_launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t st);
+cudaError_t rb_launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t st);
 // Batched LDL^T solve in shared-memory tiles (rb_kernels_n.cu): H packed upper [n(n+1)/2][hpk_states], rhs/x in qdd.
 cudaError_t rb_launch_ldlt_tiles(int n, const double* hpk, size_t hpk_states, double* qdd, size_t cnt, size_t ld,
                                  int* status, cudaStream_t st);

@@ -9,7 +9,8 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__warps_eligible.avg.per_cycle_active', 'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores',
-        'smsp__inst_executed.sum', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum']
+        'smsp__inst_executed.sum', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum', 'sm__inst_executed_pipe_fp64.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_shared_st.sum']
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
