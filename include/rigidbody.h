@@ -54,6 +54,15 @@ int multibody_n_joints(const Multibody* mb);
 int multibody_get_model(const Multibody* mb, double* parent_rot, double* parent_trans, double* mass,
                         double* h, double* inertia_origin);
 
+/* New: the chain exactly as the reference's Multibody holds it after from_urdf, field for field what
+ * `for jt in mb.iter()` (multibody.rs:79-81) exposes: jt.axis (joint.rs:27), jt.parent rotation (row-major 3x3) and
+ * translation (joint.rs:29), jt.body.mass / com / inertia_com (inertia.rs:13-15, row-major 3x3), plus the parent
+ * index (i-1 for the reference's serial chains).  These are the arrays of an RbChainDesc: a C caller (or the C test
+ * double of the Rust crate, examples/rust_crate_double.c) flattens a Multibody with this one call.  Arrays sized as
+ * in RbChainDesc; any output may be NULL. */
+int multibody_get_chain(const Multibody* mb, int32_t* parent, double* axis, double* parent_rot, double* parent_trans,
+                        double* mass, double* com, double* inertia_com);
+
 /* ===================================================================== Part 2: batched engine */
 typedef enum RbStatus {
     RB_OK = 0,

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "multibody_free_result": (None, [_dp]),
     "multibody_n_joints": (_i, [_vp]),
     "multibody_get_model": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "multibody_get_chain": (_i, [_vp, C.POINTER(C.c_int32), _dp, _dp, _dp, _dp, _dp, _dp]),
     "multibody_gpu_new": (_i, [C.POINTER(RbChainDesc), _i, C.POINTER(_vp)]),
     "multibody_gpu_new_from_urdf": (_i, [C.c_char_p, _i, C.POINTER(_vp)]),
     "multibody_gpu_from_multibody": (_i, [_vp, _i, C.POINTER(_vp)]),

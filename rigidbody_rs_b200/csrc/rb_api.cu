@@ -786,6 +786,22 @@ extern "C" int multibody_get_model(const Multibody* mb, double* parent_rot, doub
     return RB_OK;
 }
 
+extern "C" int multibody_get_chain(const Multibody* mb, int32_t* parent, double* axis, double* parent_rot, double* parent_trans,
+                                   double* mass, double* com, double* inertia_com) {
+    if (!mb) return fail(RB_ERR_NULL, "Multibody handle is NULL");
+    for (int i = 0; i < mb->model.n; ++i) {
+        const RbRawJoint& j = mb->model.raw[(size_t)i];
+        if (parent) parent[i] = j.parent;
+        if (axis) memcpy(axis + 3 * i, j.axis, sizeof j.axis);
+        if (parent_rot) memcpy(parent_rot + 9 * i, j.R, sizeof j.R);
+        if (parent_trans) memcpy(parent_trans + 3 * i, j.t, sizeof j.t);
+        if (mass) mass[i] = j.mass;
+        if (com) memcpy(com + 3 * i, j.com, sizeof j.com);
+        if (inertia_com) memcpy(inertia_com + 9 * i, j.Ic, sizeof j.Ic);
+    }
+    return RB_OK;
+}
+
 extern "C" int multibody_gpu_get_limits(const RbGpu* g, RbJointLimits* out) {
     if (!g || !out) return fail(RB_ERR_NULL, "NULL argument");
     *out = g->model.lim;

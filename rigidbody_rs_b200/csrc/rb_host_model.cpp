@@ -157,10 +157,7 @@ void origin_inertia(double mass, const double c[3], const double Ic[9], double I
     I6[5] = Ic[8] + mass * (cc - cz * cz);
 }
 
-// One movable joint as the sources give it: axis and link inertia in the joint's own (child) frame.
-struct RawJoint {
-    double axis[3]; double R[9]; double t[3]; double mass; double com[3]; double Ic[9]; int parent;
-};
+using RawJoint = RbRawJoint;
 
 void mat3_mul(const double A[9], const double B[9], double C[9]) {
     double T[9];
@@ -184,6 +181,7 @@ void mat3_vec(const double A[9], const double v[3], double o[3]) {
 // and everything attached to that frame (link inertia, the next joint's placement) is re-expressed in the rotated
 // frame.  tau, qdd, H and the tip position are invariant; the tip-frame Jacobian needs the last Q back (model.tip).
 int build_model(const std::vector<RawJoint>& raw, RbHostModel& out, std::string& err) {
+    out.raw = raw;
     std::vector<double> Qs(raw.size() * 9);
     std::vector<char> Qid(raw.size());
     for (size_t i = 0; i < raw.size(); ++i) {

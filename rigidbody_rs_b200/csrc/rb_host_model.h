@@ -10,8 +10,16 @@
 #include "rb_model.h"
 #include "../../include/rigidbody.h"
 
+// One movable joint as the sources give it (URDF or RbChainDesc): axis and link inertia in the joint's own (child)
+// frame -- field for field what the reference keeps in RevoluteJoint { axis, parent, body } (joint.rs:26-31) and
+// Inertia { mass, com, inertia_com } (inertia.rs:12-17).
+struct RbRawJoint {
+    double axis[3]; double R[9]; double t[3]; double mass; double com[3]; double Ic[9]; int parent;
+};
+
 struct RbHostModel {
     int n = 0;
+    std::vector<RbRawJoint> raw;             // the chain as loaded, before re-basing / flattening (multibody_get_chain)
     std::vector<RbJointK> jt;
     double g[3] = {0.0, 0.0, 9.81};          // multibody.rs:118
     double tip[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

@@ -977,6 +977,19 @@ def test_forward_dynamics_error_budget_against_mpmath_truth(rb, oracle_fr3, orac
             assert (e <= fd_bound(cond)).all() and e.max() < 1e-11, (mb.kernel_variant, e.max(), cond.max())
 
 
+def test_rust_crate_double_runs(rb, tmp_path):
+    """examples/rust_crate_double.c: the call sequence of rust/rigidbody_gpu_bindings (ChainArrays::from_multibody ->
+    multibody_gpu_new -> the batch calls on pinned host buffers -> Drop) in C99 against the same ABI, for the FR3 and for
+    the 32-joint chain (run-time-n / long-chain families behind the same calls)."""
+    import subprocess
+    from test_host import _build_rust_double
+    exe = _build_rust_double(tmp_path)
+    for urdf, family in ((FR3, "fr3-specialised"), (CHAIN32, "chain32-specialised")):
+        r = subprocess.run([exe, urdf], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert family in r.stdout and "all checks passed" in r.stdout
+
+
 # ------------------------------------------------------------------------------------------------ multi-device engine
 def _two_devices():
     """[0, 1] on a multi-GPU box; on a one-GPU box the same device twice (test hook of multibody_gpu_new_multi): the

@@ -32,6 +32,78 @@ def test_library_exports_every_header_symbol(rb):
     assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
 
 
+def _c_prototypes():
+    """name -> number of parameters, for every function include/rigidbody.h declares (Rust-bridge block excluded)."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#ifdef RIGIDBODY_HAVE_RUST_BRIDGE.*?#endif", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(multibody_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_rust_crate_binds_the_whole_header():
+    """rust/rigidbody_gpu_bindings cannot be compiled here (no cargo): instead its `extern "C"` block is held against
+    include/rigidbody.h -- every Part-2 symbol (everything but the reference's own single-state symbols, which the Rust
+    cdylib rigidbody_bindings keeps exporting) must be bound, with the same number of parameters, and nothing else."""
+    rs = open(os.path.join(ROOT, "rust", "rigidbody_gpu_bindings", "src", "lib.rs")).read()
+    block = rs[rs.index('extern "C" {'):]
+    block = block[: block.index("\n}\n")]
+    block = re.sub(r"//.*", "", block)
+    rust = {}
+    for m in re.finditer(r"pub fn (multibody_[a-z0-9_]+)\s*\(([^;]*?)\)\s*(->[^;]*)?;", block, flags=re.S):
+        args = m.group(2).strip()
+        rust[m.group(1)] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    c = _c_prototypes()
+    part1 = {"multibody_new", "multibody_new_from_urdf", "multibody_fwd_kin", "multibody_jac", "multibody_rnea", "multibody_crba",
+             "multibody_free", "multibody_free_result", "multibody_n_joints", "multibody_get_model", "multibody_get_chain"}
+    want = {k: v for k, v in c.items() if k not in part1}
+    assert set(rust) == set(want), sorted(set(rust) ^ set(want))
+    for name, nargs in want.items():
+        assert rust[name] == nargs, (name, rust[name], nargs)
+    # the crate's one export is the bridge the header declares under RIGIDBODY_HAVE_RUST_BRIDGE
+    assert "pub unsafe extern \"C\" fn multibody_gpu_from_rust(mb: *const Multibody, device: c_int, out: *mut *mut RbGpu) -> c_int" in rs
+    assert "int multibody_gpu_from_rust(const Multibody* mb, int device, RbGpu** out);" in open(HEADER).read()
+
+
+def _build_rust_double(tmp_path):
+    exe = str(tmp_path / "rust_crate_double")
+    libdir = os.path.join(ROOT, "rigidbody_rs_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "rust_crate_double.c"),
+                    "-L" + libdir, "-lrigidbody_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_rust_crate_double_builds_and_flattens_the_chain(rb, tmp_path):
+    """examples/rust_crate_double.c (the crate's call sequence in C99) builds warning-free against the header; the part
+    that needs no GPU -- ChainArrays::from_multibody -> RbChainDesc -- is checked here: the arrays multibody_get_chain
+    returns, fed back through a descriptor, give the same flattened model as the URDF loader, bit for bit."""
+    import torch
+    from rigidbody_rs_b200 import _lib
+    exe = _build_rust_double(tmp_path)
+    r = subprocess.run([exe, FR3], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stdout
+    lib = _lib.lib
+    mb = lib.multibody_new_from_urdf(FR3.encode())
+    n = lib.multibody_n_joints(mb)
+    par = (C.c_int32 * n)()
+    arrs = [np.empty(k * n) for k in (3, 9, 3, 1, 3, 9)]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    assert lib.multibody_get_chain(mb, par, *[dp(a) for a in arrs]) == 0
+    assert list(par) == list(range(-1, n - 1))
+    axis, R, t, m, com, Ic = arrs
+    assert np.array_equal(axis.reshape(n, 3), np.tile([0.0, 0.0, 1.0], (n, 1)))
+    from oracle.rb_oracle import parse_urdf
+    mo = parse_urdf(FR3)
+    assert np.array_equal(m, mo.mass) and np.array_equal(com.reshape(n, 3), mo.com) and np.array_equal(t.reshape(n, 3), mo.xyz)
+    lib.multibody_free(mb)
+
+
 def test_header_is_valid_c_and_cpp(tmp_path):
     # with and without the Rust bridge declaration
     (tmp_path / "t.c").write_text('#define RIGIDBODY_HAVE_RUST_BRIDGE 1\n#include "rigidbody.h"\nint main(void){ RbChainDesc d; (void)d; (void)multibody_gpu_from_rust; return RB_OK; }\n')
