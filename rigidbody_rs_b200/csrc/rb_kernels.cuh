@@ -341,11 +341,12 @@ rb_rollout_kernel(const __grid_constant__ typename M::Param p, const RB_R* __res
     RB_R u[N];
     if (horizon > 0) rb_load<N>(tau, ld, s, u);            // horizon == 0: no step, tau is not read (may be NULL)
     for (int t = 0; t < horizon; ++t) {
-        RB_R sn[N], cs[N], qdd[N], un[N];
+        RB_R sn[N], cs[N], qdd[N];
+        RB_R un[N];
         // prefetch the next step's torques so the load latency hides behind this step's arithmetic
         if (t + 1 < horizon) rb_load<N>(tau + (size_t)(t + 1) * step, ld, s, un);
         rb_sincos_all<N>(q, sn, cs);
-                ok = rb_forward_dynamics<M>(p, sn, cs, dq, u, qdd) && ok;
+        ok = rb_forward_dynamics<M>(p, sn, cs, dq, u, qdd) && ok;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             dq[i] = fma(dt, qdd[i], dq[i]);
