@@ -68,8 +68,10 @@ def profiled(kernel):
                          "grid": num(row.get("launch__grid_size", "0")), "block": num(row.get("launch__block_size", "0"))}
                     ops = [row.get(f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum") for o in ("dfma", "dadd", "dmul")]
                     if all(ops):
-                        d["fp64_thread_instr"] = sum(num(o) for o in ops)
                         d["fp64_thread_flops"] = 2 * num(ops[0]) + num(ops[1]) + num(ops[2])
+                        # every instruction the FP64 pipe executed (DSETP and conversions included), per thread
+                        pipe = row.get("sm__inst_executed_pipe_fp64.sum")
+                        d["fp64_thread_instr"] = 32.0 * num(pipe) if pipe else sum(num(o) for o in ops)
                     best = d
     return best
 
@@ -323,7 +325,7 @@ def run_ours(args, rank, local_rank, world):
         full = B == STATES_PER_GPU and pr is not None
         instr, src, fl = FP64_INSTR[kernel], "static SASS count minus the out-of-range sin/cos fallback (tools/sass_count.sh)", None
         if full and "fp64_thread_instr" in pr:
-            instr, src, fl = pr["fp64_thread_instr"] / B, "ncu smsp__sass_thread_inst_executed_op_d{fma,add,mul} (" + pr["source"] + ")", pr["fp64_thread_flops"] / B
+            instr, src, fl = pr["fp64_thread_instr"] / B, "ncu sm__inst_executed_pipe_fp64.sum x 32 / states (" + pr["source"] + ")", pr["fp64_thread_flops"] / B
         return fp64_roofline(kernel, ms, float(B), instr if fr3 else float("nan"), fl, alg_flops, BYTES_PER_EVAL, fp64_peak, peak_note,
                              hbm_peak, hbm_src, pr["bytes"] if full else None, pr["source"] if full else None, src)
 
@@ -375,7 +377,7 @@ def run_ours(args, rank, local_rank, world):
         and float(np.abs(hout[:n] - htau).max() / max(1.0, np.abs(htau).max())) < 1e-12
     # the ceiling: the same bytes, both directions at once, pinned memory, no kernel -- every rank at the same time
     barrier()
-    cu, cd = mb.copy_peak(up_b, down_b, 2)
+    cu, cd = mb.copy_peak(up_b, down_b, 3)
     barrier()
     ceil_ms = max_over_ranks(up_b / cu / 1e6, dev)
     e2e = {"value": e2e_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": up_b, "d2h_bytes_per_step": down_b,

@@ -293,7 +293,7 @@ int multibody_host_alloc(void** out, size_t bytes);
 void multibody_host_free(void* p);
 /* Bare ceiling of the host<->device path RB_MEM_HOST calls use: h2d_bytes from pinned host memory to the device and,
  * concurrently, d2h_bytes back (both split evenly over the devices of a multi-device engine, all devices at once), no
- * kernel in between; best of `reps` passes by wall clock.  Returns GB/s per direction, summed over devices: what an
+ * kernel in between; mean of `reps` passes by wall clock.  Returns GB/s per direction, summed over devices: what an
  * end-to-end call moving the same bytes cannot beat (bench.py reports e2e as a fraction of it). */
 int multibody_gpu_measure_copy_peak(RbGpu* g, size_t h2d_bytes, size_t d2h_bytes, int reps, double* h2d_gbs, double* d2h_gbs);
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), measured with a register-only

@@ -1234,17 +1234,20 @@ extern "C" int multibody_gpu_measure_copy_peak(RbGpu* g, size_t h2d_bytes, size_
         return RB_OK;
     };
     int rc = all();                               // warm-up
-    double best = 1e30;
+    // MEAN over the timed passes, not the best one: when several processes probe at the same time (bench.py under
+    // torchrun) their passes drift apart, and a process's fastest pass is the one the others were not competing in
+    double total = 0.0; int done = 0;
     for (int r = 0; r < reps && rc == RB_OK; ++r) {
         const auto t0 = std::chrono::steady_clock::now();
         rc = all();
-        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        best = std::min(best, sec);
+        total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ++done;
     }
     cleanup();
     if (rc != RB_OK) return rc;
-    *h2d_gbs = (double)(h2d_bytes / nd * nd) / best / 1e9;
-    *d2h_gbs = (double)(d2h_bytes / nd * nd) / best / 1e9;
+    const double sec = total / done;
+    *h2d_gbs = (double)(h2d_bytes / nd * nd) / sec / 1e9;
+    *d2h_gbs = (double)(d2h_bytes / nd * nd) / sec / 1e9;
     return RB_OK;
 }
 

@@ -205,6 +205,56 @@ def test_ragged_leading_dimension_device(rb, mb_fr3, oracle_fr3):
     assert rc == _lib.RB_ERR_ARG
 
 
+def test_ragged_leading_dimension_rollout_and_kinematics(rb, oracle_fr3):
+    """Memory safety of the remaining kernels without compute-sanitizer (closed on this pool): ld > n with NaN-poisoned
+    padding through the rollout, the fused rollout cost, the fused inverse + forward dynamics pass, crba, jac and fwd_kin,
+    in every kernel family and at sizes that leave ragged warps and blocks -- results equal the compact call bit for bit,
+    every padding element still NaN."""
+    import torch
+    from rigidbody_rs_b200 import _lib
+    lib = _lib.lib
+    dev = torch.device("cuda:0")
+    nan = float("nan")
+    H, dt = 5, 1e-3
+    lim = oracle_fr3.model
+    for mb in _variants(rb, FR3):
+        for B, ld in ((1, 8), (33, 64), (129, 200)):
+            q, dq, ddq, tin = _states(oracle_fr3, B, seed=0x5EED0021)
+            tau = np.stack([oracle_fr3.fill(0x5EED0021, 4 + t, -lim.effort, lim.effort, t * B, B) for t in range(H)])
+
+            def wide(x):                                   # [..., n, B] -> NaN-padded [..., n, ld] on the device
+                w = torch.full(x.shape[:-1] + (ld,), nan, dtype=torch.float64, device=dev)
+                w[..., :B] = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+                return w
+            p = lambda t: C.c_void_p(t.data_ptr())
+            wq, wdq, wddq, wtin, wtau = wide(q), wide(dq), wide(ddq), wide(tin), wide(tau)
+            blank = lambda *shape: torch.full(shape, nan, dtype=torch.float64, device=dev)
+            # rollout: trajectory + final state
+            qt, dqt, qf, dqf = blank(H, 7, ld), blank(H, 7, ld), blank(7, ld), blank(7, ld)
+            assert lib.multibody_rollout(mb._h, p(wq), p(wdq), p(wtau), dt, H, p(qt), p(dqt), p(qf), p(dqf), B, ld, 0, 1, None) == 0
+            # fused cost
+            w = np.linspace(0.5, 2.0, 7)
+            qc = _lib.RbQuadCost()
+            dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+            qc.w_q, qc.w_tau, qc.w_q_final = dp(w), dp(w), dp(w)
+            cost = blank(ld)
+            assert lib.multibody_rollout_cost(mb._h, p(wq), p(wdq), p(wtau), dt, H, C.byref(qc), p(cost), None, None, B, ld, 0, 1, None) == 0
+            # fused inverse + forward dynamics, crba, jac, fwd_kin
+            both, Hm, J, xyz = blank(14, ld), blank(49, ld), blank(42, ld), blank(3, ld)
+            assert lib.multibody_rnea_fd_batch(mb._h, p(wq), p(wdq), p(wddq), p(wtin), p(both), B, ld, 0, 1, None) == 0
+            assert lib.multibody_crba_batch(mb._h, p(wq), p(Hm), B, ld, 0, 1, None) == 0
+            assert lib.multibody_jac_batch(mb._h, p(wq), p(J), B, ld, 0, 1, None) == 0
+            assert lib.multibody_fwd_kin_batch(mb._h, p(wq), p(xyz), B, ld, 0, 1, None) == 0
+            mb.sync()
+            ref_qt, ref_dqt, ref_qf, ref_dqf = mb.rollout(q, dq, tau, dt, final=True)
+            ref_cost = mb.rollout_cost(q, dq, tau, dt, w_q=w, w_tau=w, w_q_final=w)
+            for got, want in ((qt, ref_qt), (dqt, ref_dqt), (qf, ref_qf), (dqf, ref_dqf), (cost, ref_cost), (both, mb.rnea_fd(q, dq, ddq, tin)),
+                              (Hm, mb.crba(q)), (J, mb.jac(q)), (xyz, mb.fwd_kin(q))):
+                g = got.cpu().numpy()
+                np.testing.assert_array_equal(g[..., :B], np.asarray(want).reshape(g[..., :B].shape), err_msg=f"{mb.kernel_variant} B={B}")
+                assert np.isnan(g[..., B:]).all(), (mb.kernel_variant, B)
+
+
 def test_ragged_leading_dimension_long_chain_and_derivatives(rb, mb_fr3, mb_chain32, oracle_chain32):
     """ld > n_states with NaN-poisoned padding through the lane-per-joint FD kernel (odd tail: half-warp pairs, staging
     groups) and the derivative kernels: results right, padding untouched."""
