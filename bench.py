@@ -231,7 +231,7 @@ def fp64_roofline(kernel, ms, units, instr_per_unit, flops_executed_per_unit, al
     sec = ms * 1e-3
     fma_eq = 2.0 * instr_per_unit * units / sec / 1e12
     d = {"kernel": kernel, "bound": "fp64", "achieved": fma_eq, "peak": fp64_peak, "unit": "TFLOP/s (FMA-equivalent: 2 x FP64 instructions executed)",
-         "frac": fma_eq / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
+         "frac": fma_eq / fp64_peak, "frac_of_nominal_peak": fma_eq / 37.2, "traffic": traffic, "traffic_source": traffic_src,
          "fp64_instr_per_unit": instr_per_unit, "fp64_instr_source": instr_src,
          "executed_tflops": flops_executed_per_unit * units / sec / 1e12 if flops_executed_per_unit else None,
          "algorithmic_flops_per_unit": alg_flops_per_unit, "algorithmic_tflops": alg_flops_per_unit * units / sec / 1e12,

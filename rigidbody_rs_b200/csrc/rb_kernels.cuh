@@ -25,8 +25,8 @@ typedef unsigned long uintptr_t;
 #endif
 // Minimum resident blocks per SM requested from ptxas (register cap = 65536 / (RB_BLOCK * min_blocks)).
 #ifndef RB_MINB_RNEA
-#define RB_MINB_RNEA 5
-#endif
+#define RB_MINB_RNEA 4     // 126 registers, no spills.  (5 blocks / 96 registers won by 4 % with the per-joint library sincos;
+#endif                     //  with the batched sincos 4 blocks win by 3 %: profiles/r2_kbench_launch_bounds.jsonl)
 #ifndef RB_MINB_FD
 #define RB_MINB_FD 4
 #endif
@@ -227,7 +227,7 @@ rb_fd_kernel(const __grid_constant__ typename M::Param p, const RB_R* __restrict
 // (336 B per FR3 state instead of the 448 B of two launches), shared sin/cos, bias recursion and mass matrix
 // (rb_rnea_fd_fused).  out holds tau in rows 0..n-1 and qdd in rows n..2n-1.
 #ifndef RB_MINB_FUSED
-#define RB_MINB_FUSED RB_MINB_FD
+#define RB_MINB_FUSED 3    // 168 registers, no spills (4 blocks: 128 registers, 148 B of spills, 2 % slower)
 #endif
 template <class M>
 __global__ void __launch_bounds__(RB_BLOCK, !M::kSpecialised ? RB_MINB_FD_RT : (M::N <= 11 ? RB_MINB_FUSED : RB_MINB_FD_LONG))
