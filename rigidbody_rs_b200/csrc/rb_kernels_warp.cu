@@ -23,6 +23,8 @@
 // sums associate differently from the reference's link-frame recursion (measured 5e-14 relative on the 32-joint
 // chain, cond(H) ~ 1e4).
 #include <atomic>
+#include <cstdlib>
+#include <type_traits>
 #include "rb_kernels.cuh"
 #include "rb_util.cuh"
 
@@ -37,6 +39,9 @@
 #endif
 #ifndef RBW_HALF
 #define RBW_HALF 1                        // 1 = half a warp per state (rbh_fd_kernel), 0 = a warp per state (rbw_fd_kernel)
+#endif
+#ifndef RBW_QUARTER
+#define RBW_QUARTER 1                     // 1 = eight lanes per state in the matrix phase (rbq_fd_kernel, the default)
 #endif
 #define RBW_LDL 34                        // row stride of the stored L columns: even, so pairs are 16-byte aligned
 #define RBW_IOS (RBW_GROUP + 1)           // padded stride of the staging rows
@@ -727,6 +732,340 @@ rbh_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
     }
     if (!all_ok && r == 0) atomicOr(status, RB_STATUS_NOT_SPD);
 }
+
+// ------------------------------------------------------------------ a quarter of a warp per state in the matrix phase
+// rbq_fd_kernel: the chain phase is rbh_fd_kernel's (half a warp per state, run twice for the four staged states), but the
+// mass matrix is built and factorised by EIGHT lanes per state, four states per warp: lane (s, r) owns rows r, r + 8,
+// r + 16, r + 24 of state s, lower triangle padded to the row group's width (8 + 16 + 24 + 32 = 80 register entries).
+// Against 16 lanes per state every broadcast load, every stored pivot column, every reciprocal and every shuffle of the
+// elimination now serves four states instead of two, and the rows of a lane are closer to the triangle (the FP64 work
+// per state drops by a quarter: 230 instead of 308 warp-level FMAs in the elimination).  The right-hand side and the
+// pivot travel together in one 16-byte header per column (no shuffle in the elimination).
+//   shared memory per state: columns of L D (column k holds rows 8 (k / 8) .. 31), then the 32 headers {d_k, y_k};
+//   the header's d_k is overwritten by 1 / d_k one step later (read by the back substitution).
+#ifndef RBQ_WARPS
+#define RBQ_WARPS 8
+#endif
+constexpr int rbq_colofs(int k) {
+    return k < 8 ? 34 * k : k < 16 ? 272 + 26 * (k - 8) : k < 24 ? 480 + 18 * (k - 16) : 624 + 8 * (k - 24);
+}
+constexpr int RBQ_COLS = 688;                         // = rbq_colofs(32)
+constexpr int RBQ_SS = RBQ_COLS + 64 + 2;             // state stride: = 2 mod 16 doubles, so the four states' 16-byte broadcasts hit four bank groups
+constexpr int RBQ_HS = 32 * 6 + 7 * 32 + 2;           // hand-over stride (screws + component-major I^c s and rhs), also = 2 mod 16
+constexpr int RBQ_IO = 3 * 32 * RBW_IOS;              // staged q, dq, tau; the results reuse the q part
+constexpr int RBQ_PER_WARP = 4 * RBQ_SS + RBQ_IO;
+static_assert(4 * RBQ_HS <= 4 * RBQ_SS, "hand-over buffers alias the column storage");
+static_assert(RBW_GROUP == 4, "rbq_fd_kernel factorises the four staged states together");
+
+// Chain phase of one state on 16 lanes (lane r <-> joints 2r, 2r + 1): world poses by a prefix product, the recursions of
+// rnea / crba as sums along the chain (see the file header), then the hand-over: screws to Sb[32][6], I^c s and
+// tau - bias to Fb[7][32] (component-major).
+__device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, const double* __restrict__ io, int st, int r, int n,
+                                                const double (&g)[3], double* __restrict__ Sb, double* __restrict__ Fb) {
+    const int j0 = 2 * r;
+    const bool act0 = j0 < n, act1 = j0 + 1 < n;
+    auto mdl2 = [&](int e) { return *reinterpret_cast<const double2*>(msm + e * 32 + j0); };
+    double R0[9], p0[3], R1[9], p1[3];
+    {
+        double sn, cs;
+        sincos(io[(0 * 32 + j0) * RBW_IOS + st], &sn, &cs);
+        double sn1, cs1;
+        sincos(io[(0 * 32 + j0 + 1) * RBW_IOS + st], &sn1, &cs1);
+        double T0[9], T1[9], t0[3], t1[3];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+            const double2 a = mdl2(3 * rr), b = mdl2(3 * rr + 1), c = mdl2(3 * rr + 2), t = mdl2(9 + rr);
+            T0[3 * rr + 0] = fma(cs, a.x, sn * b.x);   T1[3 * rr + 0] = fma(cs1, a.y, sn1 * b.y);
+            T0[3 * rr + 1] = fma(cs, b.x, -sn * a.x);  T1[3 * rr + 1] = fma(cs1, b.y, -sn1 * a.y);
+            T0[3 * rr + 2] = c.x;                      T1[3 * rr + 2] = c.y;
+            t0[rr] = t.x;                              t1[rr] = t.y;
+        }
+        double C[9], cp[3];
+        compose(T0, t0, T1, t1, C, cp);
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            double A[9], u[3];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) A[e] = up16(C[e], d);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) u[e] = up16(cp[e], d);
+            if (r >= d) {
+                double nC[9], np[3];
+                compose(A, u, C, cp, nC, np);
+#pragma unroll
+                for (int e = 0; e < 9; ++e) C[e] = nC[e];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) cp[e] = np[e];
+            }
+        }
+        double E[9], ep[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { const double x = up16(C[e], 1); E[e] = r ? x : ((e == 0 || e == 4 || e == 8) ? 1.0 : 0.0); }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { const double x = up16(cp[e], 1); ep[e] = r ? x : 0.0; }
+        compose(E, ep, T0, t0, R0, p0);
+        compose(R0, p0, T1, t1, R1, p1);
+    }
+    const double dq0 = io[(1 * 32 + j0) * RBW_IOS + st], dq1 = io[(1 * 32 + j0 + 1) * RBW_IOS + st];
+    double z0[3] = {act0 ? R0[2] : 0.0, act0 ? R0[5] : 0.0, act0 ? R0[8] : 0.0};
+    double z1[3] = {act1 ? R1[2] : 0.0, act1 ? R1[5] : 0.0, act1 ? R1[8] : 0.0};
+    double v0[3], v1[3];
+    cross(p0, z0, v0);
+    cross(p1, z1, v1);
+    const double zq0[3] = {z0[0] * dq0, z0[1] * dq0, z0[2] * dq0}, zq1[3] = {z1[0] * dq1, z1[1] * dq1, z1[2] * dq1};
+    double om0[3] = {zq0[0], zq0[1], zq0[2]}, om1[3] = {zq1[0], zq1[1], zq1[2]};
+    prefix2<3>(om0, om1, r);
+    double al0[3], al1[3];
+    cross(om0, zq0, al0);
+    cross(om1, zq1, al1);
+    prefix2<3>(al0, al1, r);
+    double ac0[3], ac1[3];
+    {
+        double omp[3], alp[3], d[3], w1[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {                // joint j0's predecessor is the previous lane's second joint
+            const double a = up16(om1[e], 1), b = up16(al1[e], 1), c = up16(p1[e], 1);
+            omp[e] = r ? a : 0.0;
+            alp[e] = r ? b : 0.0;
+            d[e] = p0[e] - (r ? c : 0.0);
+        }
+        cross(omp, d, w1);
+        cross(alp, d, ac0);
+        cross_acc(omp, w1, ac0);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) ac0[e] += r ? 0.0 : g[e];
+        const double d1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+        cross(om0, d1, w1);
+        cross(al0, d1, ac1);
+        cross_acc(om0, w1, ac1);
+    }
+    prefix2<3>(ac0, ac1, r);
+    double fw0[6], fw1[6], ci0[9], ci1[9];
+    {
+        const double2 m = mdl2(12), h0 = mdl2(13), h1 = mdl2(14), h2 = mdl2(15);
+        const double2 i0 = mdl2(16), i1 = mdl2(17), i2 = mdl2(18), i3 = mdl2(19), i4 = mdl2(20), i5 = mdl2(21);
+        const double ha[3] = {h0.x, h1.x, h2.x}, hb[3] = {h0.y, h1.y, h2.y};
+        const double Ia[6] = {i0.x, i1.x, i2.x, i3.x, i4.x, i5.x}, Ib[6] = {i0.y, i1.y, i2.y, i3.y, i4.y, i5.y};
+        link_terms(R0, p0, m.x, ha, Ia, om0, al0, ac0, fw0, ci0);
+        link_terms(R1, p1, m.y, hb, Ib, om1, al1, ac1, fw1, ci1);
+    }
+    suffix2<6>(fw0, fw1, r);
+    const double b0 = io[(2 * 32 + j0) * RBW_IOS + st]
+                      - (z0[0] * fw0[3] + z0[1] * fw0[4] + z0[2] * fw0[5] + v0[0] * fw0[0] + v0[1] * fw0[1] + v0[2] * fw0[2]);
+    const double b1 = io[(2 * 32 + j0 + 1) * RBW_IOS + st]
+                      - (z1[0] * fw1[3] + z1[1] * fw1[4] + z1[2] * fw1[5] + v1[0] * fw1[0] + v1[1] * fw1[1] + v1[2] * fw1[2]);
+    suffix2<9>(ci0, ci1, r);
+    const double2 mc = mdl2(22);
+    double Fn0[3], Ff0[3], Fn1[3], Ff1[3];
+    double2* S2 = reinterpret_cast<double2*>(Sb + j0 * 6);
+    comp_times_screw(mc.x, ci0, z0, v0, Fn0, Ff0);
+    comp_times_screw(mc.y, ci1, z1, v1, Fn1, Ff1);
+    S2[0] = make_double2(z0[0], z0[1]); S2[1] = make_double2(z0[2], v0[0]); S2[2] = make_double2(v0[1], v0[2]);
+    S2[3] = make_double2(z1[0], z1[1]); S2[4] = make_double2(z1[2], v1[0]); S2[5] = make_double2(v1[1], v1[2]);
+    double2* F2 = reinterpret_cast<double2*>(Fb + j0);
+    F2[0 * 16] = make_double2(Fn0[0], Fn1[0]); F2[1 * 16] = make_double2(Fn0[1], Fn1[1]); F2[2 * 16] = make_double2(Fn0[2], Fn1[2]);
+    F2[3 * 16] = make_double2(Ff0[0], Ff1[0]); F2[4 * 16] = make_double2(Ff0[1], Ff1[1]); F2[5 * 16] = make_double2(Ff0[2], Ff1[2]);
+    F2[6 * 16] = make_double2(act0 ? b0 : 0.0, act1 ? b1 : 0.0);
+}
+
+// compile-time loops with the index as a constant expression (register arrays of different lengths per row group)
+template <int I, int E, class F>
+__device__ __forceinline__ void rbq_for(F&& f) {
+    if constexpr (I < E) { f(std::integral_constant<int, I>{}); rbq_for<I + 1, E>(f); }
+}
+template <int I, int E, class F>
+__device__ __forceinline__ void rbq_for_down(F&& f) {          // I, I - 1, ..., E
+    if constexpr (I >= E) { f(std::integral_constant<int, I>{}); rbq_for_down<I - 1, E>(f); }
+}
+
+__global__ void __launch_bounds__(32 * RBQ_WARPS, 1)
+rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict__ q, const double* __restrict__ dq,
+              const double* __restrict__ tau, double* __restrict__ qdd, size_t B, size_t ld, int* __restrict__ status) {
+    extern __shared__ __align__(16) double rbw_sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* msm = rbw_sm;                                    // [24][32] model constants, [22][*] = composite mass
+    double* wsm = rbw_sm + RBH_MODEL + (size_t)w * RBQ_PER_WARP;
+    double* io = wsm + 4 * RBQ_SS;                           // [3][32][RBW_IOS]
+    double* ob = io;                                         // results: the q part, dead after the chain phases
+    if (w == 0) {                                            // model -> shared memory; idle joints: identity, no mass
+        const bool act = lane < n;
+        const double* row = model + (size_t)(act ? lane : 0) * 24;
+        double mc[1] = {act ? row[12] : 0.0};
+        suffix_sum<1>(mc, lane);
+#pragma unroll
+        for (int e = 0; e < 13; ++e) msm[e * 32 + lane] = act ? row[e] : ((e == 0 || e == 4 || e == 8) ? 1.0 : 0.0);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) msm[(13 + e) * 32 + lane] = act ? row[14 + e] : 0.0;
+        msm[22 * 32 + lane] = mc[0];
+    }
+    __syncthreads();
+    const double g[3] = {model[(size_t)n * 24], model[(size_t)n * 24 + 1], model[(size_t)n * 24 + 2]};
+    // chain phase: half h of the warp, lane rh of 16;  matrix phase: state s of the group, lane r of 8
+    const int h = lane >> 4, rh = lane & 15;
+    const int s = lane >> 3, r = lane & 7;
+    double* Ls = wsm + s * RBQ_SS;                           // this state's columns of L D
+    double2* hdr = reinterpret_cast<double2*>(Ls + RBQ_COLS);  // [32] {d_k (later 1 / d_k), y_k}
+    const double* Sq = wsm + s * RBQ_HS;                     // hand-over of state s: screws [32][6] ...
+    const double* Fq = Sq + 32 * 6;                          // ... and [7][32] I^c s (6 components) and tau - bias
+    int colbase[4];                                          // column r + 8 g of the lane's rows: entry of row i at colbase[g] + i
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+        const int k = r + 8 * gg;
+        colbase[gg] = (gg == 0 ? 34 * k : gg == 1 ? 272 + 26 * (k - 8) : gg == 2 ? 480 + 18 * (k - 16) : 624 + 8 * (k - 24)) - 8 * gg;
+    }
+
+    const size_t groups = (B + RBW_GROUP - 1) / RBW_GROUP;
+    bool all_ok = true;
+    for (size_t grp = (size_t)blockIdx.x * RBQ_WARPS + w; grp < groups; grp += (size_t)gridDim.x * RBQ_WARPS) {
+        const size_t s0 = grp * RBW_GROUP;
+        {
+            const int sj = lane / RBW_GROUP, ss = lane % RBW_GROUP;
+            const bool sin = s0 + ss < B;
+#pragma unroll
+            for (int it = 0; it < 32 / (32 / RBW_GROUP); ++it) {
+                const int i = it * (32 / RBW_GROUP) + sj;
+                const bool ld_ok = sin && i < n;
+                const size_t off = (size_t)i * ld + s0 + ss;
+                io[(0 * 32 + i) * RBW_IOS + ss] = ld_ok ? __ldcs(q + off) : 0.0;
+                io[(1 * 32 + i) * RBW_IOS + ss] = ld_ok ? __ldcs(dq + off) : 0.0;
+                io[(2 * 32 + i) * RBW_IOS + ss] = ld_ok ? __ldcs(tau + off) : 0.0;
+            }
+        }
+        __syncwarp();
+        const int in_group = (int)(B - s0 < RBW_GROUP ? B - s0 : RBW_GROUP);
+        // ================= chain phase, two states at a time (a state that does not exist is computed from zeros: q = dq =
+        // tau = 0 were staged for it, its matrix is that of the zero pose and nothing of it is stored)
+#pragma unroll 1
+        for (int st2 = 0; st2 < 4; st2 += 2) {
+            const int st = st2 + h;
+            rbq_chain_phase(msm, io, st, rh, n, g, wsm + st * RBQ_HS, wsm + st * RBQ_HS + 32 * 6);
+        }
+        __syncwarp();
+        // ================= matrix phase: lane (s, r) <-> rows r, r + 8, r + 16, r + 24 of state s
+        double a0[8], a1[16], a2[24], a3[32], b[4];
+        {
+            double F0[6], F1[6], F2[6], F3[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                F0[c] = Fq[c * 32 + r]; F1[c] = Fq[c * 32 + r + 8]; F2[c] = Fq[c * 32 + r + 16]; F3[c] = Fq[c * 32 + r + 24];
+            }
+            b[0] = Fq[6 * 32 + r]; b[1] = Fq[6 * 32 + r + 8]; b[2] = Fq[6 * 32 + r + 16]; b[3] = Fq[6 * 32 + r + 24];
+            auto dot6 = [](const double2& s01, const double2& s23, const double2& s45, const double (&F)[6]) {
+                return fma(s01.x, F[0], fma(s01.y, F[1], fma(s23.x, F[2], fma(s23.y, F[3], fma(s45.x, F[4], s45.y * F[5])))));
+            };
+            rbq_for<0, 32>([&](auto jc) {
+                constexpr int J = decltype(jc)::value;
+                const double2* S2 = reinterpret_cast<const double2*>(Sq + J * 6);
+                const double2 s01 = S2[0], s23 = S2[1], s45 = S2[2];
+                if constexpr (J < 8) a0[J] = dot6(s01, s23, s45, F0);
+                if constexpr (J < 16) a1[J] = dot6(s01, s23, s45, F1);
+                if constexpr (J < 24) a2[J] = dot6(s01, s23, s45, F2);
+                a3[J] = dot6(s01, s23, s45, F3);
+            });
+            if (n < 32) {                                    // idle joints: identity rows
+                rbq_for<0, 32>([&](auto jc) {
+                    constexpr int J = decltype(jc)::value;
+                    if constexpr (J < 8) a0[J] = (r >= n && J == r) ? 1.0 : a0[J];
+                    if constexpr (J < 16) a1[J] = (r + 8 >= n && J == r + 8) ? 1.0 : a1[J];
+                    if constexpr (J < 24) a2[J] = (r + 16 >= n && J == r + 16) ? 1.0 : a2[J];
+                    a3[J] = (r + 24 >= n && J == r + 24) ? 1.0 : a3[J];
+                });
+            }
+        }
+        __syncwarp();                                        // the hand-over buffers are free: the columns of L go there
+        bool ok = true;
+        double dinv_prev = 0.0;
+        rbq_for<0, 32>([&](auto kc) {
+            constexpr int K = decltype(kc)::value, GK = K >> 3, RK = K & 7;
+            constexpr int COL = rbq_colofs(K) - 8 * GK;      // entry of row i at COL + i
+            // column K: the entries of the lane's rows in groups GK..3 (finished rows of group GK store into dead slots)
+            if constexpr (GK <= 0) Ls[COL + r] = a0[K & 7];
+            if constexpr (GK <= 1) Ls[COL + r + 8] = a1[K & 15];
+            if constexpr (GK <= 2) Ls[COL + r + 16] = a2[K < 24 ? K : 0];
+            Ls[COL + r + 24] = a3[K];
+            if (r == RK) {
+                const double dk = GK == 0 ? a0[K & 7] : GK == 1 ? a1[K & 15] : GK == 2 ? a2[K < 24 ? K : 0] : a3[K];
+                hdr[K] = make_double2(dk, b[GK]);
+            }
+            __syncwarp();
+            if constexpr (K > 0) { if (r == ((K - 1) & 7)) hdr[K - 1].x = dinv_prev; }
+            const double2 hd = hdr[K];
+            ok = ok && (hd.x > 0.0);
+            const double dinv = rb_rcp_pos(hd.x);
+            dinv_prev = dinv;
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3;
+            if constexpr (GK <= 0) n0 = -a0[K & 7] * dinv;
+            if constexpr (GK <= 1) n1 = -a1[K & 15] * dinv;
+            if constexpr (GK <= 2) n2 = -a2[K < 24 ? K : 0] * dinv;
+            n3 = -a3[K] * dinv;
+            // right-hand side: rows after K only (a finished row's multiplier is meaningless)
+            if constexpr (GK == 0) { if (r > RK) b[0] = fma(n0, hd.y, b[0]); b[1] = fma(n1, hd.y, b[1]); b[2] = fma(n2, hd.y, b[2]); b[3] = fma(n3, hd.y, b[3]); }
+            if constexpr (GK == 1) { if (r > RK) b[1] = fma(n1, hd.y, b[1]); b[2] = fma(n2, hd.y, b[2]); b[3] = fma(n3, hd.y, b[3]); }
+            if constexpr (GK == 2) { if (r > RK) b[2] = fma(n2, hd.y, b[2]); b[3] = fma(n3, hd.y, b[3]); }
+            if constexpr (GK == 3) { if (r > RK) b[3] = fma(n3, hd.y, b[3]); }
+            auto upd = [&](auto jc, double c) {
+                constexpr int J = decltype(jc)::value;
+                if constexpr (J < 8 && GK <= 0) a0[J & 7] = fma(n0, c, a0[J & 7]);
+                if constexpr (J < 16 && GK <= 1) a1[J & 15] = fma(n1, c, a1[J & 15]);
+                if constexpr (J < 24 && GK <= 2) a2[J < 24 ? J : 0] = fma(n2, c, a2[J < 24 ? J : 0]);
+                a3[J] = fma(n3, c, a3[J]);
+            };
+            if constexpr (((K + 1) & 1) && K + 1 < 32) upd(std::integral_constant<int, (K + 1) & 31>{}, Ls[COL + K + 1]);
+            rbq_for<((K + 2) & ~1) / 2, 16>([&](auto pc) {
+                constexpr int J = 2 * decltype(pc)::value;
+                const double2 c2 = *reinterpret_cast<const double2*>(Ls + COL + J);
+                upd(std::integral_constant<int, J>{}, c2.x);
+                upd(std::integral_constant<int, J + 1>{}, c2.y);
+            });
+        });
+        __syncwarp();
+        if (r == 7) hdr[31].x = dinv_prev;
+        __syncwarp();
+        // back substitution: x_i = (y_i - sum_{j > i} (l_ji d_i) x_j) / d_i; the lane reads its own four columns
+        double x0 = b[0], x1 = b[1], x2 = b[2], x3 = b[3];
+        const double di0 = hdr[r].x, di1 = hdr[r + 8].x, di2 = hdr[r + 16].x, di3 = hdr[r + 24].x;
+        rbq_for_down<31, 1>([&](auto ic) {
+            constexpr int I = decltype(ic)::value, GI = I >> 3, RI = I & 7;
+            const double mine = GI == 0 ? x0 * di0 : GI == 1 ? x1 * di1 : GI == 2 ? x2 * di2 : x3 * di3;
+            const double xi = __shfl_sync(FULL, mine, RI, 8);
+            if (r == RI) { if constexpr (GI == 0) x0 = xi; if constexpr (GI == 1) x1 = xi; if constexpr (GI == 2) x2 = xi; if constexpr (GI == 3) x3 = xi; }
+            // rows before I: every row of the groups below GI, rows r < RI of group GI
+            if constexpr (GI > 0) x0 = fma(-Ls[colbase[0] + I], xi, x0);
+            if constexpr (GI > 1) x1 = fma(-Ls[colbase[1] + I], xi, x1);
+            if constexpr (GI > 2) x2 = fma(-Ls[colbase[2] + I], xi, x2);
+            if (r < RI) {
+                const double c = Ls[colbase[GI] + I];
+                if constexpr (GI == 0) x0 = fma(-c, xi, x0);
+                if constexpr (GI == 1) x1 = fma(-c, xi, x1);
+                if constexpr (GI == 2) x2 = fma(-c, xi, x2);
+                if constexpr (GI == 3) x3 = fma(-c, xi, x3);
+            }
+        });
+        if (r == 0) x0 *= di0;
+        const bool live = s < in_group;
+        all_ok = all_ok && (ok || !live);
+        __syncwarp();                                        // every lane is done with the staged inputs' neighbours (ob = io)
+        if (live) {
+            ob[r * RBW_IOS + s] = ok ? x0 : rb_nan<double>();
+            ob[(r + 8) * RBW_IOS + s] = ok ? x1 : rb_nan<double>();
+            ob[(r + 16) * RBW_IOS + s] = ok ? x2 : rb_nan<double>();
+            ob[(r + 24) * RBW_IOS + s] = ok ? x3 : rb_nan<double>();
+        }
+        __syncwarp();
+        {
+            const int sj = lane / RBW_GROUP, ss = lane % RBW_GROUP;
+            if (s0 + ss < B) {
+#pragma unroll
+                for (int it = 0; it < 32 / (32 / RBW_GROUP); ++it) {
+                    const int i = it * (32 / RBW_GROUP) + sj;
+                    if (i < n) __stcs(qdd + (size_t)i * ld + s0 + ss, ob[i * RBW_IOS + ss]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (!all_ok && r == 0) atomicOr(status, RB_STATUS_NOT_SPD);
+}
 }  // namespace
 
 // qdd = FD(q, dq, tau) for a chain of n <= 32 joints whose model rows (rb_model.h layout) are at `model` on the device.
@@ -745,6 +1084,23 @@ cudaError_t rb_launch_warp_fd(const double* model, int n, const double* q, const
         configured[dev].store(true, std::memory_order_release);
     }
     const size_t groups = (B + RBW_GROUP - 1) / RBW_GROUP;
+#if RBW_QUARTER
+    // $RIGIDBODY_B200_WARP_FD=half selects rbh_fd_kernel (16 lanes per state in the matrix phase) for comparisons
+    static const bool use_half = [] { const char* e = getenv("RIGIDBODY_B200_WARP_FD"); return e && e[0] == 'h'; }();
+    if (!use_half) {
+        constexpr size_t qsmem = ((size_t)RBQ_WARPS * RBQ_PER_WARP + RBH_MODEL) * sizeof(double);
+        static_assert(qsmem <= 232448, "rbq_fd_kernel: more than 227 KB of shared memory");
+        static std::atomic<bool> qconfigured[64];
+        if (dev >= 0 && dev < 64 && !qconfigured[dev].load(std::memory_order_acquire)) {
+            cudaError_t e = cudaFuncSetAttribute(rbq_fd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+            if (e != cudaSuccess) return e;
+            qconfigured[dev].store(true, std::memory_order_release);
+        }
+        const size_t qwant = (groups + RBQ_WARPS - 1) / RBQ_WARPS;
+        rbq_fd_kernel<<<(unsigned)(qwant < (size_t)sms ? qwant : (size_t)sms), 32 * RBQ_WARPS, qsmem, st>>>(model, n, q, dq, tau, qdd, B, ld, status);
+        return cudaGetLastError();
+    }
+#endif
 #if RBW_HALF
     constexpr size_t hsmem = ((size_t)RBW_HWARPS * RBH_PER_WARP + RBH_MODEL) * sizeof(double);
     static std::atomic<bool> hconfigured[64];
