@@ -43,6 +43,9 @@
 #ifndef RBW_QUARTER
 #define RBW_QUARTER 1                     // 1 = eight lanes per state in the matrix phase (rbq_fd_kernel, the default)
 #endif
+#ifndef RBQ_MASKSCAN
+#define RBQ_MASKSCAN 1
+#endif
 #define RBW_LDL 34                        // row stride of the stored L columns: even, so pairs are 16-byte aligned
 #define RBW_IOS (RBW_GROUP + 1)           // padded stride of the staging rows
 
@@ -377,6 +380,39 @@ constexpr int RBH_MODEL = 24 * 32;                                        // blo
 __device__ __forceinline__ double up16(double v, int d) { return __shfl_up_sync(FULL, v, d, 16); }
 __device__ __forceinline__ double dn16(double v, int d) { return __shfl_down_sync(FULL, v, d, 16); }
 
+// Scans along the chain without selects: a lane whose source lane lies outside its 16-lane segment multiplies what
+// the shuffle returned (its own value) by 0.0, every other lane by 1.0 -- the add of a scan step becomes an FMA with a
+// per-lane mask, one FP64 instruction as before, and the compare + two FSELs per step disappear (they were 10 % of the
+// instructions the kernel executed; ptxas turns a predicated add back into selects).
+struct ScanMasks { double up[4], dn[4]; };
+__device__ __forceinline__ ScanMasks scan_masks(int r) {
+    ScanMasks m;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m.up[i] = r >= (1 << i) ? 1.0 : 0.0; m.dn[i] = r + (1 << i) < 16 ? 1.0 : 0.0; }
+    return m;
+}
+template <int K>
+__device__ __forceinline__ void prefix2p(double (&x0)[K], double (&x1)[K], const ScanMasks& m) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        double t = x0[c] + x1[c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t = fma(up16(t, 1 << i), m.up[i], t);
+        x0[c] = fma(up16(t, 1), m.up[0], x0[c]);
+        x1[c] += x0[c];
+    }
+}
+template <int K>
+__device__ __forceinline__ void suffix2p(double (&x0)[K], double (&x1)[K], const ScanMasks& m) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+        double t = x0[c] + x1[c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t = fma(dn16(t, 1 << i), m.dn[i], t);
+        x1[c] = fma(dn16(t, 1), m.dn[0], x1[c]);
+        x0[c] += x1[c];
+    }
+}
 // Inclusive prefix sums along the chain for the lane's two joints (x0: joint 2r, x1: joint 2r+1).
 template <int K>
 __device__ __forceinline__ void prefix2(double (&x0)[K], double (&x1)[K], int r) {
@@ -752,7 +788,7 @@ constexpr int rbq_colofs(int k) {
 constexpr int RBQ_COLS = 688;                         // = rbq_colofs(32)
 constexpr int RBQ_SS = RBQ_COLS + 64 + 2;             // state stride: = 2 mod 16 doubles, so the four states' 16-byte broadcasts hit four bank groups
 constexpr int RBQ_HS = 32 * 6 + 7 * 32 + 2;           // hand-over stride (screws + component-major I^c s and rhs), also = 2 mod 16
-constexpr int RBQ_IO = 3 * 32 * RBW_IOS;              // staged q, dq, tau; the results reuse the q part
+constexpr int RBQ_IO = 3 * 32 * RBW_IOS;              // staged q, dq, tau
 constexpr int RBQ_PER_WARP = 4 * RBQ_SS + RBQ_IO;
 static_assert(4 * RBQ_HS <= 4 * RBQ_SS, "hand-over buffers alias the column storage");
 static_assert(RBW_GROUP == 4, "rbq_fd_kernel factorises the four staged states together");
@@ -814,11 +850,24 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
     cross(p1, z1, v1);
     const double zq0[3] = {z0[0] * dq0, z0[1] * dq0, z0[2] * dq0}, zq1[3] = {z1[0] * dq1, z1[1] * dq1, z1[2] * dq1};
     double om0[3] = {zq0[0], zq0[1], zq0[2]}, om1[3] = {zq1[0], zq1[1], zq1[2]};
+    const ScanMasks sm = scan_masks(r);
+    
+#if RBQ_MASKSCAN
+    prefix2p<3>(om0, om1, sm);
+#else
     prefix2<3>(om0, om1, r);
+#endif
+
     double al0[3], al1[3];
     cross(om0, zq0, al0);
     cross(om1, zq1, al1);
+    
+#if RBQ_MASKSCAN
+    prefix2p<3>(al0, al1, sm);
+#else
     prefix2<3>(al0, al1, r);
+#endif
+
     double ac0[3], ac1[3];
     {
         double omp[3], alp[3], d[3], w1[3];
@@ -839,7 +888,13 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
         cross(al0, d1, ac1);
         cross_acc(om0, w1, ac1);
     }
+    
+#if RBQ_MASKSCAN
+    prefix2p<3>(ac0, ac1, sm);
+#else
     prefix2<3>(ac0, ac1, r);
+#endif
+
     double fw0[6], fw1[6], ci0[9], ci1[9];
     {
         const double2 m = mdl2(12), h0 = mdl2(13), h1 = mdl2(14), h2 = mdl2(15);
@@ -849,12 +904,24 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
         link_terms(R0, p0, m.x, ha, Ia, om0, al0, ac0, fw0, ci0);
         link_terms(R1, p1, m.y, hb, Ib, om1, al1, ac1, fw1, ci1);
     }
+    
+#if RBQ_MASKSCAN
+    suffix2p<6>(fw0, fw1, sm);
+#else
     suffix2<6>(fw0, fw1, r);
+#endif
+
     const double b0 = io[(2 * 32 + j0) * RBW_IOS + st]
                       - (z0[0] * fw0[3] + z0[1] * fw0[4] + z0[2] * fw0[5] + v0[0] * fw0[0] + v0[1] * fw0[1] + v0[2] * fw0[2]);
     const double b1 = io[(2 * 32 + j0 + 1) * RBW_IOS + st]
                       - (z1[0] * fw1[3] + z1[1] * fw1[4] + z1[2] * fw1[5] + v1[0] * fw1[0] + v1[1] * fw1[1] + v1[2] * fw1[2]);
+    
+#if RBQ_MASKSCAN
+    suffix2p<9>(ci0, ci1, sm);
+#else
     suffix2<9>(ci0, ci1, r);
+#endif
+
     const double2 mc = mdl2(22);
     double Fn0[3], Ff0[3], Fn1[3], Ff1[3];
     double2* S2 = reinterpret_cast<double2*>(Sb + j0 * 6);
@@ -866,6 +933,22 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
     F2[0 * 16] = make_double2(Fn0[0], Fn1[0]); F2[1 * 16] = make_double2(Fn0[1], Fn1[1]); F2[2 * 16] = make_double2(Fn0[2], Fn1[2]);
     F2[3 * 16] = make_double2(Ff0[0], Ff1[0]); F2[4 * 16] = make_double2(Ff0[1], Ff1[1]); F2[5 * 16] = make_double2(Ff0[2], Ff1[2]);
     F2[6 * 16] = make_double2(act0 ? b0 : 0.0, act1 ? b1 : 0.0);
+}
+
+// A broadcast read of shared memory that stays an 8-byte load: nvcc pairs adjacent 8-byte loads whose alignment it can
+// prove into one 16-byte load, and a 16-byte load is served a quarter of a warp at a time -- four wavefronts for the four
+// states' addresses where two 8-byte loads take one each (measured: 3.8 wavefronts per LDS.128 in the elimination).
+#ifndef RBQ_LDS64
+#define RBQ_LDS64 1
+#endif
+__device__ __forceinline__ double rbq_lds(const double* p) {
+#if RBQ_LDS64
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+#else
+    return *p;
+#endif
 }
 
 // compile-time loops with the index as a constant expression (register arrays of different lengths per row group)
@@ -886,7 +969,7 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
     double* msm = rbw_sm;                                    // [24][32] model constants, [22][*] = composite mass
     double* wsm = rbw_sm + RBH_MODEL + (size_t)w * RBQ_PER_WARP;
     double* io = wsm + 4 * RBQ_SS;                           // [3][32][RBW_IOS]
-    double* ob = io;                                         // results: the q part, dead after the chain phases
+    double* ob = wsm;                                        // results [32][RBW_IOS]: over the columns of L, dead after the back substitution
     if (w == 0) {                                            // model -> shared memory; idle joints: identity, no mass
         const bool act = lane < n;
         const double* row = model + (size_t)(act ? lane : 0) * 24;
@@ -914,23 +997,45 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
         colbase[gg] = (gg == 0 ? 34 * k : gg == 1 ? 272 + 26 * (k - 8) : gg == 2 ? 480 + 18 * (k - 16) : 624 + 8 * (k - 24)) - 8 * gg;
     }
 
+    // The trip count is the same for every warp of the grid (a warp whose last group does not exist repeats the grid's last
+    // group and stores nothing): control flow that depends only on kernel parameters lets the compiler prove the warp
+    // converged at every shuffle -- with a per-warp loop bound it re-materialised the member mask and tested for
+    // divergence before each of the ~450 shuffles of an iteration (6 % of the instructions executed).
     const size_t groups = (B + RBW_GROUP - 1) / RBW_GROUP;
+    const size_t per_sweep = (size_t)gridDim.x * RBQ_WARPS;
+    const size_t sweeps = (groups + per_sweep - 1) / per_sweep;
     bool all_ok = true;
-    for (size_t grp = (size_t)blockIdx.x * RBQ_WARPS + w; grp < groups; grp += (size_t)gridDim.x * RBQ_WARPS) {
-        const size_t s0 = grp * RBW_GROUP;
-        {
-            const int sj = lane / RBW_GROUP, ss = lane % RBW_GROUP;
-            const bool sin = s0 + ss < B;
+    // Staging: a group's q, dq, tau travel global -> shared as 8-byte asynchronous copies (zero-filled where the state or
+    // the joint does not exist), issued for the NEXT group as soon as the chain phases have consumed the current one, so
+    // the HBM latency hides behind the matrix phase (with plain loads at the top of the iteration it was 9.5 % of the
+    // kernel's stall samples).
+    auto stage = [&](size_t grp_) {
+        const size_t s0_ = grp_ * RBW_GROUP;
+        const int sj = lane / RBW_GROUP, ss = lane % RBW_GROUP;
+        const bool sin = s0_ + ss < B;
 #pragma unroll
-            for (int it = 0; it < 32 / (32 / RBW_GROUP); ++it) {
-                const int i = it * (32 / RBW_GROUP) + sj;
-                const bool ld_ok = sin && i < n;
-                const size_t off = (size_t)i * ld + s0 + ss;
-                io[(0 * 32 + i) * RBW_IOS + ss] = ld_ok ? __ldcs(q + off) : 0.0;
-                io[(1 * 32 + i) * RBW_IOS + ss] = ld_ok ? __ldcs(dq + off) : 0.0;
-                io[(2 * 32 + i) * RBW_IOS + ss] = ld_ok ? __ldcs(tau + off) : 0.0;
-            }
+        for (int it = 0; it < 32 / (32 / RBW_GROUP); ++it) {
+            const int i = it * (32 / RBW_GROUP) + sj;
+            const bool ld_ok = sin && i < n;
+            const size_t off = ld_ok ? (size_t)i * ld + s0_ + ss : 0;
+            const unsigned bytes = ld_ok ? 8u : 0u;
+            const unsigned d0 = (unsigned)__cvta_generic_to_shared(io + (0 * 32 + i) * RBW_IOS + ss);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0), "l"(q + off), "r"(bytes) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 32 * RBW_IOS * 8), "l"(dq + off), "r"(bytes) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 2 * 32 * RBW_IOS * 8), "l"(tau + off), "r"(bytes) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto group_of = [&](size_t sweep_) {
+        const size_t want = sweep_ * per_sweep + (size_t)blockIdx.x * RBQ_WARPS + w;
+        return want < groups ? want : groups - 1;
+    };
+    stage(group_of(0));
+    for (size_t sweep = 0; sweep < sweeps; ++sweep) {
+        const bool valid = sweep * per_sweep + (size_t)blockIdx.x * RBQ_WARPS + w < groups;
+        const size_t grp = group_of(sweep);
+        const size_t s0 = grp * RBW_GROUP;
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
         const int in_group = (int)(B - s0 < RBW_GROUP ? B - s0 : RBW_GROUP);
         // ================= chain phase, two states at a time (a state that does not exist is computed from zeros: q = dq =
@@ -941,6 +1046,7 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             rbq_chain_phase(msm, io, st, rh, n, g, wsm + st * RBQ_HS, wsm + st * RBQ_HS + 32 * 6);
         }
         __syncwarp();
+        if (sweep + 1 < sweeps) stage(group_of(sweep + 1));  // the staging buffer is free: fetch the next group
         // ================= matrix phase: lane (s, r) <-> rows r, r + 8, r + 16, r + 24 of state s
         double a0[8], a1[16], a2[24], a3[32], b[4];
         {
@@ -955,8 +1061,11 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             };
             rbq_for<0, 32>([&](auto jc) {
                 constexpr int J = decltype(jc)::value;
-                const double2* S2 = reinterpret_cast<const double2*>(Sq + J * 6);
-                const double2 s01 = S2[0], s23 = S2[1], s45 = S2[2];
+                // 8-byte broadcasts: the four states' addresses are one wavefront (a 16-byte load is served a quarter
+                // of a warp at a time: four wavefronts for the same four addresses, measured)
+                const double* Sj = Sq + J * 6;
+                const double2 s01 = make_double2(rbq_lds(Sj), rbq_lds(Sj + 1)), s23 = make_double2(rbq_lds(Sj + 2), rbq_lds(Sj + 3)),
+                              s45 = make_double2(rbq_lds(Sj + 4), rbq_lds(Sj + 5));
                 if constexpr (J < 8) a0[J] = dot6(s01, s23, s45, F0);
                 if constexpr (J < 16) a1[J] = dot6(s01, s23, s45, F1);
                 if constexpr (J < 24) a2[J] = dot6(s01, s23, s45, F2);
@@ -989,7 +1098,7 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             }
             __syncwarp();
             if constexpr (K > 0) { if (r == ((K - 1) & 7)) hdr[K - 1].x = dinv_prev; }
-            const double2 hd = hdr[K];
+            const double2 hd = make_double2(rbq_lds(Ls + RBQ_COLS + 2 * K), rbq_lds(Ls + RBQ_COLS + 2 * K + 1));
             ok = ok && (hd.x > 0.0);
             const double dinv = rb_rcp_pos(hd.x);
             dinv_prev = dinv;
@@ -1010,12 +1119,11 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
                 if constexpr (J < 24 && GK <= 2) a2[J < 24 ? J : 0] = fma(n2, c, a2[J < 24 ? J : 0]);
                 a3[J] = fma(n3, c, a3[J]);
             };
-            if constexpr (((K + 1) & 1) && K + 1 < 32) upd(std::integral_constant<int, (K + 1) & 31>{}, Ls[COL + K + 1]);
+            if constexpr (((K + 1) & 1) && K + 1 < 32) upd(std::integral_constant<int, (K + 1) & 31>{}, rbq_lds(Ls + COL + K + 1));
             rbq_for<((K + 2) & ~1) / 2, 16>([&](auto pc) {
                 constexpr int J = 2 * decltype(pc)::value;
-                const double2 c2 = *reinterpret_cast<const double2*>(Ls + COL + J);
-                upd(std::integral_constant<int, J>{}, c2.x);
-                upd(std::integral_constant<int, J + 1>{}, c2.y);
+                upd(std::integral_constant<int, J>{}, rbq_lds(Ls + COL + J));
+                upd(std::integral_constant<int, J + 1>{}, rbq_lds(Ls + COL + J + 1));
             });
         });
         __syncwarp();
@@ -1042,9 +1150,9 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             }
         });
         if (r == 0) x0 *= di0;
-        const bool live = s < in_group;
+        const bool live = valid && s < in_group;
         all_ok = all_ok && (ok || !live);
-        __syncwarp();                                        // every lane is done with the staged inputs' neighbours (ob = io)
+        __syncwarp();                                        // every lane is done with the stored columns (ob lies over them)
         if (live) {
             ob[r * RBW_IOS + s] = ok ? x0 : rb_nan<double>();
             ob[(r + 8) * RBW_IOS + s] = ok ? x1 : rb_nan<double>();
@@ -1054,7 +1162,7 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
         __syncwarp();
         {
             const int sj = lane / RBW_GROUP, ss = lane % RBW_GROUP;
-            if (s0 + ss < B) {
+            if (valid && s0 + ss < B) {
 #pragma unroll
                 for (int it = 0; it < 32 / (32 / RBW_GROUP); ++it) {
                     const int i = it * (32 / RBW_GROUP) + sj;

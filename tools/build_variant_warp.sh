@@ -7,5 +7,5 @@ NAME=$1; FLAGS=$2
 make -s -j8 -C "$C"
 rm -rf "$C/build_$NAME"; mkdir -p "$C/build_$NAME" "$ROOT/var"
 cp "$C"/build/*.o "$C/build_$NAME/"; rm -f "$C/build_$NAME/rb_kernels_warp.o"
-make -s -j8 -C "$C" B=build_$NAME OUT=$ROOT/var/librb_$NAME.so EXTRA_NVFLAGS="$FLAGS -Xptxas -v" 2>&1 | grep -A2 "rbh_fd_kernel" | grep "spill\|Used" | sed 's/ptxas info    : //' | cut -c1-140
+make -s -j8 -C "$C" B=build_$NAME OUT=$ROOT/var/librb_$NAME.so EXTRA_NVFLAGS="$FLAGS -Xptxas -v" 2>&1 | grep -A2 "rb[hq]_fd_kernel" | grep "spill\|Used" | sed 's/ptxas info    : //' | cut -c1-140
 rm -rf "$C/build_$NAME"
