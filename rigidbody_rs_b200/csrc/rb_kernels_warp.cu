@@ -43,9 +43,6 @@
 #ifndef RBW_QUARTER
 #define RBW_QUARTER 1                     // 1 = eight lanes per state in the matrix phase (rbq_fd_kernel, the default)
 #endif
-#ifndef RBQ_MASKSCAN
-#define RBQ_MASKSCAN 1
-#endif
 #define RBW_LDL 34                        // row stride of the stored L columns: even, so pairs are 16-byte aligned
 #define RBW_IOS (RBW_GROUP + 1)           // padded stride of the staging rows
 
@@ -395,10 +392,12 @@ template <int K>
 __device__ __forceinline__ void prefix2p(double (&x0)[K], double (&x1)[K], const ScanMasks& m) {
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-        double t = x0[c] + x1[c];
+        const double own = x0[c] + x1[c];
+        double t = own;
 #pragma unroll
         for (int i = 0; i < 4; ++i) t = fma(up16(t, 1 << i), m.up[i], t);
-        x0[c] = fma(up16(t, 1), m.up[0], x0[c]);
+        x0[c] += t - own;                    // the lanes before this one: inclusive total minus the own pair (no fifth shuffle;
+                                             // the difference is off by at most half an ulp of the total)
         x1[c] += x0[c];
     }
 }
@@ -406,10 +405,11 @@ template <int K>
 __device__ __forceinline__ void suffix2p(double (&x0)[K], double (&x1)[K], const ScanMasks& m) {
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-        double t = x0[c] + x1[c];
+        const double own = x0[c] + x1[c];
+        double t = own;
 #pragma unroll
         for (int i = 0; i < 4; ++i) t = fma(dn16(t, 1 << i), m.dn[i], t);
-        x1[c] = fma(dn16(t, 1), m.dn[0], x1[c]);
+        x1[c] += t - own;
         x0[c] += x1[c];
     }
 }
@@ -786,12 +786,36 @@ constexpr int rbq_colofs(int k) {
     return k < 8 ? 34 * k : k < 16 ? 272 + 26 * (k - 8) : k < 24 ? 480 + 18 * (k - 16) : 624 + 8 * (k - 24);
 }
 constexpr int RBQ_COLS = 688;                         // = rbq_colofs(32)
-constexpr int RBQ_SS = RBQ_COLS + 64 + 2;             // state stride: = 2 mod 16 doubles, so the four states' 16-byte broadcasts hit four bank groups
-constexpr int RBQ_HS = 32 * 6 + 7 * 32 + 2;           // hand-over stride (screws + component-major I^c s and rhs), also = 2 mod 16
+// The four states' areas are 2 doubles (mod 16) apart: an 8-byte broadcast (one address per state) touches four different
+// bank pairs = one wavefront.  (Offsets 0, 8, 2, 10 mod 16, which also make the column stores conflict-free, measured 17 %
+// SLOWER in time and 7 % in cycles although the wavefront count fell by 10 %: profiles/r2_kbench_chain32.jsonl, qB.)
+constexpr int RBQ_SS = RBQ_COLS + 64;                 // columns + headers of one state
+constexpr int RBQ_HS = 32 * 6 + 7 * 32;               // hand-over of one state: screws + component-major I^c s and rhs
+__device__ __forceinline__ constexpr int rbq_bank_shift(int st) { return 2 * st; }
+constexpr int RBQ_REGION = 4 * RBQ_SS + 32;
 constexpr int RBQ_IO = 3 * 32 * RBW_IOS;              // staged q, dq, tau
-constexpr int RBQ_PER_WARP = 4 * RBQ_SS + RBQ_IO;
-static_assert(4 * RBQ_HS <= 4 * RBQ_SS, "hand-over buffers alias the column storage");
+constexpr int RBQ_PER_WARP = RBQ_REGION + RBQ_IO;
+static_assert(RBQ_SS % 16 == 0 && RBQ_HS % 16 == 0 && RBQ_HS <= RBQ_SS, "hand-over buffers alias the column storage");
 static_assert(RBW_GROUP == 4, "rbq_fd_kernel factorises the four staged states together");
+
+// A broadcast read of shared memory that stays an 8-byte load: nvcc pairs adjacent 8-byte loads whose alignment it can
+// prove into one 16-byte load, and a 16-byte load is served a quarter of a warp at a time -- four wavefronts for the four
+// states' addresses where two 8-byte loads take one each (measured: 3.8 wavefronts per LDS.128 in the elimination).
+#ifndef RBQ_LDS64
+#define RBQ_LDS64 1
+#endif
+__device__ __forceinline__ void rbq_sts(double* p, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ double rbq_lds(const double* p) {
+#if RBQ_LDS64
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
 
 // Chain phase of one state on 16 lanes (lane r <-> joints 2r, 2r + 1): world poses by a prefix product, the recursions of
 // rnea / crba as sums along the chain (see the file header), then the hand-over: screws to Sb[32][6], I^c s and
@@ -800,7 +824,8 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
                                                 const double (&g)[3], double* __restrict__ Sb, double* __restrict__ Fb) {
     const int j0 = 2 * r;
     const bool act0 = j0 < n, act1 = j0 + 1 < n;
-    auto mdl2 = [&](int e) { return *reinterpret_cast<const double2*>(msm + e * 32 + j0); };
+    // model constants [e][parity][16]: the lane's two joints are two 8-byte loads of 16 consecutive doubles each
+    auto mdl2 = [&](int e) { return make_double2(msm[e * 32 + r], msm[e * 32 + 16 + r]); };
     double R0[9], p0[3], R1[9], p1[3];
     {
         double sn, cs;
@@ -852,21 +877,13 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
     double om0[3] = {zq0[0], zq0[1], zq0[2]}, om1[3] = {zq1[0], zq1[1], zq1[2]};
     const ScanMasks sm = scan_masks(r);
     
-#if RBQ_MASKSCAN
     prefix2p<3>(om0, om1, sm);
-#else
-    prefix2<3>(om0, om1, r);
-#endif
 
     double al0[3], al1[3];
     cross(om0, zq0, al0);
     cross(om1, zq1, al1);
     
-#if RBQ_MASKSCAN
     prefix2p<3>(al0, al1, sm);
-#else
-    prefix2<3>(al0, al1, r);
-#endif
 
     double ac0[3], ac1[3];
     {
@@ -889,11 +906,7 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
         cross_acc(om0, w1, ac1);
     }
     
-#if RBQ_MASKSCAN
     prefix2p<3>(ac0, ac1, sm);
-#else
-    prefix2<3>(ac0, ac1, r);
-#endif
 
     double fw0[6], fw1[6], ci0[9], ci1[9];
     {
@@ -905,22 +918,14 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
         link_terms(R1, p1, m.y, hb, Ib, om1, al1, ac1, fw1, ci1);
     }
     
-#if RBQ_MASKSCAN
     suffix2p<6>(fw0, fw1, sm);
-#else
-    suffix2<6>(fw0, fw1, r);
-#endif
 
     const double b0 = io[(2 * 32 + j0) * RBW_IOS + st]
                       - (z0[0] * fw0[3] + z0[1] * fw0[4] + z0[2] * fw0[5] + v0[0] * fw0[0] + v0[1] * fw0[1] + v0[2] * fw0[2]);
     const double b1 = io[(2 * 32 + j0 + 1) * RBW_IOS + st]
                       - (z1[0] * fw1[3] + z1[1] * fw1[4] + z1[2] * fw1[5] + v1[0] * fw1[0] + v1[1] * fw1[1] + v1[2] * fw1[2]);
     
-#if RBQ_MASKSCAN
     suffix2p<9>(ci0, ci1, sm);
-#else
-    suffix2<9>(ci0, ci1, r);
-#endif
 
     const double2 mc = mdl2(22);
     double Fn0[3], Ff0[3], Fn1[3], Ff1[3];
@@ -933,22 +938,6 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
     F2[0 * 16] = make_double2(Fn0[0], Fn1[0]); F2[1 * 16] = make_double2(Fn0[1], Fn1[1]); F2[2 * 16] = make_double2(Fn0[2], Fn1[2]);
     F2[3 * 16] = make_double2(Ff0[0], Ff1[0]); F2[4 * 16] = make_double2(Ff0[1], Ff1[1]); F2[5 * 16] = make_double2(Ff0[2], Ff1[2]);
     F2[6 * 16] = make_double2(act0 ? b0 : 0.0, act1 ? b1 : 0.0);
-}
-
-// A broadcast read of shared memory that stays an 8-byte load: nvcc pairs adjacent 8-byte loads whose alignment it can
-// prove into one 16-byte load, and a 16-byte load is served a quarter of a warp at a time -- four wavefronts for the four
-// states' addresses where two 8-byte loads take one each (measured: 3.8 wavefronts per LDS.128 in the elimination).
-#ifndef RBQ_LDS64
-#define RBQ_LDS64 1
-#endif
-__device__ __forceinline__ double rbq_lds(const double* p) {
-#if RBQ_LDS64
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-    return v;
-#else
-    return *p;
-#endif
 }
 
 // compile-time loops with the index as a constant expression (register arrays of different lengths per row group)
@@ -968,27 +957,28 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double* msm = rbw_sm;                                    // [24][32] model constants, [22][*] = composite mass
     double* wsm = rbw_sm + RBH_MODEL + (size_t)w * RBQ_PER_WARP;
-    double* io = wsm + 4 * RBQ_SS;                           // [3][32][RBW_IOS]
+    double* io = wsm + RBQ_REGION;                           // [3][32][RBW_IOS]
     double* ob = wsm;                                        // results [32][RBW_IOS]: over the columns of L, dead after the back substitution
     if (w == 0) {                                            // model -> shared memory; idle joints: identity, no mass
         const bool act = lane < n;
         const double* row = model + (size_t)(act ? lane : 0) * 24;
         double mc[1] = {act ? row[12] : 0.0};
         suffix_sum<1>(mc, lane);
+        const int slot = (lane & 1) * 16 + (lane >> 1);      // [parity][joint / 2]
 #pragma unroll
-        for (int e = 0; e < 13; ++e) msm[e * 32 + lane] = act ? row[e] : ((e == 0 || e == 4 || e == 8) ? 1.0 : 0.0);
+        for (int e = 0; e < 13; ++e) msm[e * 32 + slot] = act ? row[e] : ((e == 0 || e == 4 || e == 8) ? 1.0 : 0.0);
 #pragma unroll
-        for (int e = 0; e < 9; ++e) msm[(13 + e) * 32 + lane] = act ? row[14 + e] : 0.0;
-        msm[22 * 32 + lane] = mc[0];
+        for (int e = 0; e < 9; ++e) msm[(13 + e) * 32 + slot] = act ? row[14 + e] : 0.0;
+        msm[22 * 32 + slot] = mc[0];
     }
     __syncthreads();
     const double g[3] = {model[(size_t)n * 24], model[(size_t)n * 24 + 1], model[(size_t)n * 24 + 2]};
     // chain phase: half h of the warp, lane rh of 16;  matrix phase: state s of the group, lane r of 8
     const int h = lane >> 4, rh = lane & 15;
     const int s = lane >> 3, r = lane & 7;
-    double* Ls = wsm + s * RBQ_SS;                           // this state's columns of L D
+    double* Ls = wsm + s * RBQ_SS + rbq_bank_shift(s);       // this state's columns of L D
     double2* hdr = reinterpret_cast<double2*>(Ls + RBQ_COLS);  // [32] {d_k (later 1 / d_k), y_k}
-    const double* Sq = wsm + s * RBQ_HS;                     // hand-over of state s: screws [32][6] ...
+    const double* Sq = wsm + s * RBQ_HS + rbq_bank_shift(s); // hand-over of state s: screws [32][6] ...
     const double* Fq = Sq + 32 * 6;                          // ... and [7][32] I^c s (6 components) and tau - bias
     int colbase[4];                                          // column r + 8 g of the lane's rows: entry of row i at colbase[g] + i
 #pragma unroll
@@ -1043,7 +1033,8 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
 #pragma unroll 1
         for (int st2 = 0; st2 < 4; st2 += 2) {
             const int st = st2 + h;
-            rbq_chain_phase(msm, io, st, rh, n, g, wsm + st * RBQ_HS, wsm + st * RBQ_HS + 32 * 6);
+            double* ho = wsm + st * RBQ_HS + rbq_bank_shift(st);
+            rbq_chain_phase(msm, io, st, rh, n, g, ho, ho + 32 * 6);
         }
         __syncwarp();
         if (sweep + 1 < sweeps) stage(group_of(sweep + 1));  // the staging buffer is free: fetch the next group
@@ -1094,7 +1085,8 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             Ls[COL + r + 24] = a3[K];
             if (r == RK) {
                 const double dk = GK == 0 ? a0[K & 7] : GK == 1 ? a1[K & 15] : GK == 2 ? a2[K < 24 ? K : 0] : a3[K];
-                hdr[K] = make_double2(dk, b[GK]);
+                rbq_sts(Ls + RBQ_COLS + 2 * K, dk);          // two 8-byte stores: one wavefront each (a 16-byte store by four lanes: four)
+                rbq_sts(Ls + RBQ_COLS + 2 * K + 1, b[GK]);
             }
             __syncwarp();
             if constexpr (K > 0) { if (r == ((K - 1) & 7)) hdr[K - 1].x = dinv_prev; }
