@@ -221,6 +221,40 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def bare_copy_ms(up_bytes, down_bytes, reps, dev, barrier):
+    """Milliseconds one rank needs to move `up_bytes` host -> device and `down_bytes` device -> host at the same time with
+    plain pinned copies (no kernel): the ceiling of the end-to-end figure.  Collective: every rank calls it; allocation and
+    a warm-up pass come first, then a barrier, then the timed passes -- so the ranks really compete for the host's memory."""
+    cap, piece = 2 << 30, 64 << 20
+    nu, nd = max(1, min(cap, up_bytes)), max(1, min(cap, down_bytes))
+    hu = torch.empty(nu, dtype=torch.uint8, pin_memory=True); du = torch.empty(nu, dtype=torch.uint8, device=dev)
+    hd = torch.empty(nd, dtype=torch.uint8, pin_memory=True); dd = torch.zeros(nd, dtype=torch.uint8, device=dev)
+    hu.fill_(1)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def one_pass():
+        with torch.cuda.stream(s_up):
+            for off in range(0, up_bytes, piece):
+                ho = off % nu; ln = min(piece, up_bytes - off, nu - ho)
+                du[ho:ho + ln].copy_(hu[ho:ho + ln], non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            for off in range(0, down_bytes, piece):
+                ho = off % nd; ln = min(piece, down_bytes - off, nd - ho)
+                hd[ho:ho + ln].copy_(dd[ho:ho + ln], non_blocking=True)
+        s_up.synchronize(); s_dn.synchronize()
+
+    one_pass()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    barrier()
+    del hu, hd, du, dd
+    return ms
+
+
 def fp64_roofline(kernel, ms, units, instr_per_unit, flops_executed_per_unit, alg_flops_per_unit, bytes_per_unit,
                   fp64_peak, peak_note, hbm_peak, hbm_src, traffic=None, traffic_src=None, instr_src="static SASS count"):
     """The roofline object of one FP64-pipe-bound kernel.  `frac` is the share of the FP64 pipe's issue slots the launch
@@ -375,18 +409,20 @@ def run_ours(args, rank, local_rank, world):
     # the host results equal the device-resident ones: qdd bit for bit, tau to rounding (fused kernel)
     same = bool(np.array_equal(htau[:, :4096], tau[:, :4096].cpu().numpy())) and bool(np.array_equal(hout[n:], hqdd)) \
         and float(np.abs(hout[:n] - htau).max() / max(1.0, np.abs(htau).max())) < 1e-12
-    # the ceiling: the same bytes, both directions at once, pinned memory, no kernel -- every rank at the same time
-    barrier()
-    cu, cd = mb.copy_peak(up_b, down_b, 3)
-    barrier()
-    ceil_ms = max_over_ranks(up_b / cu / 1e6, dev)
+    # the ceiling: the same bytes, both directions at once, pinned memory, no kernel -- every rank at the same time.
+    # Buffers are allocated and warmed BEFORE the barrier: pinning 4 GB takes about a second and the ranks' allocations
+    # serialise in the kernel, so a probe that allocates inside its timed call (multibody_gpu_measure_copy_peak, round 2's
+    # first version) let the ranks' passes drift apart until nobody competed with anybody -- 215 GB/s "ceilings" for 8
+    # processes on a host whose DRAM serves about 100 GB/s of H2D next to 50 GB/s of D2H.
+    ceil_ms = max_over_ranks(bare_copy_ms(up_b, down_b, 3, dev, barrier), dev)
     e2e = {"value": e2e_units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": up_b, "d2h_bytes_per_step": down_b,
            "states_per_gpu": Be, "steps": e2e_steps, "ms_per_step": e2e_ms,
            "h2d_GBs": world * up_b / e2e_ms / 1e6, "d2h_GBs": world * down_b / e2e_ms / 1e6,
            "copy_ceiling": {"h2d_GBs": world * up_b / ceil_ms / 1e6, "d2h_GBs": world * down_b / ceil_ms / 1e6, "ms_per_step": ceil_ms,
                             "evals_per_s": e2e_units / (ceil_ms * 1e-3),
-                            "how": "multibody_gpu_measure_copy_peak: the same bytes per direction from/to pinned host memory, both directions at "
-                                   "once, no kernel, all ranks at the same time (max over ranks)"},
+                            "how": "the same bytes per direction from / to pinned host memory (buffers of up to 2 GiB walked front to back, "
+                                   "64 MiB copies, two streams: both directions at once), no kernel; buffers pinned before a barrier, then all "
+                                   "ranks copy at the same time; max over ranks of the mean pass"},
            "frac_of_copy_ceiling": ceil_ms / e2e_ms,
            "api": "Multibody.rnea_fd on pinned numpy arrays -> multibody_rnea_fd_batch(RB_MEM_HOST), one process per GPU: q, dq, ddq, tau_in up, tau and qdd down",
            "matches_device_path": same,
@@ -499,15 +535,21 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         ms_cr, ms_cf = max_over_ranks(tr / ksteps, dev), max_over_ranks(tf / ksteps, dev)
         c_units = sum_over_ranks(2.0 * Bc, dev)
-        prf, prr = profiled("rbh_fd_kernel"), profiled("rb_long_rnea_kernel")
+        prf, prr = profiled("rbq_fd_kernel"), profiled("rb_long_rnea_kernel")
+
+        def scaled(pr_):      # DRAM bytes of this launch, scaled per state from the committed 2^20-state capture
+            return (pr_["bytes"] / (1 << 20) * Bc, pr_["source"] + f" (per state, x {Bc} states)") if pr_ else (None, None)
         cfg_chain32 = {"metric": "chain32 RNEA+FD evals/sec (fp64)", "value": c_units / ((ms_cr + ms_cf) * 1e-3), "unit": UNIT,
                        "ms_per_step": ms_cr + ms_cf, "scaling": "strong", "states": args.chain32_states, "states_per_gpu": Bc, "n_joints": nc,
-                       "kernel_variant": mc.kernel_variant, "step": "1 rb_long_rnea_kernel launch + 1 rbh_fd_kernel launch over all states",
-                       "roofline": fp64_roofline("rbh_fd_kernel", ms_cf, float(Bc), prf["fp64_thread_instr"] / (1 << 20) if prf and "fp64_thread_instr" in prf else 1130.0 * 16,
-                                                 None, 53800.0, 1024.0, fp64_peak, peak_note, hbm_peak, hbm_src, None, prf["source"] if prf else None,
-                                                 "FP64 instructions per state over the 16 lanes that own it (1130 warp instructions per state, ncu)"),
+                       "kernel_variant": mc.kernel_variant, "step": "1 rb_long_rnea_kernel launch + 1 rbq_fd_kernel launch over all states",
+                       "roofline": fp64_roofline("rbq_fd_kernel", ms_cf, float(Bc), prf["fp64_thread_instr"] / (1 << 20) if prf and "fp64_thread_instr" in prf else 908.0 * 32,
+                                                 prf["fp64_thread_flops"] / (1 << 20) if prf and "fp64_thread_flops" in prf else None,
+                                                 53800.0, 1024.0, fp64_peak, peak_note, hbm_peak, hbm_src, *scaled(prf),
+                                                 "FP64-pipe instruction slots per state: warp instructions x 32 lanes / states of the capture (8 lanes own a state in "
+                                                 "the matrix phase, 16 in the chain phase; idle triangle lanes count as used slots)"),
                        "roofline_rnea": fp64_roofline("rb_long_rnea_kernel", ms_cr, float(Bc), prr["fp64_thread_instr"] / (1 << 20) if prr and "fp64_thread_instr" in prr else 3626.0,
-                                                      None, 9476.0, 1024.0, fp64_peak, peak_note, hbm_peak, hbm_src, None, prr["source"] if prr else None)}
+                                                      prr["fp64_thread_flops"] / (1 << 20) if prr and "fp64_thread_flops" in prr else None,
+                                                      9476.0, 1024.0, fp64_peak, peak_note, hbm_peak, hbm_src, *scaled(prr))}
         del cq, cdq, cx, cin, co1, co2
 
     line = {
