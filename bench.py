@@ -225,6 +225,7 @@ def bare_copy_ms(up_bytes, down_bytes, reps, dev, barrier):
     """Milliseconds one rank needs to move `up_bytes` host -> device and `down_bytes` device -> host at the same time with
     plain pinned copies (no kernel): the ceiling of the end-to-end figure.  Collective: every rank calls it; allocation and
     a warm-up pass come first, then a barrier, then the timed passes -- so the ranks really compete for the host's memory."""
+    import torch
     cap, piece = 2 << 30, 64 << 20
     nu, nd = max(1, min(cap, up_bytes)), max(1, min(cap, down_bytes))
     hu = torch.empty(nu, dtype=torch.uint8, pin_memory=True); du = torch.empty(nu, dtype=torch.uint8, device=dev)
