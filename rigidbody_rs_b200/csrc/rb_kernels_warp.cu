@@ -214,12 +214,18 @@ constexpr int rbq_colofs(int k) {
     return k < 8 ? 34 * k : k < 16 ? 272 + 26 * (k - 8) : k < 24 ? 480 + 18 * (k - 16) : 624 + 8 * (k - 24);
 }
 constexpr int RBQ_COLS = 688;                         // = rbq_colofs(32)
-// The four states' areas are 2 doubles (mod 16) apart: an 8-byte broadcast (one address per state) touches four different
-// bank pairs = one wavefront.  (Offsets 0, 8, 2, 10 mod 16, which also make the column stores conflict-free, measured 17 %
-// SLOWER in time and 7 % in cycles although the wavefront count fell by 10 %: profiles/r2_kbench_chain32.jsonl, qB.)
+// The four states' column areas are 3 doubles (mod 16) apart: an 8-byte broadcast (one address per state) touches four
+// different bank pairs = one wavefront, and the back substitution's column reads (lane r of a state reads every 34th /
+// 26th / 18th double: even bank pairs) interleave with the neighbouring state's (odd bank pairs).  Measured with the
+// team barriers in place (deterministic timing, profiles/r2_kbench_chain32.jsonl): odd offsets 3, 5, 7, 9 -> 3.26 ms,
+// even offsets 2, 4, 6 -> 3.36 ms, offset 1 -> 3.62 ms, offsets 0, 8, 2, 10 (conflict-free column stores) -> 3.59 ms.
+// Nothing in the column area is accessed 16 bytes at a time, so the odd offset costs no alignment.
 constexpr int RBQ_SS = RBQ_COLS + 64;                 // columns + headers of one state
 constexpr int RBQ_HS = 32 * 6 + 7 * 32;               // hand-over of one state: screws + component-major I^c s and rhs
-__device__ __forceinline__ constexpr int rbq_bank_shift(int st) { return 2 * st; }
+#ifndef RBQ_SHIFT
+#define RBQ_SHIFT 3
+#endif
+__device__ __forceinline__ constexpr int rbq_bank_shift(int st) { return RBQ_SHIFT * st; }
 constexpr int RBQ_REGION = 4 * RBQ_SS + 32;
 constexpr int RBQ_IO = 3 * 32 * RBW_IOS;              // staged q, dq, tau
 constexpr int RBQ_PER_WARP = RBQ_REGION + RBQ_IO;
@@ -368,6 +374,9 @@ __device__ __forceinline__ void rbq_chain_phase(const double* __restrict__ msm, 
     F2[6 * 16] = make_double2(act0 ? b0 : 0.0, act1 ? b1 : 0.0);
 }
 
+#ifndef RBQ_TEAMS
+#define RBQ_TEAMS 2
+#endif
 // compile-time loops with the index as a constant expression (register arrays of different lengths per row group)
 template <int I, int E, class F>
 __device__ __forceinline__ void rbq_for(F&& f) {
@@ -405,8 +414,8 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
     const int h = lane >> 4, rh = lane & 15;
     const int s = lane >> 3, r = lane & 7;
     double* Ls = wsm + s * RBQ_SS + rbq_bank_shift(s);       // this state's columns of L D
-    double2* hdr = reinterpret_cast<double2*>(Ls + RBQ_COLS);  // [32] {d_k (later 1 / d_k), y_k}
-    const double* Sq = wsm + s * RBQ_HS + rbq_bank_shift(s); // hand-over of state s: screws [32][6] ...
+    // Ls[RBQ_COLS + 2 k], Ls[RBQ_COLS + 2 k + 1]: header of column k = {d_k (later 1 / d_k), y_k}
+    const double* Sq = wsm + s * RBQ_HS + 2 * s; // hand-over of state s: screws [32][6] ...
     const double* Fq = Sq + 32 * 6;                          // ... and [7][32] I^c s (6 components) and tau - bias
     int colbase[4];                                          // column r + 8 g of the lane's rows: entry of row i at colbase[g] + i
 #pragma unroll
@@ -454,14 +463,20 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
         const size_t grp = group_of(sweep);
         const size_t s0 = grp * RBW_GROUP;
         asm volatile("cp.async.wait_all;" ::: "memory");
+#if RBQ_TEAMS
+        // teams of RBQ_WARPS / RBQ_TEAMS warps meet at a named barrier at the top of every sweep: a team streams one copy of
+        // the code through the instruction cache, different teams drift apart and mix their phases on the pipes
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + w / (RBQ_WARPS / RBQ_TEAMS)), "n"(32 * (RBQ_WARPS / RBQ_TEAMS)) : "memory");
+#else
         __syncwarp();
+#endif
         const int in_group = (int)(B - s0 < RBW_GROUP ? B - s0 : RBW_GROUP);
         // ================= chain phase, two states at a time (a state that does not exist is computed from zeros: q = dq =
         // tau = 0 were staged for it, its matrix is that of the zero pose and nothing of it is stored)
 #pragma unroll 1
         for (int st2 = 0; st2 < 4; st2 += 2) {
             const int st = st2 + h;
-            double* ho = wsm + st * RBQ_HS + rbq_bank_shift(st);
+            double* ho = wsm + st * RBQ_HS + 2 * st;
             rbq_chain_phase(msm, io, st, rh, n, g, ho, ho + 32 * 6);
         }
         __syncwarp();
@@ -517,7 +532,7 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
                 rbq_sts(Ls + RBQ_COLS + 2 * K + 1, b[GK]);
             }
             __syncwarp();
-            if constexpr (K > 0) { if (r == ((K - 1) & 7)) hdr[K - 1].x = dinv_prev; }
+            if constexpr (K > 0) { if (r == ((K - 1) & 7)) Ls[RBQ_COLS + 2 * (K - 1)] = dinv_prev; }
             const double2 hd = make_double2(rbq_lds(Ls + RBQ_COLS + 2 * K), rbq_lds(Ls + RBQ_COLS + 2 * K + 1));
             ok = ok && (hd.x > 0.0);
             const double dinv = rb_rcp_pos(hd.x);
@@ -547,11 +562,11 @@ rbq_fd_kernel(const double* __restrict__ model, int n, const double* __restrict_
             });
         });
         __syncwarp();
-        if (r == 7) hdr[31].x = dinv_prev;
+        if (r == 7) Ls[RBQ_COLS + 2 * 31] = dinv_prev;
         __syncwarp();
         // back substitution: x_i = (y_i - sum_{j > i} (l_ji d_i) x_j) / d_i; the lane reads its own four columns
         double x0 = b[0], x1 = b[1], x2 = b[2], x3 = b[3];
-        const double di0 = hdr[r].x, di1 = hdr[r + 8].x, di2 = hdr[r + 16].x, di3 = hdr[r + 24].x;
+        const double di0 = Ls[RBQ_COLS + 2 * r], di1 = Ls[RBQ_COLS + 2 * (r + 8)], di2 = Ls[RBQ_COLS + 2 * (r + 16)], di3 = Ls[RBQ_COLS + 2 * (r + 24)];
         rbq_for_down<31, 1>([&](auto ic) {
             constexpr int I = decltype(ic)::value, GI = I >> 3, RI = I & 7;
             const double mine = GI == 0 ? x0 * di0 : GI == 1 ? x1 * di1 : GI == 2 ? x2 * di2 : x3 * di3;
