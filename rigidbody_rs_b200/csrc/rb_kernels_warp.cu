@@ -29,7 +29,8 @@
 // History (numbers: 32-joint chain, 2^20 states on one B200; profiles/r1_kbench_chain32_warp_fd.jsonl,
 // profiles/r2_kbench_chain32.jsonl): a warp per state (lane = joint = row) 0.148 G evals/s; half a warp per state in both
 // phases 0.224; eight lanes per state in the matrix phase 0.268; warp-uniform loop bounds, mask-FMA scans, 8-byte
-// broadcasts, asynchronous staging, no fifth scan shuffle 0.308.  The two older kernels live in
+// broadcasts, asynchronous staging, no fifth scan shuffle 0.308; team barriers, odd offset between the states' column
+// areas 0.322 (17.3 TFLOP/s by SURVEY 8d flops = 0.51 of the measured FP64 peak).  The two older kernels live in
 // experiments/rb_warp_fd_old.cuh (build with -DRBW_OLD_KERNELS=1; $RIGIDBODY_B200_WARP_FD=half selects the second).
 #include <atomic>
 #include <cstdlib>
