@@ -267,7 +267,7 @@ def fd_mp(model, q, dq, tau, dps=40, return_cond=False):
     """mpmath evaluation of forward dynamics for ONE state: the composition SURVEY.md 3.3 defines,
     qdd = H(q)^-1 (tau - rnea(q, dq, 0)), with H built column by column from the same `dps`-digit recursion
     (H e_j = rnea(q, 0, e_j) - rnea(q, 0, 0), multibody.rs:111-153) and the system solved at `dps` digits: the value every
-    fp64 path (oracle LL^T, CUDA LDL^T, half-warp elimination) is an approximation OF.  With return_cond also the
+    fp64 path (oracle LL^T, CUDA LDL^T, quarter-warp elimination) is an approximation OF.  With return_cond also the
     2-norm condition number of H (fp64 is plenty for that)."""
     import mpmath as mp
     mp.mp.dps = dps

@@ -8,7 +8,7 @@
 //     spills are private, interleaved per thread, hence coalesced);
 //   * forward dynamics is not here: H (528 doubles at N = 32) cannot be held by a thread, and a 400 KB unrolled
 //     "CRBA to HBM" kernel plus a tile solver ran at 0.089 G evals/s.  The run-time-n family's lane-per-joint kernels
-//     (rb_kernels_warp.cu, 0.218 G evals/s) serve it through the fallback table.
+//     (rb_kernels_warp.cu, 0.32 G evals/s) serve it through the fallback table.
 #pragma once
 #include "rb_kernels.cuh"
 #ifndef RB_DEVICE_ONLY

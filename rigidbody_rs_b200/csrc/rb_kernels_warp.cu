@@ -199,8 +199,8 @@ __device__ __forceinline__ void comp_times_screw(double mc, const double (&ci)[9
 #endif
 
 // ------------------------------------------------------------------ a quarter of a warp per state in the matrix phase
-// rbq_fd_kernel: the chain phase is rbh_fd_kernel's (half a warp per state, run twice for the four staged states), but the
-// mass matrix is built and factorised by EIGHT lanes per state, four states per warp: lane (s, r) owns rows r, r + 8,
+// rbq_fd_kernel: the chain phase runs on 16 lanes per state (twice for the four staged states), the mass matrix is built
+// and factorised by EIGHT lanes per state, four states per warp: lane (s, r) owns rows r, r + 8,
 // r + 16, r + 24 of state s, lower triangle padded to the row group's width (8 + 16 + 24 + 32 = 80 register entries).
 // Against 16 lanes per state every broadcast load, every stored pivot column, every reciprocal and every shuffle of the
 // elimination now serves four states instead of two, and the rows of a lane are closer to the triangle (the FP64 work

@@ -256,7 +256,7 @@ def test_ragged_leading_dimension_rollout_and_kinematics(rb, oracle_fr3):
 
 
 def test_ragged_leading_dimension_long_chain_and_derivatives(rb, mb_fr3, mb_chain32, oracle_chain32):
-    """ld > n_states with NaN-poisoned padding through the lane-per-joint FD kernel (odd tail: half-warp pairs, staging
+    """ld > n_states with NaN-poisoned padding through the lane-per-joint FD kernel (odd tail: half- and quarter-warp state slots, staging
     groups) and the derivative kernels: results right, padding untouched."""
     import torch
     from rigidbody_rs_b200 import _lib
@@ -1009,7 +1009,7 @@ def test_cpp_example_runs(rb, tmp_path):
 
 def test_forward_dynamics_error_budget_against_mpmath_truth(rb, oracle_fr3, oracle_chain32):
     """Who owns the forward-dynamics error: a 40-digit mpmath solve (oracle/rb_oracle_np.py::fd_mp) is the truth, the
-    oracle's LL^T and the CUDA paths (in-register LDL^T with hardware-seeded reciprocals; half-warp elimination with
+    oracle's LL^T and the CUDA paths (in-register LDL^T with hardware-seeded reciprocals; quarter-warp elimination with
     world-frame sums for the 32-joint chain) are both measured against it.  Every path sits within
     conftest.fd_bound(cond) = max(1e-10, 8 cond(H) eps) -- in fact below 1e-12 (profiles/r2_error_budget.jsonl)."""
     from conftest import fd_bound, spd_cond
