@@ -523,6 +523,29 @@ def test_chain32_medium_batch(rb, mb_chain32, oracle_chain32):
     assert state_err(qt, oq, 1).max() < TOL and state_err(dqt, odq, 1).max() < TOL
 
 
+def test_long_chain_fd_is_independent_of_how_the_batch_is_cut(mb_chain32, oracle_chain32):
+    """rbq_fd_kernel walks the batch in sweeps of (SMs x 8 warps) groups of 4 states; a warp whose group does not exist
+    repeats the grid's last group and stores nothing, a state that does not exist is computed from zeros.  Whatever
+    the cut -- one call, two calls at an odd boundary, a tail of 1..3 states, a batch smaller than one sweep -- every
+    state's result is the same bits, and right."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    per_sweep = sms * 8 * 4                               # states one sweep of the grid covers
+    B = 2 * per_sweep + 4 + 3                             # two full sweeps, then one full group and a 3-state tail
+    o = oracle_chain32
+    q = o.fill(0x5EED0005, 0, -np.pi, np.pi, 0, B); dq = o.fill(0x5EED0005, 1, -2.0, 2.0, 0, B)
+    tau = o.fill(0x5EED0005, 3, -50.0, 50.0, 0, B)
+    whole = mb_chain32.forward_dynamics(q, dq, tau)
+    assert np.isfinite(whole).all()
+    for cut in (1, 5, per_sweep - 1, per_sweep + 2, B - 3, B - 1):
+        a = mb_chain32.forward_dynamics(np.ascontiguousarray(q[:, :cut]), np.ascontiguousarray(dq[:, :cut]), np.ascontiguousarray(tau[:, :cut]))
+        b = mb_chain32.forward_dynamics(np.ascontiguousarray(q[:, cut:]), np.ascontiguousarray(dq[:, cut:]), np.ascontiguousarray(tau[:, cut:]))
+        np.testing.assert_array_equal(np.concatenate([a, b], axis=1), whole, err_msg=f"cut at {cut}")
+    idx = np.r_[0:64, per_sweep - 32:per_sweep + 32, B - 40:B]
+    want = o.forward_dynamics_batch(np.ascontiguousarray(q[:, idx]), np.ascontiguousarray(dq[:, idx]), np.ascontiguousarray(tau[:, idx]))
+    assert state_err(whole[:, idx], want, 0).max() < TOL
+
+
 def test_jit_equals_ahead_of_time_build_bitwise(rb, oracle_fr3):
     """The FR3 kernels compiled at load time by NVRTC are the kernels nvcc compiled ahead of time: same bits out."""
     import torch
